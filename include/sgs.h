@@ -1,0 +1,182 @@
+/*
+ * sgs.h — C ABI of libsgs.so, the B200-native exact stabilizer-ground-state search.
+ *
+ * The reference (SUSYUSTC/stabilizer_gs) has NO FFI today: cpp/ and py/ are two independent
+ * implementations.  This header is the boundary a maintainer binds instead:
+ * every entry point names the reference interface it replaces (file:line under the reference
+ * root).  Plain C types only; no C++ / CUDA / torch types cross it.
+ *
+ * Conventions
+ *   - Packed Pauli rows: W = ceil(2n/64) little-endian u64 words per row, bit 2j = z_j,
+ *     bit 2j+1 = x_j (the reference's Pauli::array() column order, cpp/stab.cpp:194-199).
+ *   - Signs are +1 / -1 (int8_t); a term sign of 0 means "not in the group"
+ *     (Stab::energy, cpp/stab.cpp:579-587).
+ *   - Every function returns 0 on success or a negative SGS_ERR_* code; the message is
+ *     available from sgs_last_error() (thread-local).  No exception crosses the boundary.
+ *   - Ownership: the caller owns its inputs; result buffers are allocated by the library and
+ *     released with the matching *_free.  Handles are not thread-safe.
+ *   - There is NO CPU fallback: a search fails with SGS_ERR_NO_DEVICE when no CUDA device
+ *     is usable.
+ */
+#ifndef SGS_H
+#define SGS_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGS_OK 0
+#define SGS_ERR_IO (-1)          /* cannot read the Hamiltonian file                         */
+#define SGS_ERR_PARSE (-2)       /* malformed file (bad letter, letters/sites mismatch, ...) */
+#define SGS_ERR_ARG (-3)         /* invalid argument                                         */
+#define SGS_ERR_NO_DEVICE (-4)   /* no usable CUDA device (the product has no CPU path)      */
+#define SGS_ERR_CUDA (-5)        /* CUDA runtime error                                       */
+#define SGS_ERR_LIMIT (-6)       /* instance exceeds a compiled limit (n, T, rank)           */
+#define SGS_ERR_NCCL (-7)        /* NCCL error                                               */
+#define SGS_ERR_OVERFLOW (-8)    /* a device work queue overflowed                           */
+#define SGS_ERR_DEAD (-9)        /* the DP ended with no state                               */
+
+#define SGS_MAX_QUBITS 128       /* rows are at most 4 u64 words                             */
+#define SGS_MAX_RANK 64          /* rank histogram size - 1                                  */
+#define SGS_NCCL_ID_BYTES 128
+
+typedef struct sgs_ham sgs_ham;          /* opaque Hamiltonian handle                        */
+typedef struct sgs_klocal sgs_klocal;    /* opaque k-local DP machine (StateMachine)         */
+
+/* ---------------------------------------------------------------- Hamiltonian ---------- */
+
+/* Hamiltonian::from_file (cpp/state.cpp:58-81, py/state.py:34-49); periodic != 0 →
+ * Hamiltonian.from_file_periodic(path, cmax) (py/state.py:51-72). */
+int sgs_ham_load(const char *path, int periodic, int cmax, sgs_ham **out);
+/* same parser on an in-memory text (what from_file reads) */
+int sgs_ham_from_text(const char *text, int periodic, int cmax, sgs_ham **out);
+/* Hamiltonian(n,k) + add_Pauli (cpp/state.cpp:37-45,83-86) from packed arrays: zx is T x W,
+ * begin/end give each term's window [min site, max site + 1) (NULL → derived from the bits). */
+int sgs_ham_from_arrays(int n, int k, int T, const uint64_t *zx, const double *w,
+                        const int *begin, const int *end, sgs_ham **out);
+void sgs_ham_free(sgs_ham *h);
+int sgs_ham_n(const sgs_ham *h);
+int sgs_ham_k(const sgs_ham *h);
+int sgs_ham_l(const sgs_ham *h);         /* period of a periodic file, else 0                */
+int sgs_ham_nterms(const sgs_ham *h);
+int sgs_ham_words(const sgs_ham *h);     /* W                                                */
+/* original_paulis (file order): copies T x W words, T weights, T begins, T ends (any may be NULL) */
+int sgs_ham_terms(const sgs_ham *h, uint64_t *zx, double *w, int *begin, int *end);
+/* paulis_list order (cpp/state.cpp:88-96): order[i] = file index of the i-th term */
+int sgs_ham_order(const sgs_ham *h, int *order);
+
+/* ---------------------------------------------------------------- options / result ----- */
+
+typedef struct {
+    int device;              /* CUDA device ordinal of this process (default 0)                */
+    int ngpus;               /* single-process multi-GPU: use devices device..device+ngpus-1   */
+    int rank, world;         /* multi-process sharding: this process is shard `rank` of `world`
+                                (world <= 1 → no sharding).  Combined with ngpus: global shard
+                                = rank * ngpus + local gpu.                                    */
+    const void *nccl_id;     /* SGS_NCCL_ID_BYTES bytes from sgs_nccl_unique_id(), shared by all
+                                ranks, or NULL: with world > 1 and NULL the result is this
+                                shard's only (no collective).                                  */
+    int verbose;             /* klocal: -v level (cpp/klocal_sparse.cpp:10)                    */
+    int expand_depth;        /* sparse: force the prefix depth handed to the DFS kernel; 0=auto */
+    int reserved[8];
+} sgs_opts;
+void sgs_opts_default(sgs_opts *o);
+
+typedef struct {
+    double energy;               /* ground-state energy                                       */
+    int n, m, W, T;
+    uint64_t *gens;              /* m x W canonical generator rows (RREF, sorted by pivot)     */
+    int8_t *gen_signs;           /* m signs                                                    */
+    int8_t *term_signs;          /* T, file order (cpp/sparse.cpp:13-16)                       */
+    /* sparse search statistics */
+    uint64_t candidates;         /* closed commuting groups evaluated (= leaves of FullState's tree) */
+    uint64_t rank_hist[SGS_MAX_RANK + 1];
+    double sum_2m;               /* sum over candidates of 2^rank (signed candidates)          */
+    uint64_t slow_nodes;         /* candidates that needed the general (dependent-term) path   */
+    /* k-local statistics */
+    int nsites;
+    int *sright_counts;          /* n+1: "m count" lines of generate_Sright_all                */
+    int *states_per_site;        /* n+1: index 0 = initial states                              */
+    uint64_t transitions;        /* evolve_single calls                                        */
+    /* timing (seconds) */
+    double seconds_total;        /* wall, call entry → result on host                          */
+    double seconds_device;       /* CUDA-event time of the search kernels (max over local GPUs) */
+    double seconds_hot_kernel;   /* CUDA-event time of the dominant kernel                     */
+    uint32_t kernel_launches;    /* launches of this library's kernels during the call         */
+    int reserved[7];
+} sgs_result;
+void sgs_result_free(sgs_result *r);     /* frees the buffers inside *r (not r itself)        */
+
+/* ---------------------------------------------------------------- searches ------------- */
+
+/* FullState(paulis).evolve() (cpp/state.cpp:555-564,636-687; py/state.py:88-147) + the
+ * per-term signs of cpp/sparse.cpp:13-16.  Runs entirely on the GPU(s). */
+int sgs_sparse_search(const sgs_ham *h, const sgs_opts *opts, sgs_result *out);
+
+/* Device-resident variant for repeated searches: upload once, search many times. */
+typedef struct sgs_sparse_plan sgs_sparse_plan;
+int sgs_sparse_plan_create(const sgs_ham *h, const sgs_opts *opts, sgs_sparse_plan **out);
+int sgs_sparse_plan_run(sgs_sparse_plan *p, sgs_result *out);
+void sgs_sparse_plan_free(sgs_sparse_plan *p);
+
+/* StateMachine(H).evolve() until m == n, generate_gs(), get_stab_gs()
+ * (cpp/klocal_sparse.cpp:26-75, cpp/state.cpp:445-550). */
+int sgs_klocal_search(const sgs_ham *h, const sgs_opts *opts, sgs_result *out);
+
+/* Finer-grained DP handle for the periodic driver (py/klocal_periodic.py):
+ * generate_Sright_all / generate_Sright_periodic + StateMachine / StateMachinePeriodic. */
+int sgs_klocal_create(const sgs_ham *h, const sgs_opts *opts, int periodic_cmax, sgs_klocal **out);
+void sgs_klocal_free(sgs_klocal *k);
+int sgs_klocal_m(const sgs_klocal *k);                 /* StateMachine.m                          */
+int sgs_klocal_nstates(const sgs_klocal *k);           /* len(state_dict)                         */
+int sgs_klocal_sright_count(const sgs_klocal *k, int m);
+int sgs_klocal_evolve(sgs_klocal *k);                  /* StateMachine::evolve, one site          */
+int sgs_klocal_ground_state(sgs_klocal *k, sgs_result *out);   /* generate_gs + get_stab_gs      */
+
+/* py/klocal_periodic.py:1-63 as one call: orbits of the infinite periodic chain */
+typedef struct {
+    double energy;          /* energy over c periods                                          */
+    int begin, end, m;      /* window and number of generators                                */
+    uint64_t *gens;         /* m x W rows (history order, NOT canonicalised: return_stab=False) */
+    int8_t *signs;          /* m                                                               */
+} sgs_orbit;
+typedef struct {
+    int l, k, n, W, nterms;
+    int nlog; int *sright_log;        /* (m, count) pairs printed by generate_Sright_periodic     */
+    int nfixed; int *fixed_sizes;     /* sizes printed while the state set converges              */
+    int norbits; sgs_orbit *orbits;   /* sorted by (energy, begin, end, generators)               */
+    double seconds_total;
+} sgs_periodic_result;
+int sgs_klocal_periodic(const char *path, int cmax, int c, const sgs_opts *opts, sgs_periodic_result *out);
+void sgs_periodic_result_free(sgs_periodic_result *r);
+
+/* ---------------------------------------------------------------- group utilities ------ */
+/* The Python classes the reference scripts touch (py/stab.py StabilizerGroup) are thin shims
+ * over these; all of them run as CUDA kernels on `device`. */
+
+/* StabilizerGroup(Ps) canonicalisation (py/stab.py:45-51, cpp/stab.cpp:437-449): rows/signs are
+ * overwritten with the canonical generators; *rank receives their number. */
+int sgs_group_canonicalize(int device, int n, int m, uint64_t *rows, int8_t *signs, int *rank);
+/* StabilizerGroup.get_energy(P) / Stab::energy for a batch of B Paulis (py/stab.py:147-153):
+ * out[i] = 0 if P_i is not in ±S, else the relative sign. */
+int sgs_group_energy(int device, int n, int m, const uint64_t *rows, const int8_t *signs,
+                     int B, const uint64_t *P, const int8_t *Psigns, int8_t *out);
+/* Pauli::commute for B pairs (cpp/stab.cpp:314-318): out[i] = 1 if a_i and b_i commute */
+int sgs_pauli_commute(int device, int n, int B, const uint64_t *a, const uint64_t *b, uint8_t *out);
+
+/* ---------------------------------------------------------------- multi-GPU ------------ */
+int sgs_nccl_unique_id(void *id_out /* SGS_NCCL_ID_BYTES */);
+int sgs_device_count(void);
+
+/* ---------------------------------------------------------------- misc ----------------- */
+const char *sgs_last_error(void);
+const char *sgs_version(void);
+/* integer-pipe issue-rate microbenchmarks (roofline denominators):
+ * 32-bit LOP3 and POPC ops per second over the whole chip at the running clock */
+int sgs_measure_int_peaks(int device, double *lop3_ops_per_s, double *popc_ops_per_s, double *sm_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

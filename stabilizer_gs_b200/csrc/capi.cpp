@@ -1,0 +1,282 @@
+// capi.cpp — the extern "C" boundary declared in include/sgs.h.  No exception crosses it.
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "common.hpp"
+#include "group_ops.hpp"
+#include "hamiltonian.hpp"
+#include "klocal_search.hpp"
+#include "nccl_glue.hpp"
+#include "sparse_search.hpp"
+
+using namespace sgs;
+
+struct sgs_ham { Hamiltonian H; };
+struct sgs_sparse_plan { std::unique_ptr<SparsePlan> plan; };
+struct sgs_klocal { std::unique_ptr<KlocalMachine> M; };
+
+static int fail(int code, const std::string &msg) { set_last_error(msg); return code; }
+static int done(const Status &s) { if (!s.ok()) set_last_error(s.msg); return s.code; }
+
+#define SGS_GUARD_BEGIN try {
+#define SGS_GUARD_END                                                                       \
+    } catch (const std::bad_alloc &) { return fail(SGS_ERR_LIMIT, "out of host memory"); } \
+    catch (const std::exception &e) { return fail(SGS_ERR_ARG, e.what()); }                \
+    catch (...) { return fail(SGS_ERR_ARG, "unknown error"); }
+
+extern "C" {
+
+const char *sgs_last_error(void) { return get_last_error(); }
+const char *sgs_version(void) { return "stabilizer_gs_b200 0.1 (sm_100a)"; }
+
+void sgs_opts_default(sgs_opts *o)
+{
+    memset(o, 0, sizeof(*o));
+    o->ngpus = 1;
+    o->world = 1;
+}
+
+int sgs_ham_load(const char *path, int periodic, int cmax, sgs_ham **out)
+{
+    SGS_GUARD_BEGIN
+    if (!path || !out) return fail(SGS_ERR_ARG, "null argument");
+    std::unique_ptr<sgs_ham> h(new sgs_ham());
+    ParseError err;
+    if (!load_hamiltonian_file(path, periodic != 0, cmax, h->H, err)) return fail(err.code, err.msg);
+    *out = h.release();
+    return SGS_OK;
+    SGS_GUARD_END
+}
+
+int sgs_ham_from_text(const char *text, int periodic, int cmax, sgs_ham **out)
+{
+    SGS_GUARD_BEGIN
+    if (!text || !out) return fail(SGS_ERR_ARG, "null argument");
+    std::unique_ptr<sgs_ham> h(new sgs_ham());
+    ParseError err;
+    if (!parse_hamiltonian_text(text, periodic != 0, cmax, h->H, err)) return fail(err.code, err.msg);
+    *out = h.release();
+    return SGS_OK;
+    SGS_GUARD_END
+}
+
+int sgs_ham_from_arrays(int n, int k, int T, const uint64_t *zx, const double *w, const int *begin, const int *end,
+                        sgs_ham **out)
+{
+    SGS_GUARD_BEGIN
+    if (!out || (T > 0 && (!zx || !w))) return fail(SGS_ERR_ARG, "null argument");
+    if (n <= 0 || n + 1 > SGS_MAX_QUBITS || k <= 0 || T < 0) return fail(SGS_ERR_ARG, "n, k or T out of range");
+    std::unique_ptr<sgs_ham> h(new sgs_ham());
+    h->H.n = n; h->H.k = k;
+    const int W = (2 * n + 63) / 64;
+    for (int t = 0; t < T; t++) {
+        PackedRow r;
+        for (int i = 0; i < W; i++) r.w[i] = zx[(size_t)t * W + i];
+        int b = n, e = 0;
+        for (int j = 0; j < n; j++)
+            if ((r.w[(2 * j) >> 6] >> ((2 * j) & 63)) & 3) { if (j < b) b = j; e = j + 1; }
+        if (2 * n < 64 * W) {
+            // bits beyond qubit n-1 are not part of the Hamiltonian
+            for (int bit = 2 * n; bit < 64 * W; bit++) if ((r.w[bit >> 6] >> (bit & 63)) & 1) return fail(SGS_ERR_ARG, "term has bits beyond qubit n-1");
+        }
+        if (begin && end) { b = begin[t]; e = end[t]; }
+        if (e <= b) { b = 0; e = 1; }     // identity string: window [0,1)
+        if (b < 0 || e > n) return fail(SGS_ERR_ARG, "term window out of range");
+        h->H.add_term(r, w[t], b, e);
+    }
+    h->H.finalize();
+    *out = h.release();
+    return SGS_OK;
+    SGS_GUARD_END
+}
+
+void sgs_ham_free(sgs_ham *h) { delete h; }
+int sgs_ham_n(const sgs_ham *h) { return h ? h->H.n : 0; }
+int sgs_ham_k(const sgs_ham *h) { return h ? h->H.k : 0; }
+int sgs_ham_l(const sgs_ham *h) { return h ? h->H.l : 0; }
+int sgs_ham_nterms(const sgs_ham *h) { return h ? h->H.T() : 0; }
+int sgs_ham_words(const sgs_ham *h) { return h ? (2 * h->H.n + 63) / 64 : 0; }
+
+int sgs_ham_terms(const sgs_ham *h, uint64_t *zx, double *w, int *begin, int *end)
+{
+    if (!h) return fail(SGS_ERR_ARG, "null handle");
+    const int W = (2 * h->H.n + 63) / 64;
+    for (int t = 0; t < h->H.T(); t++) {
+        if (zx) for (int i = 0; i < W; i++) zx[(size_t)t * W + i] = h->H.terms[t].w[i];
+        if (w) w[t] = h->H.weights[t];
+        if (begin) begin[t] = h->H.begin[t];
+        if (end) end[t] = h->H.end[t];
+    }
+    return SGS_OK;
+}
+
+int sgs_ham_order(const sgs_ham *h, int *order)
+{
+    if (!h || !order) return fail(SGS_ERR_ARG, "null argument");
+    for (int t = 0; t < h->H.T(); t++) order[t] = h->H.order[t];
+    return SGS_OK;
+}
+
+void sgs_result_free(sgs_result *r)
+{
+    if (!r) return;
+    free(r->gens); free(r->gen_signs); free(r->term_signs); free(r->sright_counts); free(r->states_per_site);
+    r->gens = nullptr; r->gen_signs = r->term_signs = nullptr; r->sright_counts = r->states_per_site = nullptr;
+}
+
+int sgs_sparse_plan_create(const sgs_ham *h, const sgs_opts *opts, sgs_sparse_plan **out)
+{
+    SGS_GUARD_BEGIN
+    if (!h || !out) return fail(SGS_ERR_ARG, "null argument");
+    sgs_opts o;
+    if (opts) o = *opts; else sgs_opts_default(&o);
+    std::unique_ptr<sgs_sparse_plan> p(new sgs_sparse_plan());
+    Status s = SparsePlan::create(h->H, o, p->plan);
+    if (!s.ok()) return done(s);
+    *out = p.release();
+    return SGS_OK;
+    SGS_GUARD_END
+}
+
+int sgs_sparse_plan_run(sgs_sparse_plan *p, sgs_result *out)
+{
+    SGS_GUARD_BEGIN
+    if (!p || !out) return fail(SGS_ERR_ARG, "null argument");
+    Status s = p->plan->run(out);
+    if (!s.ok()) sgs_result_free(out);
+    return done(s);
+    SGS_GUARD_END
+}
+
+void sgs_sparse_plan_free(sgs_sparse_plan *p) { delete p; }
+
+int sgs_sparse_search(const sgs_ham *h, const sgs_opts *opts, sgs_result *out)
+{
+    sgs_sparse_plan *p = nullptr;
+    int rc = sgs_sparse_plan_create(h, opts, &p);
+    if (rc != SGS_OK) return rc;
+    rc = sgs_sparse_plan_run(p, out);
+    sgs_sparse_plan_free(p);
+    return rc;
+}
+
+int sgs_klocal_create(const sgs_ham *h, const sgs_opts *opts, int periodic_cmax, sgs_klocal **out)
+{
+    SGS_GUARD_BEGIN
+    if (!h || !out) return fail(SGS_ERR_ARG, "null argument");
+    sgs_opts o;
+    if (opts) o = *opts; else sgs_opts_default(&o);
+    std::unique_ptr<sgs_klocal> k(new sgs_klocal());
+    Status s = KlocalMachine::create(h->H, o, periodic_cmax, k->M);
+    if (!s.ok()) return done(s);
+    *out = k.release();
+    return SGS_OK;
+    SGS_GUARD_END
+}
+
+void sgs_klocal_free(sgs_klocal *k) { delete k; }
+int sgs_klocal_m(const sgs_klocal *k) { return k ? k->M->m() : 0; }
+int sgs_klocal_nstates(const sgs_klocal *k) { return k ? k->M->nstates() : 0; }
+int sgs_klocal_sright_count(const sgs_klocal *k, int m) { return k ? k->M->sright_count(m) : 0; }
+
+int sgs_klocal_evolve(sgs_klocal *k)
+{
+    SGS_GUARD_BEGIN
+    if (!k) return fail(SGS_ERR_ARG, "null handle");
+    return done(k->M->evolve());
+    SGS_GUARD_END
+}
+
+int sgs_klocal_ground_state(sgs_klocal *k, sgs_result *out)
+{
+    SGS_GUARD_BEGIN
+    if (!k || !out) return fail(SGS_ERR_ARG, "null argument");
+    memset(out, 0, sizeof(*out));
+    Status s = k->M->ground_state(out);
+    if (!s.ok()) sgs_result_free(out);
+    return done(s);
+    SGS_GUARD_END
+}
+
+int sgs_klocal_search(const sgs_ham *h, const sgs_opts *opts, sgs_result *out)
+{
+    SGS_GUARD_BEGIN
+    if (!h || !out) return fail(SGS_ERR_ARG, "null argument");
+    sgs_opts o;
+    if (opts) o = *opts; else sgs_opts_default(&o);
+    memset(out, 0, sizeof(*out));
+    Status s = klocal_search(h->H, o, out);
+    if (!s.ok()) sgs_result_free(out);
+    return done(s);
+    SGS_GUARD_END
+}
+
+int sgs_klocal_periodic(const char *path, int cmax, int c, const sgs_opts *opts, sgs_periodic_result *out)
+{
+    SGS_GUARD_BEGIN
+    if (!path || !out) return fail(SGS_ERR_ARG, "null argument");
+    sgs_opts o;
+    if (opts) o = *opts; else sgs_opts_default(&o);
+    memset(out, 0, sizeof(*out));
+    Hamiltonian H;
+    ParseError err;
+    if (!load_hamiltonian_file(path, true, cmax, H, err)) return fail(err.code, err.msg);
+    Status s = klocal_periodic(H, cmax, c, o, out);
+    if (!s.ok()) sgs_periodic_result_free(out);
+    return done(s);
+    SGS_GUARD_END
+}
+
+void sgs_periodic_result_free(sgs_periodic_result *r)
+{
+    if (!r) return;
+    for (int i = 0; i < r->norbits; i++) { free(r->orbits[i].gens); free(r->orbits[i].signs); }
+    free(r->orbits); free(r->sright_log); free(r->fixed_sizes);
+    r->orbits = nullptr; r->sright_log = r->fixed_sizes = nullptr; r->norbits = r->nlog = r->nfixed = 0;
+}
+
+int sgs_group_canonicalize(int device, int n, int m, uint64_t *rows, int8_t *signs, int *rank)
+{
+    SGS_GUARD_BEGIN
+    if (!rows || !signs || !rank || n <= 0 || n > SGS_MAX_QUBITS || m < 0) return fail(SGS_ERR_ARG, "invalid argument");
+    return done(group_canonicalize(device, n, m, rows, signs, rank));
+    SGS_GUARD_END
+}
+
+int sgs_group_energy(int device, int n, int m, const uint64_t *rows, const int8_t *signs, int B, const uint64_t *P,
+                     const int8_t *Psigns, int8_t *out)
+{
+    SGS_GUARD_BEGIN
+    if ((m > 0 && (!rows || !signs)) || (B > 0 && (!P || !out)) || n <= 0 || n > SGS_MAX_QUBITS) return fail(SGS_ERR_ARG, "invalid argument");
+    return done(group_energy(device, n, m, rows, signs, B, P, Psigns, out));
+    SGS_GUARD_END
+}
+
+int sgs_pauli_commute(int device, int n, int B, const uint64_t *a, const uint64_t *b, uint8_t *out)
+{
+    SGS_GUARD_BEGIN
+    if (B > 0 && (!a || !b || !out)) return fail(SGS_ERR_ARG, "invalid argument");
+    return done(pauli_commute_batch(device, n, B, a, b, out));
+    SGS_GUARD_END
+}
+
+int sgs_nccl_unique_id(void *id_out)
+{
+    SGS_GUARD_BEGIN
+    if (!id_out) return fail(SGS_ERR_ARG, "null argument");
+    return done(NcclWorld::unique_id(id_out));
+    SGS_GUARD_END
+}
+
+int sgs_device_count(void) { return device_count(); }
+
+int sgs_measure_int_peaks(int device, double *lop3, double *popc, double *sm_mhz)
+{
+    SGS_GUARD_BEGIN
+    return done(measure_int_peaks(device, lop3, popc, sm_mhz));
+    SGS_GUARD_END
+}
+
+}  // extern "C"

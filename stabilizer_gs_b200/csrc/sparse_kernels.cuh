@@ -1,0 +1,851 @@
+// sparse_kernels.cuh — sm_100a kernels of the sparse exact stabilizer-ground-state search.
+//
+// What they replace (reference): FullState::{include_pauli, exclude_pauli, evolve}
+// (cpp/state.cpp:578-687) together with everything they call — Pauli::commute/dot (cpp/stab.cpp:314-345),
+// Stab::canonicalize/decompose/include (cpp/stab.cpp:437-511), linear::Gauss_elimination/solve_modN
+// (cpp/linear.cpp:21-121) and the StabEnergies sign tables (cpp/stab.cpp:667-843).
+//
+// Design (not a port):
+//   The reference's include/exclude tree has one leaf per closed commuting group (= distinct GF(2) span
+//   of a pairwise-commuting subset of terms).  We enumerate exactly those groups, each once, by
+//   prefix-preserving closure extension: a group G with canonical generating terms g_1 < ... < g_m
+//   (g_i = lowest-index term of G outside <g_1..g_{i-1}>) is extended by a term j > g_m that commutes
+//   with G, lies outside G, and whose coset j*G contains no lower-index term.
+//
+//   k_adjacency : T x T commutation bit-matrix (POPC of a & swapzx(b)).
+//   k_general   : one warp evaluates ONE group from scratch, for any input: echelon basis with phase
+//                 and coefficient tracking, membership/sign of every commuting term, exact minimum over
+//                 generator signs, valid children.  Used for the top levels of the tree (work-item
+//                 generation) and as the exact path for groups that contain linearly dependent terms.
+//   k_dfs       : the hot kernel.  Persistent warps pull subtree roots from a queue and walk them
+//                 depth-first; a tree level is a compacted list (residue mod G, term index) of the terms
+//                 still commuting with G, one lane per term, kept in shared memory.  A child costs one
+//                 pass over the parent's list: POPC commutation test, conditional XOR with the new
+//                 generator's residue at its pivot bit, __ballot_sync compaction, __match_any_sync
+//                 duplicate-residue detection.  While residues stay pairwise distinct no term outside
+//                 the generating set can enter the group, so E_min = -sum |w_g| exactly; the first
+//                 duplicate hands that node to k_general.
+//   k_reduce_best / k_finalize : deterministic argmin over per-warp records, then canonical RREF with
+//                 sign tracking, per-term signs and the reference's first-minimum sign pattern.
+#pragma once
+#include <cstdint>
+
+#include "packed.cuh"
+
+namespace sgs {
+
+constexpr int kMaxG = 64;            // max rank (generators per group) in the sparse search
+constexpr int kMaxFrames = kMaxG + 1;
+constexpr int kCapM = 256;           // max non-trivial (dependent) members of one group in k_general
+constexpr int kMaxBrute = 26;        // max entangled sign variables minimised by enumeration
+constexpr unsigned kFlagUnclean = 1; // node has members outside its generating set
+constexpr unsigned kFlagExpandOnly = 2;   // already counted and evaluated: only emit children
+
+struct BestRec {
+    double E;
+    int m;
+    int valid;
+    uint16_t g[kMaxG];
+};
+
+struct SparseStats {
+    unsigned long long hist[kMaxG + 1];   // candidates per rank
+    unsigned long long slow_nodes;        // candidates evaluated by k_general
+    unsigned int error;                   // SGS_ERR_* (positive) set by a kernel
+    unsigned int pad;
+};
+
+struct SparseDev {
+    int n, T, TW, S;             // TW = ceil(T/64); S = node record stride in u16 (2 + max rank)
+    const uint64_t *rows;        // [T * W] terms in paulis_list order
+    const double *wgt;           // [T]
+    const double *wabs;          // [T]
+    const uint64_t *adj;         // [T * TW] commutation bit-matrix (diagonal 0)
+    BestRec *wbest;              // per-warp best records
+    SparseStats *stats;
+    uint16_t *slow;              // work stack of nodes needing k_general
+    unsigned int *slow_count;
+    unsigned int slow_cap;
+};
+
+enum { kErrOverflow = 8, kErrLimit = 6 };
+
+SGS_D uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+// lexicographic order on generating tuples with "end of tuple" sorting last: the order in which the
+// reference's include-first tree lists its leaves (tie-break).
+SGS_D bool tuple_before(const uint16_t *a, int na, const uint16_t *b, int nb)
+{
+    for (int i = 0;; i++) {
+        if (i == na) return false;
+        if (i == nb) return true;
+        if (a[i] != b[i]) return a[i] < b[i];
+    }
+}
+
+SGS_D uint32_t tuple_hash(const uint16_t *g, int m)
+{
+    uint32_t h = 2166136261u;
+    for (int i = 0; i < m; i++) { h ^= g[i]; h *= 16777619u; }
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: commutation bit-matrix.  One thread per (term i, 64-term word).
+template <int W>
+__global__ void k_adjacency(int T, int TW, const uint64_t *__restrict__ rows, uint64_t *__restrict__ adj)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T * TW) return;
+    int i = idx / TW, wj = idx % TW;
+    uint64_t sw[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) sw[k] = swapzx(rows[(size_t)i * W + k]);
+    uint64_t bits = 0;
+    for (int b = 0; b < 64; b++) {
+        int j = wj * 64 + b;
+        if (j >= T) break;
+        if (j == i) continue;
+        if (!row_anticommute_sw<W>(rows + (size_t)j * W, sw)) bits |= 1ULL << b;
+    }
+    adj[idx] = bits;
+}
+
+// push one node record onto the slow work stack (warp-uniform call)
+SGS_D void push_slow(const SparseDev &D, const uint16_t *g, int m, unsigned flags, int lane)
+{
+    unsigned slot = 0;
+    if (lane == 0) slot = atomicAdd(D.slow_count, 1u);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= D.slow_cap) {
+        if (lane == 0) atomicMax(&D.stats->error, (unsigned)kErrOverflow);
+        return;
+    }
+    uint16_t *rec = D.slow + (size_t)slot * D.S;
+    if (lane == 0) { rec[0] = (uint16_t)m; rec[1] = (uint16_t)flags; }
+    for (int i = lane; i < m; i += 32) rec[2 + i] = g[i];
+}
+
+// alive terms of the group generated by g[0..m): bitset AND of adjacency rows, compacted into tt[]
+// (ascending term index).  Returns the count, or -1 if it exceeds cap.
+SGS_D int alive_list(const SparseDev &D, const uint16_t *g, int m, uint16_t *tt, int cap, int lane)
+{
+    int total = 0;
+    for (int w0 = 0; w0 < D.TW; w0 += 32) {
+        int w = w0 + lane;
+        uint64_t a = 0;
+        if (w < D.TW) {
+            a = ~0ULL;
+            int rem = D.T - w * 64;
+            if (rem < 64) a = (1ULL << rem) - 1;
+            for (int i = 0; i < m; i++) a &= D.adj[(size_t)g[i] * D.TW + w];
+        }
+        int c = popc64(a), inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        int off = total + inc - c;
+        int tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (total + tot > cap) return -1;
+        while (a) {
+            int b = ctz64(a);
+            a &= a - 1;
+            tt[off++] = (uint16_t)(w * 64 + b);
+        }
+        total += tot;
+    }
+    __syncwarp();
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_general: exact from-scratch evaluation of one closed commuting group per warp.
+// smem per warp (bytes): see general_smem_bytes().
+template <int W>
+__host__ __device__ inline size_t general_smem_bytes(int T)
+{
+    size_t b = 0;
+    b += (size_t)kMaxG * W * 8;      // basis rows
+    b += (size_t)kMaxG * 8;          // basis coefficient masks
+    b += (size_t)kMaxG * 8;          // lin[]
+    b += (size_t)T * W * 8;          // alive residues
+    b += (size_t)kCapM * 8 * 2;      // extras: mask, weight
+    b += (size_t)kCapM * 4;          // extras: compressed mask
+    b += (size_t)((T + 3) / 4) * 8;  // alive term indices (u16)
+    b += kMaxG * 2 + 64;             // pivots, phases, vpos
+    b += kMaxG * 2;                  // best tuple
+    b += (kMaxG + 1) * 4 + 4;        // hist
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int W>
+__global__ void __launch_bounds__(128)
+k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *__restrict__ out,
+          unsigned int *out_count, unsigned out_cap, int shard, int nshards, int smem_per_warp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int T = D.T;
+    unsigned char *p = smem_raw + (size_t)warp * smem_per_warp;
+    uint64_t *B = (uint64_t *)p;            p += (size_t)kMaxG * W * 8;
+    uint64_t *cB = (uint64_t *)p;           p += (size_t)kMaxG * 8;
+    double *lin = (double *)p;              p += (size_t)kMaxG * 8;
+    uint64_t *R = (uint64_t *)p;            p += (size_t)T * W * 8;
+    uint64_t *exC = (uint64_t *)p;          p += (size_t)kCapM * 8;
+    double *exA = (double *)p;              p += (size_t)kCapM * 8;
+    uint32_t *exV = (uint32_t *)p;          p += (size_t)kCapM * 4;
+    uint16_t *tt = (uint16_t *)p;           p += (size_t)((T + 3) / 4) * 8;
+    uint8_t *pivB = (uint8_t *)p;           p += kMaxG;
+    uint8_t *qB = (uint8_t *)p;             p += kMaxG;
+    uint8_t *vpos = (uint8_t *)p;           p += 64;
+    uint16_t *bestG = (uint16_t *)p;        p += kMaxG * 2;
+    uint32_t *hist = (uint32_t *)p;
+
+    const unsigned gw = blockIdx.x * wpb + warp, nw = gridDim.x * wpb;
+    BestRec *myrec = D.wbest + gw;
+    double bestE = myrec->valid ? myrec->E : 1e300;
+    int bestM = myrec->valid ? myrec->m : 0;
+    int haveBest = myrec->valid;
+    for (int i = lane; i < bestM; i += 32) bestG[i] = myrec->g[i];
+    for (int i = lane; i <= kMaxG; i += 32) hist[i] = 0;
+    unsigned slowNodes = 0;
+    __syncwarp();
+
+    for (unsigned node = gw; node < nin; node += nw) {
+        const uint16_t *rec = in + (size_t)node * D.S;
+        const int m = rec[0];
+        const unsigned flags = rec[1];
+        const uint16_t *g = rec + 2;
+        const bool mine = nshards <= 1 || (int)(tuple_hash(g, m) % (unsigned)nshards) == shard;
+
+        // ---- 1. echelon basis of the generators with phase and coefficient tracking (K1) ----
+        // basis[i] = exact operator product of the generator terms selected by cB[i]; pivot = its
+        // lowest set bit; later basis rows are clear at every earlier pivot.
+        for (int i = 0; i < m; i++) {
+            uint64_t v[W];
+            const int t = g[i];
+#pragma unroll
+            for (int k = 0; k < W; k++) v[k] = D.rows[(size_t)t * W + k];
+            int q = row_plus_phase<W>(v);
+            uint64_t c = 1ULL << i;
+            for (int b = 0; b < i; b++) {
+                if (row_bit<W>(v, pivB[b])) {
+                    uint64_t bb[W];
+#pragma unroll
+                    for (int k = 0; k < W; k++) bb[k] = B[b * W + k];
+                    row_mul<W>(v, q, bb, qB[b]);
+                    c ^= cB[b];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < W; k++) B[i * W + k] = v[k];
+                cB[i] = c;
+                qB[i] = (uint8_t)q;
+                pivB[i] = (uint8_t)row_lowbit<W>(v);
+                lin[i] = D.wgt[t];
+            }
+            __syncwarp();
+        }
+
+        // ---- 2. terms commuting with every generator (K3, via the adjacency bitsets) ----
+        int na = alive_list(D, g, m, tt, T, lane);
+
+        // ---- 3. reduce each one modulo the group (K2): member (with sign) or alive residue ----
+        double cst = 0.0;
+        int ne = 0, nkeep = 0;
+        bool overflow = false;
+        for (int i0 = 0; i0 < na; i0 += 32) {
+            const int i = i0 + lane;
+            uint64_t v[W];
+            int q = 0, t = 0;
+            uint64_t c = 0;
+            bool act = i < na;
+            if (act) {
+                t = tt[i];
+#pragma unroll
+                for (int k = 0; k < W; k++) v[k] = D.rows[(size_t)t * W + k];
+                q = row_plus_phase<W>(v);
+                for (int b = 0; b < m; b++) {
+                    if (row_bit<W>(v, pivB[b])) {
+                        uint64_t bb[W];
+#pragma unroll
+                        for (int k = 0; k < W; k++) bb[k] = B[b * W + k];
+                        row_mul<W>(v, q, bb, qB[b]);
+                        c ^= cB[b];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < W; k++) v[k] = 1;
+            }
+            const bool member = act && row_is_zero<W>(v);
+            const bool keep = act && !member;
+            // P_t * prod(used basis rows) = i^q * I with q in {0,2}: P_t = (-1)^{q/2} * prod_{k in c} P_{g_k}
+            const double a = member ? ((q & 2) ? -D.wgt[t] : D.wgt[t]) : 0.0;
+            unsigned mb = __ballot_sync(0xffffffffu, member);
+            while (mb) {                                   // deterministic (term) order
+                const int src = __ffs(mb) - 1;
+                mb &= mb - 1;
+                const uint64_t cc = __shfl_sync(0xffffffffu, c, src);
+                const double aa = __shfl_sync(0xffffffffu, a, src);
+                const int pc = popc64(cc);
+                if (pc == 0) cst += aa;
+                else if (pc == 1) { if (lane == 0) lin[ctz64(cc)] += aa; }
+                else {
+                    if (ne < kCapM) { if (lane == 0) { exC[ne] = cc; exA[ne] = aa; } }
+                    else overflow = true;
+                    ne++;
+                }
+                __syncwarp();
+            }
+            const unsigned kb = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) {
+                const int pos = nkeep + __popc(kb & lanemask_lt());
+#pragma unroll
+                for (int k = 0; k < W; k++) R[(size_t)pos * W + k] = v[k];
+                tt[pos] = (uint16_t)t;
+            }
+            nkeep += __popc(kb);
+            __syncwarp();
+        }
+        const int nmem = na - nkeep;
+        na = nkeep;
+        if (overflow) { if (lane == 0) atomicMax(&D.stats->error, (unsigned)kErrLimit); continue; }
+
+        // ---- 4. exact minimum over generator signs (K5) ----
+        // E(s) = cst + sum_k lin[k] s_k + sum_e exA[e] prod_{k in exC[e]} s_k, s_k = sign of generator term k.
+        // Variables outside V = union of the extras' supports minimise independently.
+        if (!(flags & kFlagExpandOnly)) {
+            uint64_t V = 0;
+            for (int e = 0; e < ne; e++) V |= exC[e];
+            double E = cst;
+            for (int k = 0; k < m; k++) if (!((V >> k) & 1)) E -= fabs(lin[k]);
+            const int nv = popc64(V);
+            if (nv > kMaxBrute) { if (lane == 0) atomicMax(&D.stats->error, (unsigned)kErrLimit); continue; }
+            if (nv > 0) {
+                if (lane == 0) {
+                    int j = 0;
+                    for (int k = 0; k < m; k++) if ((V >> k) & 1) vpos[j++] = (uint8_t)k;
+                    for (int e = 0; e < ne; e++) {
+                        uint32_t cv = 0;
+                        for (int jj = 0; jj < nv; jj++) if ((exC[e] >> vpos[jj]) & 1) cv |= 1u << jj;
+                        exV[e] = cv;
+                    }
+                }
+                __syncwarp();
+                double mn = 1e300;
+                for (uint32_t pat = lane; pat < (1u << nv); pat += 32) {
+                    double val = 0.0;
+                    for (int jj = 0; jj < nv; jj++) val += ((pat >> jj) & 1) ? -lin[vpos[jj]] : lin[vpos[jj]];
+                    for (int e = 0; e < ne; e++) val += (__popc(pat & exV[e]) & 1) ? -exA[e] : exA[e];
+                    mn = fmin(mn, val);
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+                E += mn;
+            }
+            if (mine) {
+                if (lane == 0) hist[m]++;
+                slowNodes++;
+                if (!haveBest || E < bestE || (E == bestE && tuple_before(g, m, bestG, bestM))) {
+                    haveBest = 1; bestE = E; bestM = m;
+                    __syncwarp();
+                    for (int i = lane; i < m; i += 32) bestG[i] = g[i];
+                    __syncwarp();
+                }
+            }
+        }
+
+        // ---- 5. children: alive terms above the core whose coset holds no lower-index term ----
+        const int core = m ? (int)g[m - 1] : -1;
+        const bool parentUnclean = (flags & kFlagUnclean) || nmem > 0;
+        for (int i0 = 0; i0 < na; i0 += 32) {
+            const int i = i0 + lane;
+            bool valid = false, higher = false;
+            if (i < na && (int)tt[i] > core) {
+                uint64_t mineR[W];
+#pragma unroll
+                for (int k = 0; k < W; k++) mineR[k] = R[(size_t)i * W + k];
+                bool lower = false;
+                for (int e = 0; e < na; e++) {
+                    if (e == i) continue;
+                    if (row_equal<W>(R + (size_t)e * W, mineR)) { if (e < i) lower = true; else higher = true; }
+                }
+                valid = !lower;
+            }
+            const unsigned vb = __ballot_sync(0xffffffffu, valid);
+            if (vb == 0) continue;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(out_count, (unsigned)__popc(vb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + __popc(vb) > out_cap) {
+                if (lane == 0) atomicMax(&D.stats->error, (unsigned)kErrOverflow);
+                continue;
+            }
+            if (valid) {
+                uint16_t *o = out + (size_t)(base + __popc(vb & lanemask_lt())) * D.S;
+                o[0] = (uint16_t)(m + 1);
+                o[1] = (uint16_t)((parentUnclean || higher) ? kFlagUnclean : 0);
+                for (int k = 0; k < m; k++) o[2 + k] = g[k];
+                o[2 + m] = tt[i];
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- write back the warp's best record and statistics ----
+    __syncwarp();
+    if (haveBest) {
+        if (lane == 0) { myrec->E = bestE; myrec->m = bestM; myrec->valid = 1; }
+        for (int i = lane; i < bestM; i += 32) myrec->g[i] = bestG[i];
+    }
+    for (int i = lane; i <= kMaxG; i += 32)
+        if (hist[i]) atomicAdd(&D.stats->hist[i], (unsigned long long)hist[i]);
+    if (lane == 0 && slowNodes) atomicAdd(&D.stats->slow_nodes, (unsigned long long)slowNodes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_dfs: the hot kernel.
+template <int W>
+__host__ __device__ inline size_t dfs_smem_bytes(int cap)
+{
+    size_t b = 0;
+    b += (size_t)cap * W * 8;          // residues
+    b += (size_t)kMaxG * W * 8;        // basis (subtree-root setup)
+    b += (size_t)kMaxFrames * 8;       // frame E
+    b += (size_t)kMaxFrames * 4 * 3;   // frame base, a, q
+    b += (size_t)(kMaxG + 1) * 4 + 4;  // hist
+    b += (size_t)cap * 2;              // term indices
+    b += (size_t)kMaxG * 2 * 2;        // path, best tuple
+    b += kMaxG;                        // pivots
+    return (b + 15) & ~(size_t)15;
+}
+
+// any two equal residues among R[0..n)?  (no zero residue can occur: see the caller)
+template <int W>
+SGS_D bool has_duplicate(const uint64_t *R, int n, int lane)
+{
+    if (n <= 32) {
+        bool dup = false;
+        if (lane < n) {
+            const unsigned mask = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+            unsigned mm = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < W; k++) mm &= __match_any_sync(mask, R[(size_t)lane * W + k]);
+            dup = (mm & (mm - 1)) != 0;
+        }
+        return __any_sync(0xffffffffu, dup);
+    }
+    bool dup = false;
+    for (int e = 0; e + 1 < n; e++) {
+        uint64_t ref[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) ref[k] = R[(size_t)e * W + k];
+        for (int i = e + 1 + lane; i < n; i += 32) dup |= row_equal<W>(R + (size_t)i * W, ref);
+    }
+    return __any_sync(0xffffffffu, dup);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned int *item_counter,
+      int shard, int nshards, int cap, int smem_per_warp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    unsigned char *p = smem_raw + (size_t)warp * smem_per_warp;
+    uint64_t *R = (uint64_t *)p;        p += (size_t)cap * W * 8;
+    uint64_t *B = (uint64_t *)p;        p += (size_t)kMaxG * W * 8;
+    double *fE = (double *)p;           p += (size_t)kMaxFrames * 8;
+    int *fbase = (int *)p;              p += (size_t)kMaxFrames * 4;
+    int *fa = (int *)p;                 p += (size_t)kMaxFrames * 4;
+    int *fq = (int *)p;                 p += (size_t)kMaxFrames * 4;
+    uint32_t *hist = (uint32_t *)p;     p += (size_t)(kMaxG + 1) * 4 + 4;
+    uint16_t *TT = (uint16_t *)p;       p += (size_t)cap * 2;
+    uint16_t *path = (uint16_t *)p;     p += (size_t)kMaxG * 2;
+    uint16_t *bestG = (uint16_t *)p;    p += (size_t)kMaxG * 2;
+    uint8_t *pivB = (uint8_t *)p;
+
+    const unsigned gw = blockIdx.x * wpb + warp;
+    BestRec *myrec = D.wbest + gw;
+    double bestE = myrec->valid ? myrec->E : 1e300;
+    int bestM = myrec->valid ? myrec->m : 0;
+    int haveBest = myrec->valid;
+    for (int i = lane; i < bestM; i += 32) bestG[i] = myrec->g[i];
+    for (int i = lane; i <= kMaxG; i += 32) hist[i] = 0;
+    __syncwarp();
+
+    // record (path[0..len-1] ++ [last]) as the best tuple if E beats the incumbent
+#define SGS_TRY_BEST(Eval, len, lastTerm, withLast)                                                     \
+    do {                                                                                                \
+        bool better_ = !haveBest || (Eval) < bestE;                                                     \
+        if (!better_ && (Eval) == bestE) {                                                              \
+            if (withLast) path[len] = (uint16_t)(lastTerm);                                             \
+            __syncwarp();                                                                               \
+            better_ = tuple_before(path, (len) + ((withLast) ? 1 : 0), bestG, bestM);                   \
+        }                                                                                               \
+        if (better_) {                                                                                  \
+            haveBest = 1; bestE = (Eval); bestM = (len) + ((withLast) ? 1 : 0);                         \
+            __syncwarp();                                                                               \
+            for (int i_ = lane; i_ < (len); i_ += 32) bestG[i_] = path[i_];                             \
+            if ((withLast) && lane == 0) bestG[len] = (uint16_t)(lastTerm);                             \
+            __syncwarp();                                                                               \
+        }                                                                                               \
+    } while (0)
+
+    for (;;) {
+        // ---- fetch the next subtree root owned by this shard ----
+        unsigned it = 0;
+        if (lane == 0) it = atomicAdd(item_counter, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= nitems) break;
+        const uint16_t *rec = items + (size_t)it * D.S;
+        const int m0 = rec[0];
+        const unsigned flags = rec[1];
+        if (nshards > 1 && (int)(tuple_hash(rec + 2, m0) % (unsigned)nshards) != shard) continue;
+        __syncwarp();
+        for (int i = lane; i < m0; i += 32) path[i] = rec[2 + i];
+        __syncwarp();
+        if (flags & kFlagUnclean) { push_slow(D, path, m0, flags, lane); continue; }
+
+        // ---- root: basis of the m0 generators (bits only), alive list, residues ----
+        double E0 = 0.0;
+        for (int i = 0; i < m0; i++) {
+            uint64_t v[W];
+            const int t = path[i];
+#pragma unroll
+            for (int k = 0; k < W; k++) v[k] = D.rows[(size_t)t * W + k];
+            for (int b = 0; b < i; b++)
+                if (row_bit<W>(v, pivB[b])) {
+#pragma unroll
+                    for (int k = 0; k < W; k++) v[k] ^= B[b * W + k];
+                }
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < W; k++) B[i * W + k] = v[k];
+                pivB[i] = (uint8_t)row_lowbit<W>(v);
+            }
+            E0 -= D.wabs[t];
+            __syncwarp();
+        }
+        int a = alive_list(D, path, m0, TT, cap, lane);
+        if (a < 0) { push_slow(D, path, m0, flags, lane); continue; }
+        bool member = false;
+        for (int i = lane; i < a; i += 32) {
+            uint64_t v[W];
+            const int t = TT[i];
+#pragma unroll
+            for (int k = 0; k < W; k++) v[k] = D.rows[(size_t)t * W + k];
+            for (int b = 0; b < m0; b++)
+                if (row_bit<W>(v, pivB[b])) {
+#pragma unroll
+                    for (int k = 0; k < W; k++) v[k] ^= B[b * W + k];
+                }
+            member |= row_is_zero<W>(v);
+#pragma unroll
+            for (int k = 0; k < W; k++) R[(size_t)i * W + k] = v[k];
+        }
+        __syncwarp();
+        if (__any_sync(0xffffffffu, member)) { push_slow(D, path, m0, flags | kFlagUnclean, lane); continue; }
+
+        if (lane == 0) hist[m0]++;
+        const int core0 = m0 ? (int)path[m0 - 1] : -1;
+        int q0 = 0;                                         // first list position above the core
+        for (int i = lane; i < a; i += 32) q0 += ((int)TT[i] <= core0);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) q0 += __shfl_xor_sync(0xffffffffu, q0, d);
+        if (q0 >= a) { SGS_TRY_BEST(E0, m0, 0, false); continue; }        // no extension: a leaf
+        if (has_duplicate<W>(R, a, lane)) {
+            SGS_TRY_BEST(E0, m0, 0, false);
+            push_slow(D, path, m0, flags | kFlagExpandOnly, lane);
+            continue;
+        }
+        if (lane == 0) hist[m0 + 1] += (uint32_t)(a - q0);
+
+        // ---- depth-first walk; the top frame lives in registers ----
+        int fd = 0, base = 0, q = q0;
+        double E = E0;
+        for (;;) {
+            if (q >= a) {                                   // frame exhausted: pop
+                if (fd == 0) break;
+                fd--;
+                base = fbase[fd]; a = fa[fd]; q = fq[fd]; E = fE[fd];
+                continue;
+            }
+            const int depth = m0 + fd;                      // rank of the frame's group
+            const int jq = q++;
+            uint64_t rj[W], sw[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) { rj[k] = R[(size_t)(base + jq) * W + k]; sw[k] = swapzx(rj[k]); }
+            const int tj = TT[base + jq];
+            const double Ec = E - D.wabs[tj];
+
+            // pass 1: which list entries commute with the new generator (POPC), and is any above it?
+            int nal = 0, nlow = 0;
+            unsigned hiAny = 0;
+            for (int r0 = 0; r0 < a; r0 += 32) {
+                const int i = r0 + lane;
+                bool com = false;
+                if (i < a && i != jq) com = !row_anticommute_sw<W>(R + (size_t)(base + i) * W, sw);
+                const unsigned bal = __ballot_sync(0xffffffffu, com);
+                const int rel = jq - r0;                    // position of jq inside this row
+                if (rel >= 32) nlow += __popc(bal);
+                else if (rel >= 0) { nlow += __popc(bal & ((1u << rel) - 1u)); hiAny |= (rel == 31) ? 0u : (bal >> (rel + 1)); }
+                else hiAny |= bal;
+                nal += __popc(bal);
+            }
+            if (hiAny == 0) {                               // child is a leaf of the tree
+                SGS_TRY_BEST(Ec, depth, tj, true);
+                continue;
+            }
+            if (lane == 0) path[depth] = (uint16_t)tj;
+            const int cb = base + a;
+            if (cb + nal > cap || depth + 1 >= kMaxG) {     // out of list space: the exact kernel takes over
+                __syncwarp();
+                SGS_TRY_BEST(Ec, depth + 1, 0, false);
+                push_slow(D, path, depth + 1, kFlagExpandOnly, lane);
+                continue;
+            }
+            // pass 2: child list = surviving entries, reduced by the new generator at its pivot bit
+            const int pv = row_lowbit<W>(rj);
+            int off = 0;
+            for (int r0 = 0; r0 < a; r0 += 32) {
+                const int i = r0 + lane;
+                bool com = false;
+                uint64_t v[W];
+                int t = 0;
+                if (i < a && i != jq) {
+#pragma unroll
+                    for (int k = 0; k < W; k++) v[k] = R[(size_t)(base + i) * W + k];
+                    com = !row_anticommute_sw<W>(v, sw);
+                    t = TT[base + i];
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, com);
+                if (com) {
+                    if (row_bit<W>(v, pv)) {
+#pragma unroll
+                        for (int k = 0; k < W; k++) v[k] ^= rj[k];
+                    }
+                    const int pos = cb + off + __popc(bal & lanemask_lt());
+#pragma unroll
+                    for (int k = 0; k < W; k++) R[(size_t)pos * W + k] = v[k];
+                    TT[pos] = (uint16_t)t;
+                }
+                off += __popc(bal);
+            }
+            __syncwarp();
+            // residues pairwise distinct ⇒ every child of this child is a new group whose only members
+            // are its generators.  Otherwise the exact kernel expands it.
+            if (has_duplicate<W>(R + (size_t)cb * W, nal, lane)) {
+                SGS_TRY_BEST(Ec, depth + 1, 0, false);
+                push_slow(D, path, depth + 1, kFlagExpandOnly, lane);
+                continue;
+            }
+            if (lane == 0) hist[depth + 2] += (uint32_t)(nal - nlow);
+            fbase[fd] = base; fa[fd] = a; fq[fd] = q; fE[fd] = E;
+            fd++;
+            base = cb; a = nal; q = nlow; E = Ec;
+        }
+    }
+#undef SGS_TRY_BEST
+
+    __syncwarp();
+    if (haveBest) {
+        if (lane == 0) { myrec->E = bestE; myrec->m = bestM; myrec->valid = 1; }
+        for (int i = lane; i < bestM; i += 32) myrec->g[i] = bestG[i];
+    }
+    for (int i = lane; i <= kMaxG; i += 32)
+        if (hist[i]) atomicAdd(&D.stats->hist[i], (unsigned long long)hist[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic argmin over the per-warp records: minimum energy, ties by tuple order.  One warp.
+__global__ void k_reduce_best(const BestRec *__restrict__ recs, int nrecs, BestRec *__restrict__ out)
+{
+    const int lane = threadIdx.x;
+    int best = -1;
+    for (int i = lane; i < nrecs; i += 32) {
+        if (!recs[i].valid) continue;
+        if (best < 0 || recs[i].E < recs[best].E ||
+            (recs[i].E == recs[best].E && tuple_before(recs[i].g, recs[i].m, recs[best].g, recs[best].m)))
+            best = i;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, best, d);
+        if (other >= 0 &&
+            (best < 0 || recs[other].E < recs[best].E ||
+             (recs[other].E == recs[best].E && other != best &&
+              tuple_before(recs[other].g, recs[other].m, recs[best].g, recs[best].m))))
+            best = other;
+    }
+    if (lane == 0) {
+        if (best >= 0) *out = recs[best];
+        else { out->valid = 0; out->m = 0; out->E = 0.0; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_finalize: the winning group → the reference's printed result.
+//   canonical generators = RREF of the generator rows, rows sorted by pivot, with tracked signs
+//   (Stab::canonicalize, cpp/stab.cpp:437-449 via Gauss_elimination_full cpp/linear.cpp:129);
+//   sign pattern = FIRST minimum of the 2^m table indexed with generator 0 as the most significant bit
+//   and '+' = 0 (cpp/state.cpp:681-682, cpp/stab.cpp:37-45); per-term signs = Stab::energy
+//   (cpp/stab.cpp:579-587, printed by cpp/sparse.cpp:13-16).
+struct FinalOut {
+    double energy;
+    int m;
+    int error;
+    uint64_t rows[kMaxG * 4];
+    int8_t signs[kMaxG];
+};
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_finalize(SparseDev D, const BestRec *__restrict__ best, const int *__restrict__ order, FinalOut *out,
+           int8_t *__restrict__ term_signs, uint64_t *__restrict__ memX, double *__restrict__ memA,
+           int *__restrict__ memT, int *memCount)
+{
+    __shared__ uint64_t C[kMaxG * W];
+    __shared__ int qC[kMaxG], pivC[kMaxG];
+    __shared__ double redE[256];
+    __shared__ unsigned long long redI[256];
+    const int tid = threadIdx.x, m = best->m, T = D.T;
+
+    if (tid == 0) {
+        out->error = 0;
+        // K1: reduced row echelon form, pivot = lowest set bit, with phase tracking
+        for (int i = 0; i < m; i++) {
+            uint64_t v[W];
+            const int t = best->g[i];
+            for (int k = 0; k < W; k++) v[k] = D.rows[(size_t)t * W + k];
+            int q = row_plus_phase<W>(v);
+            for (int b = 0; b < i; b++)
+                if (row_bit<W>(v, pivC[b])) row_mul<W>(v, q, C + b * W, qC[b]);
+            const int pv = row_lowbit<W>(v);
+            for (int b = 0; b < i; b++)                       // clear the new pivot from earlier rows
+                if (row_bit<W>(C + b * W, pv)) row_mul<W>(C + b * W, qC[b], v, q);
+            for (int k = 0; k < W; k++) C[i * W + k] = v[k];
+            qC[i] = q; pivC[i] = pv;
+        }
+        for (int i = 1; i < m; i++) {                         // sort rows by pivot (insertion sort)
+            uint64_t v[W];
+            for (int k = 0; k < W; k++) v[k] = C[i * W + k];
+            const int q = qC[i], pv = pivC[i];
+            int j = i - 1;
+            while (j >= 0 && pivC[j] > pv) {
+                for (int k = 0; k < W; k++) C[(j + 1) * W + k] = C[j * W + k];
+                qC[j + 1] = qC[j]; pivC[j + 1] = pivC[j];
+                j--;
+            }
+            for (int k = 0; k < W; k++) C[(j + 1) * W + k] = v[k];
+            qC[j + 1] = q; pivC[j + 1] = pv;
+        }
+        // canonicalize_signs (cpp/stab.cpp:685-691): tables are indexed against '+' generators
+        for (int i = 0; i < m; i++) qC[i] = row_plus_phase<W>(C + i * W);
+        *memCount = 0;
+    }
+    __syncthreads();
+
+    // K2: decompose every term over the '+' canonical generators
+    for (int t0 = 0; t0 < T; t0 += blockDim.x) {
+        const int t = t0 + tid;
+        bool member = false;
+        uint64_t x = 0;
+        int q = 0;
+        if (t < T) {
+            uint64_t v[W];
+            for (int k = 0; k < W; k++) v[k] = D.rows[(size_t)t * W + k];
+            q = row_plus_phase<W>(v);
+            bool com = true;
+            for (int i = 0; i < m; i++) com &= !row_anticommute<W>(v, C + i * W);
+            if (com) {
+                for (int i = 0; i < m; i++)
+                    if (row_bit<W>(v, pivC[i])) { row_mul<W>(v, q, C + i * W, qC[i]); x |= 1ULL << (m - 1 - i); }
+                member = row_is_zero<W>(v);
+            }
+        }
+        if (member) {   // P_t = tau * prod_{i in x} C_i^+, tau = (-1)^{q/2}; bit 30 of memT carries tau < 0
+            const int slot = atomicAdd(memCount, 1);
+            memT[slot] = t | ((q & 2) ? (1 << 30) : 0); memX[slot] = x; memA[slot] = (q & 2) ? -D.wgt[t] : D.wgt[t];
+        }
+        if (t < T) term_signs[order[t]] = 0;
+    }
+    __syncthreads();
+    const int nm = *memCount;
+    if (tid == 0) {   // deterministic summation order: ascending term index
+        for (int i = 1; i < nm; i++) {
+            const int t = memT[i]; const uint64_t x = memX[i]; const double a = memA[i];
+            int j = i - 1;
+            while (j >= 0 && (memT[j] & 0xffff) > (t & 0xffff)) { memT[j + 1] = memT[j]; memX[j + 1] = memX[j]; memA[j + 1] = memA[j]; j--; }
+            memT[j + 1] = t; memX[j + 1] = x; memA[j + 1] = a;
+        }
+    }
+    __syncthreads();
+
+    // K5: first minimum over the 2^m sign patterns
+    double myE = 1e300;
+    unsigned long long myI = ~0ULL;
+    if (m <= kMaxBrute) {
+        for (unsigned long long idx = tid; idx < (1ULL << m); idx += blockDim.x) {
+            double e = 0.0;
+            for (int i = 0; i < nm; i++) e += (popc64(idx & memX[i]) & 1) ? -memA[i] : memA[i];
+            if (e < myE) { myE = e; myI = idx; }
+        }
+    } else {
+        // more generators than the table limit: exact only if every member is a generator on its own
+        // (then the signs decouple); otherwise report the limit.
+        if (tid == 0) {
+            bool ok = nm == m;
+            unsigned long long idx = 0;
+            double e = 0.0;
+            // solve x-matrix (unit-triangular after sorting by pivot is not guaranteed): Gaussian solve over GF(2)
+            uint64_t Xm[kMaxG]; int want[kMaxG];
+            for (int i = 0; i < nm && ok; i++) { Xm[i] = memX[i]; want[i] = memA[i] > 0.0 ? 1 : 0; e -= fabs(memA[i]); }
+            // find idx with parity(idx & Xm[i]) = want[i] for all i
+            for (int c = 0, r = 0; c < m && ok; c++) {
+                int pr = -1;
+                for (int i = r; i < nm; i++) if ((Xm[i] >> c) & 1) { pr = i; break; }
+                if (pr < 0) { ok = false; break; }
+                uint64_t tx = Xm[pr]; Xm[pr] = Xm[r]; Xm[r] = tx;
+                int tw = want[pr]; want[pr] = want[r]; want[r] = tw;
+                for (int i = 0; i < nm; i++) if (i != r && ((Xm[i] >> c) & 1)) { Xm[i] ^= Xm[r]; want[i] ^= want[r]; }
+                r++;
+            }
+            if (ok) { for (int i = 0; i < m; i++) if (want[i]) idx |= 1ULL << ctz64(Xm[i]); myE = e; myI = idx; }
+            else out->error = kErrLimit;
+        }
+    }
+    redE[tid] = myE; redI[tid] = myI;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            if (redE[tid + s] < redE[tid] || (redE[tid + s] == redE[tid] && redI[tid + s] < redI[tid])) {
+                redE[tid] = redE[tid + s]; redI[tid] = redI[tid + s];
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned long long idx = redI[0];
+    if (tid == 0) {
+        out->energy = redE[0];
+        out->m = m;
+        for (int i = 0; i < m; i++) {
+            for (int k = 0; k < W; k++) out->rows[i * W + k] = C[i * W + k];
+            out->signs[i] = ((idx >> (m - 1 - i)) & 1) ? -1 : 1;
+        }
+    }
+    for (int i = tid; i < nm; i += blockDim.x) {
+        const int tau = (memT[i] >> 30) & 1;
+        const int flip = popc64(idx & memX[i]) & 1;
+        term_signs[order[memT[i] & 0xffff]] = (int8_t)((tau ^ flip) ? -1 : 1);
+    }
+}
+
+}  // namespace sgs

@@ -1,0 +1,447 @@
+// sparse_search.cu — host driver of the sparse search (the C++ side of cpp/sparse.cpp's
+// FullState(paulis).evolve(), cpp/state.cpp:636-687).  The host only orchestrates: it uploads the term
+// table, launches the kernels of sparse_kernels.cuh and reads back one record.  There is no CPU
+// search path; without a CUDA device every entry point fails with SGS_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "common.hpp"
+#include "hamiltonian.hpp"
+#include "nccl_glue.hpp"
+#include "sparse_kernels.cuh"
+#include "sparse_search.hpp"
+
+namespace sgs {
+
+namespace {
+
+struct DevCtx {
+    int device = 0;
+    int shard = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evh0 = nullptr, evh1 = nullptr;
+    int sms = 0;
+    // device buffers
+    uint64_t *rows = nullptr, *adj = nullptr;
+    double *wgt = nullptr, *wabs = nullptr;
+    int *order = nullptr;
+    BestRec *wbest = nullptr, *gbest = nullptr, *allbest = nullptr;
+    SparseStats *stats = nullptr;
+    unsigned long long *hist_sum = nullptr;
+    uint16_t *qA = nullptr, *qB = nullptr, *slow = nullptr, *work = nullptr;
+    unsigned int *counters = nullptr;   // [0] next-level count, [1] item counter, [2] slow count
+    FinalOut *fin = nullptr;
+    int8_t *term_signs = nullptr;
+    uint64_t *memX = nullptr;
+    double *memA = nullptr;
+    int *memT = nullptr, *memCount = nullptr;
+    int nwbest = 0;
+    // results of the local search
+    SparseStats hstats{};
+    BestRec hbest{};
+    float ms_device = 0.f, ms_hot = 0.f;
+    unsigned launches = 0;
+    Status status;
+};
+
+template <typename T>
+cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc((void **)p, count * sizeof(T)); }
+
+}  // namespace
+
+struct SparsePlan::Impl {
+    Hamiltonian H;
+    sgs_opts opts{};
+    int W = 1, T = 0, TW = 0, S = 0, n = 0;
+    int nshards = 1;
+    unsigned qcap = 0, slow_cap = 0, chunk = 0;
+    int dfs_cap = 0;
+    std::vector<DevCtx> devs;
+    std::unique_ptr<NcclWorld> nccl;
+
+    ~Impl();
+    Status init();
+    Status init_device(DevCtx &c);
+    template <int W_> Status search_local(DevCtx &c);
+    template <int W_> Status finalize(DevCtx &c, const BestRec &best, sgs_result *out);
+    Status run(sgs_result *out);
+    SparseDev dev_view(const DevCtx &c) const;
+};
+
+SparsePlan::Impl::~Impl()
+{
+    nccl.reset();
+    for (auto &c : devs) {
+        cudaSetDevice(c.device);
+        cudaFree(c.rows); cudaFree(c.adj); cudaFree(c.wgt); cudaFree(c.wabs); cudaFree(c.order);
+        cudaFree(c.wbest); cudaFree(c.gbest); cudaFree(c.allbest); cudaFree(c.stats); cudaFree(c.hist_sum);
+        cudaFree(c.qA); cudaFree(c.qB); cudaFree(c.slow); cudaFree(c.work); cudaFree(c.counters);
+        cudaFree(c.fin); cudaFree(c.term_signs); cudaFree(c.memX); cudaFree(c.memA); cudaFree(c.memT);
+        cudaFree(c.memCount);
+        if (c.ev0) cudaEventDestroy(c.ev0);
+        if (c.ev1) cudaEventDestroy(c.ev1);
+        if (c.evh0) cudaEventDestroy(c.evh0);
+        if (c.evh1) cudaEventDestroy(c.evh1);
+        if (c.stream) cudaStreamDestroy(c.stream);
+    }
+}
+
+SparseDev SparsePlan::Impl::dev_view(const DevCtx &c) const
+{
+    SparseDev D{};
+    D.n = n; D.T = T; D.TW = TW; D.S = S;
+    D.rows = c.rows; D.wgt = c.wgt; D.wabs = c.wabs; D.adj = c.adj;
+    D.wbest = c.wbest; D.stats = c.stats;
+    D.slow = c.slow; D.slow_count = c.counters + 2; D.slow_cap = slow_cap;
+    return D;
+}
+
+Status SparsePlan::Impl::init()
+{
+    n = H.n; T = H.T();
+    if (n > 2 * 64) return Status::fail(SGS_ERR_LIMIT, "sparse search supports n <= 128");
+    if (T > 65535) return Status::fail(SGS_ERR_LIMIT, "sparse search supports at most 65535 terms");
+    if (T > 8192) return Status::fail(SGS_ERR_LIMIT, "sparse search supports at most 8192 terms (shared-memory lists)");
+    W = (2 * n + 63) / 64;
+    if (W == 3) W = 4;
+    TW = (T + 63) / 64;
+    if (TW < 1) TW = 1;
+    const int maxrank = std::min(std::min(n, std::max(T, 1)), kMaxG);
+    S = 2 + maxrank;
+    if (S & 1) S++;
+    const unsigned long long want = std::max<unsigned long long>(1ull << 18, 64ull * T * T);
+    qcap = (unsigned)std::min<unsigned long long>(want, 1ull << 25);
+    slow_cap = 1u << 22;
+    chunk = 1u << 16;
+    int c = 64;
+    while (c < T / 2 && c < 1024) c <<= 1;
+    dfs_cap = c;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return Status::fail(SGS_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                                   " (libsgs has no CPU search path)");
+    const int ng = std::max(1, opts.ngpus);
+    if (opts.device < 0 || opts.device + ng > ndev) return Status::fail(SGS_ERR_ARG, "device ordinal out of range");
+    const int world = std::max(1, opts.world);
+    nshards = world * ng;
+    devs.resize(ng);
+    for (int i = 0; i < ng; i++) {
+        devs[i].device = opts.device + i;
+        devs[i].shard = std::max(0, opts.rank) * ng + i;
+        Status s = init_device(devs[i]);
+        if (!s.ok()) return s;
+    }
+    if (nshards > 1 && (opts.nccl_id != nullptr || (world == 1 && ng > 1))) {
+        std::vector<int> ids;
+        for (auto &d : devs) ids.push_back(d.device);
+        nccl.reset(new NcclWorld());
+        Status s = nccl->init(ids, std::max(0, opts.rank), world, opts.nccl_id);
+        if (!s.ok()) return s;
+    }
+    return Status();
+}
+
+Status SparsePlan::Impl::init_device(DevCtx &c)
+{
+    SGS_CUDA_TRY(cudaSetDevice(c.device));
+    cudaDeviceProp prop{};
+    SGS_CUDA_TRY(cudaGetDeviceProperties(&prop, c.device));
+    c.sms = prop.multiProcessorCount;
+    SGS_CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    SGS_CUDA_TRY(cudaEventCreate(&c.ev0));
+    SGS_CUDA_TRY(cudaEventCreate(&c.ev1));
+    SGS_CUDA_TRY(cudaEventCreate(&c.evh0));
+    SGS_CUDA_TRY(cudaEventCreate(&c.evh1));
+    const int Tn = std::max(T, 1);
+    SGS_CUDA_TRY(dmalloc(&c.rows, (size_t)Tn * W));
+    SGS_CUDA_TRY(dmalloc(&c.adj, (size_t)Tn * TW));
+    SGS_CUDA_TRY(dmalloc(&c.wgt, Tn));
+    SGS_CUDA_TRY(dmalloc(&c.wabs, Tn));
+    SGS_CUDA_TRY(dmalloc(&c.order, Tn));
+    c.nwbest = c.sms * 64;
+    SGS_CUDA_TRY(dmalloc(&c.wbest, c.nwbest));
+    SGS_CUDA_TRY(dmalloc(&c.gbest, 1));
+    SGS_CUDA_TRY(dmalloc(&c.allbest, std::max(nshards, 1)));
+    SGS_CUDA_TRY(dmalloc(&c.stats, 1));
+    SGS_CUDA_TRY(dmalloc(&c.hist_sum, kMaxG + 2));
+    SGS_CUDA_TRY(dmalloc(&c.qA, (size_t)qcap * S));
+    SGS_CUDA_TRY(dmalloc(&c.qB, (size_t)qcap * S));
+    SGS_CUDA_TRY(dmalloc(&c.slow, (size_t)slow_cap * S));
+    SGS_CUDA_TRY(dmalloc(&c.work, (size_t)chunk * S));
+    SGS_CUDA_TRY(dmalloc(&c.counters, 4));
+    SGS_CUDA_TRY(dmalloc(&c.fin, 1));
+    SGS_CUDA_TRY(dmalloc(&c.term_signs, Tn));
+    SGS_CUDA_TRY(dmalloc(&c.memX, Tn));
+    SGS_CUDA_TRY(dmalloc(&c.memA, Tn));
+    SGS_CUDA_TRY(dmalloc(&c.memT, Tn));
+    SGS_CUDA_TRY(dmalloc(&c.memCount, 1));
+
+    // term table in paulis_list order (cpp/state.cpp:88-96)
+    std::vector<uint64_t> rows((size_t)Tn * W, 0);
+    std::vector<double> wgt(Tn, 0.0), wabs(Tn, 0.0);
+    for (int p = 0; p < T; p++) {
+        const int f = H.order[p];
+        for (int k = 0; k < W; k++) rows[(size_t)p * W + k] = H.terms[f].w[k];
+        wgt[p] = H.weights[f];
+        wabs[p] = std::fabs(H.weights[f]);
+    }
+    SGS_CUDA_TRY(cudaMemcpyAsync(c.rows, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, c.stream));
+    SGS_CUDA_TRY(cudaMemcpyAsync(c.wgt, wgt.data(), wgt.size() * 8, cudaMemcpyHostToDevice, c.stream));
+    SGS_CUDA_TRY(cudaMemcpyAsync(c.wabs, wabs.data(), wabs.size() * 8, cudaMemcpyHostToDevice, c.stream));
+    if (T > 0) SGS_CUDA_TRY(cudaMemcpyAsync(c.order, H.order.data(), (size_t)T * 4, cudaMemcpyHostToDevice, c.stream));
+    SGS_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    if (T > 0) {
+        const int total = T * TW;
+        if (W == 1) k_adjacency<1><<<(total + 127) / 128, 128, 0, c.stream>>>(T, TW, c.rows, c.adj);
+        else if (W == 2) k_adjacency<2><<<(total + 127) / 128, 128, 0, c.stream>>>(T, TW, c.rows, c.adj);
+        else k_adjacency<4><<<(total + 127) / 128, 128, 0, c.stream>>>(T, TW, c.rows, c.adj);
+        SGS_CUDA_TRY(cudaGetLastError());
+        SGS_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    }
+    return Status();
+}
+
+template <int W_>
+Status SparsePlan::Impl::search_local(DevCtx &c)
+{
+    SGS_CUDA_TRY(cudaSetDevice(c.device));
+    const SparseDev D = dev_view(c);
+    cudaStream_t st = c.stream;
+    c.launches = 0;
+    SGS_CUDA_TRY(cudaMemsetAsync(c.wbest, 0, sizeof(BestRec) * c.nwbest, st));
+    SGS_CUDA_TRY(cudaMemsetAsync(c.stats, 0, sizeof(SparseStats), st));
+    SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, 4 * sizeof(unsigned), st));
+    // root record: the empty group
+    std::vector<uint16_t> root(S, 0);
+    SGS_CUDA_TRY(cudaMemcpyAsync(c.qA, root.data(), S * 2, cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaEventRecord(c.ev0, st));
+
+    // ---- k_general launch geometry ----
+    const size_t gen_pw = general_smem_bytes<W_>(std::max(T, 1));
+    int gen_wpb = 4;
+    while (gen_wpb > 1 && gen_pw * gen_wpb > 96 * 1024) gen_wpb >>= 1;
+    if (gen_pw * gen_wpb > 200 * 1024) return Status::fail(SGS_ERR_LIMIT, "too many terms for the general kernel's shared-memory lists");
+    SGS_CUDA_TRY(cudaFuncSetAttribute(k_general<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(gen_pw * gen_wpb)));
+    int gen_occ = 1;
+    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gen_occ, k_general<W_>, gen_wpb * 32, gen_pw * gen_wpb));
+    gen_occ = std::max(1, gen_occ);
+    const unsigned gen_maxgrid = (unsigned)std::min<long long>((long long)c.sms * gen_occ, c.nwbest / gen_wpb);
+    auto launch_general = [&](const uint16_t *in, unsigned nin, uint16_t *out, unsigned *out_count, unsigned out_cap,
+                              int shard, int nsh) {
+        unsigned grid = std::min<unsigned>((nin + gen_wpb - 1) / gen_wpb, gen_maxgrid);
+        if (grid == 0) return;
+        k_general<W_><<<grid, gen_wpb * 32, gen_pw * gen_wpb, st>>>(D, in, nin, out, out_count, out_cap, shard, nsh, (int)gen_pw);
+        c.launches++;
+    };
+
+    // ---- breadth-first expansion of the top of the tree into subtree roots ----
+    const unsigned target = opts.expand_depth > 0 ? 0xffffffffu : (1u << 19) * (unsigned)std::min(nshards, 8);
+    const int dmax = opts.expand_depth > 0 ? opts.expand_depth : 8;
+    uint16_t *cur = c.qA, *nxt = c.qB;
+    unsigned count = 1;
+    double ratio = (double)std::max(T, 1);
+    int depth = 0;
+    SparseStats hs{};
+    unsigned hcnt[4];
+    while (count > 0 && depth < dmax && count < target) {
+        const double bound = (double)count * std::min<double>((double)std::max(T, 1), ratio);
+        if (bound > (double)qcap) break;
+        SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, sizeof(unsigned), st));
+        launch_general(cur, count, nxt, c.counters, qcap, c.shard, nshards);
+        SGS_CUDA_TRY(cudaGetLastError());
+        SGS_CUDA_TRY(cudaMemcpyAsync(hcnt, c.counters, sizeof(hcnt), cudaMemcpyDeviceToHost, st));
+        SGS_CUDA_TRY(cudaMemcpyAsync(&hs, c.stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        SGS_CUDA_TRY(cudaStreamSynchronize(st));
+        if (hs.error) return Status::fail(hs.error == kErrOverflow ? SGS_ERR_OVERFLOW : SGS_ERR_LIMIT,
+                                          "sparse search: device limit hit while expanding the tree (queue overflow or rank/table limit)");
+        ratio = std::max(1.0, (double)hcnt[0] / (double)count);
+        count = hcnt[0];
+        std::swap(cur, nxt);
+        depth++;
+    }
+
+    // ---- the hot kernel: depth-first enumeration below every subtree root ----
+    if (count > 0) {
+        const size_t pw = dfs_smem_bytes<W_>(dfs_cap);
+        const int wpb = 8;
+        SGS_CUDA_TRY(cudaFuncSetAttribute(k_dfs<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pw * wpb)));
+        int occ = 1;
+        SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dfs<W_>, wpb * 32, pw * wpb));
+        occ = std::max(1, occ);
+        unsigned grid = (unsigned)std::min<long long>((long long)c.sms * occ, c.nwbest / wpb);
+        grid = std::min<unsigned>(grid, (count + wpb - 1) / wpb);
+        SGS_CUDA_TRY(cudaEventRecord(c.evh0, st));
+        k_dfs<W_><<<grid, wpb * 32, pw * wpb, st>>>(D, cur, count, c.counters + 1, c.shard, nshards, dfs_cap, (int)pw);
+        c.launches++;
+        SGS_CUDA_TRY(cudaGetLastError());
+        SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
+    } else {
+        SGS_CUDA_TRY(cudaEventRecord(c.evh0, st));
+        SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
+    }
+
+    // ---- drain the work stack of groups with dependent terms through the exact kernel ----
+    for (;;) {
+        SGS_CUDA_TRY(cudaMemcpyAsync(hcnt, c.counters, sizeof(hcnt), cudaMemcpyDeviceToHost, st));
+        SGS_CUDA_TRY(cudaMemcpyAsync(&hs, c.stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        SGS_CUDA_TRY(cudaStreamSynchronize(st));
+        if (hs.error) return Status::fail(hs.error == kErrOverflow ? SGS_ERR_OVERFLOW : SGS_ERR_LIMIT,
+                                          "sparse search: device limit hit (work-stack overflow, or a group whose sign table exceeds the limit)");
+        const unsigned sc = hcnt[2];
+        if (sc == 0) break;
+        const unsigned take = std::min(sc, chunk);
+        SGS_CUDA_TRY(cudaMemcpyAsync(c.work, c.slow + (size_t)(sc - take) * S, (size_t)take * S * 2, cudaMemcpyDeviceToDevice, st));
+        const unsigned left = sc - take;
+        SGS_CUDA_TRY(cudaMemcpyAsync(c.counters + 2, &left, sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        launch_general(c.work, take, c.slow, c.counters + 2, slow_cap, 0, 1);
+        SGS_CUDA_TRY(cudaGetLastError());
+    }
+
+    k_reduce_best<<<1, 32, 0, st>>>(c.wbest, c.nwbest, c.gbest);
+    c.launches++;
+    SGS_CUDA_TRY(cudaGetLastError());
+    SGS_CUDA_TRY(cudaEventRecord(c.ev1, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(&c.hbest, c.gbest, sizeof(BestRec), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(&c.hstats, c.stats, sizeof(SparseStats), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    SGS_CUDA_TRY(cudaEventElapsedTime(&c.ms_device, c.ev0, c.ev1));
+    SGS_CUDA_TRY(cudaEventElapsedTime(&c.ms_hot, c.evh0, c.evh1));
+    return Status();
+}
+
+template <int W_>
+Status SparsePlan::Impl::finalize(DevCtx &c, const BestRec &best, sgs_result *out)
+{
+    SGS_CUDA_TRY(cudaSetDevice(c.device));
+    const SparseDev D = dev_view(c);
+    cudaStream_t st = c.stream;
+    SGS_CUDA_TRY(cudaMemcpyAsync(c.gbest, &best, sizeof(BestRec), cudaMemcpyHostToDevice, st));
+    k_finalize<W_><<<1, 256, 0, st>>>(D, c.gbest, c.order, c.fin, c.term_signs, c.memX, c.memA, c.memT, c.memCount);
+    c.launches++;
+    SGS_CUDA_TRY(cudaGetLastError());
+    FinalOut fo;
+    std::vector<int8_t> ts(std::max(T, 1));
+    SGS_CUDA_TRY(cudaMemcpyAsync(&fo, c.fin, sizeof(FinalOut), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(ts.data(), c.term_signs, std::max(T, 1), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    if (fo.error) return Status::fail(SGS_ERR_LIMIT, "ground-state group rank exceeds the sign-table limit and its terms are linearly dependent");
+    const int Wout = (2 * n + 63) / 64;
+    out->energy = fo.energy;
+    out->n = n; out->m = fo.m; out->W = Wout; out->T = T;
+    out->gens = (uint64_t *)calloc((size_t)std::max(fo.m, 1) * Wout, 8);
+    out->gen_signs = (int8_t *)calloc(std::max(fo.m, 1), 1);
+    out->term_signs = (int8_t *)calloc(std::max(T, 1), 1);
+    for (int i = 0; i < fo.m; i++) {
+        for (int k = 0; k < Wout; k++) out->gens[(size_t)i * Wout + k] = fo.rows[i * W_ + k];
+        out->gen_signs[i] = fo.signs[i];
+    }
+    memcpy(out->term_signs, ts.data(), T);
+    return Status();
+}
+
+Status SparsePlan::Impl::run(sgs_result *out)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    memset(out, 0, sizeof(*out));
+    auto local = [&](DevCtx &c) {
+        if (W == 1) c.status = search_local<1>(c);
+        else if (W == 2) c.status = search_local<2>(c);
+        else c.status = search_local<4>(c);
+    };
+    if (devs.size() == 1) local(devs[0]);
+    else {
+        std::vector<std::thread> th;
+        for (auto &c : devs) th.emplace_back(local, std::ref(c));
+        for (auto &t : th) t.join();
+    }
+    for (auto &c : devs) if (!c.status.ok()) return c.status;
+
+    // ---- combine the shards: one (energy, generating tuple) record per shard + the counters ----
+    BestRec best = devs[0].hbest;
+    SparseStats tot = devs[0].hstats;
+    if (nccl) {
+        // NCCL all-gather of the per-shard minima and all-reduce(sum) of the counters over NVLink,
+        // then the same deterministic argmin on every GPU
+        for (auto &c : devs) {
+            cudaSetDevice(c.device);
+            cudaMemcpyAsync(c.hist_sum, c.hstats.hist, sizeof(unsigned long long) * (kMaxG + 1), cudaMemcpyHostToDevice, c.stream);
+            cudaMemcpyAsync(c.hist_sum + kMaxG + 1, &c.hstats.slow_nodes, sizeof(unsigned long long), cudaMemcpyHostToDevice, c.stream);
+        }
+        std::vector<void *> sendb, recvb, sumb;
+        std::vector<cudaStream_t> sts;
+        for (auto &c : devs) { sendb.push_back(c.gbest); recvb.push_back(c.allbest); sumb.push_back(c.hist_sum); sts.push_back(c.stream); }
+        Status s = nccl->all_gather_bytes(sendb, recvb, sizeof(BestRec), sts);
+        if (!s.ok()) return s;
+        s = nccl->all_reduce_sum_u64(sumb, kMaxG + 2, sts);
+        if (!s.ok()) return s;
+        for (auto &c : devs) {
+            cudaSetDevice(c.device);
+            k_reduce_best<<<1, 32, 0, c.stream>>>(c.allbest, nshards, c.gbest);
+            c.launches++;
+        }
+        DevCtx &c0 = devs[0];
+        cudaSetDevice(c0.device);
+        unsigned long long hsum[kMaxG + 2];
+        SGS_CUDA_TRY(cudaMemcpyAsync(&best, c0.gbest, sizeof(BestRec), cudaMemcpyDeviceToHost, c0.stream));
+        SGS_CUDA_TRY(cudaMemcpyAsync(hsum, c0.hist_sum, sizeof(hsum), cudaMemcpyDeviceToHost, c0.stream));
+        for (auto &c : devs) { cudaSetDevice(c.device); SGS_CUDA_TRY(cudaStreamSynchronize(c.stream)); }
+        memcpy(tot.hist, hsum, sizeof(unsigned long long) * (kMaxG + 1));
+        tot.slow_nodes = hsum[kMaxG + 1];
+    } else {
+        for (size_t i = 1; i < devs.size(); i++) {      // only reachable with world > 1 && nccl_id == NULL per process: no merge
+            const BestRec &b = devs[i].hbest;
+            (void)b;
+        }
+    }
+    if (!best.valid) return Status::fail(SGS_ERR_CUDA, "sparse search produced no candidate");
+
+    DevCtx &c0 = devs[0];
+    Status s;
+    if (W == 1) s = finalize<1>(c0, best, out);
+    else if (W == 2) s = finalize<2>(c0, best, out);
+    else s = finalize<4>(c0, best, out);
+    if (!s.ok()) return s;
+
+    out->candidates = 0;
+    out->sum_2m = 0.0;
+    for (int i = 0; i <= kMaxG && i <= SGS_MAX_RANK; i++) {
+        out->rank_hist[i] = tot.hist[i];
+        out->candidates += tot.hist[i];
+        out->sum_2m += (double)tot.hist[i] * std::ldexp(1.0, i);
+    }
+    out->slow_nodes = tot.slow_nodes;
+    float msd = 0.f, msh = 0.f;
+    unsigned launches = 0;
+    for (auto &c : devs) { msd = std::max(msd, c.ms_device); msh = std::max(msh, c.ms_hot); launches += c.launches; }
+    out->seconds_device = msd * 1e-3;
+    out->seconds_hot_kernel = msh * 1e-3;
+    out->kernel_launches = launches;
+    out->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return Status();
+}
+
+SparsePlan::SparsePlan() : impl_(new Impl()) {}
+SparsePlan::~SparsePlan() { delete impl_; }
+
+Status SparsePlan::create(const Hamiltonian &H, const sgs_opts &opts, std::unique_ptr<SparsePlan> &out)
+{
+    std::unique_ptr<SparsePlan> p(new SparsePlan());
+    p->impl_->H = H;
+    p->impl_->opts = opts;
+    Status s = p->impl_->init();
+    if (!s.ok()) return s;
+    out = std::move(p);
+    return Status();
+}
+
+Status SparsePlan::run(sgs_result *out) { return impl_->run(out); }
+
+}  // namespace sgs
