@@ -1,0 +1,197 @@
+"""GPU parity tests of the sparse search: CUDA path (through the C ABI) vs the CPU oracle and the
+golden vectors of the Python reference.  Bit-exact for generators / signs / counts; energy to 1e-10."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import gen_hamiltonians as G
+import oracle_py as O
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+SPARSE = sorted(f for f in glob.glob(os.path.join(GOLDEN, '*.json')) if 'sparse' in json.load(open(f)))
+
+
+def _name(p):
+    return os.path.basename(p)[:-5]
+
+
+def sgs():
+    import stabilizer_gs_b200 as S
+    return S
+
+
+def check_same(gpu, ref, counts=True):
+    assert gpu['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12)
+    assert gpu['generators'] == ref['generators']
+    assert gpu['term_signs'] == ref['term_signs']
+    if counts:
+        assert gpu['candidates'] == ref['candidates']
+        assert {int(k): v for k, v in gpu['rank_hist'].items()} == {int(k): v for k, v in ref['rank_hist'].items()}
+
+
+@pytest.mark.parametrize('depth', [0, 1, 2, 3])
+@pytest.mark.parametrize('path', SPARSE, ids=_name)
+def test_golden_python_reference(path, depth):
+    S = sgs()
+    g = json.load(open(path))
+    ref = dict(g['sparse'])
+    ref['rank_hist'] = ref['ranks']
+    H = S.HamHandle.load(os.path.join(GOLDEN, g['file']))
+    r = S.sparse_search(H, expand_depth=depth)
+    check_same(r, ref)
+    assert r['sum_2m'] == ref['sum_2m']
+
+
+@pytest.mark.parametrize('depth', [0, 1, 2])
+@pytest.mark.parametrize('n,T,seed', [(5, 12, 0), (6, 18, 3), (7, 22, 4), (8, 26, 5), (9, 30, 6), (10, 34, 7), (12, 36, 8),
+                                      (12, 30, 9), (3, 12, 10), (4, 20, 11), (2, 9, 12), (16, 40, 13)])
+def test_random_vs_oracle(n, T, seed, depth):
+    S = sgs()
+    T = min(T, 4 ** n - 1)
+    text = G.sparse_text(n, T, seed)
+    ref = O.sparse(text=text, threads=4)
+    r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=depth)
+    check_same(r, ref)
+
+
+@pytest.mark.parametrize('n,k,per,seed', [(8, 3, 2, 0), (10, 3, 3, 1), (9, 4, 2, 2), (12, 2, 2, 3)])
+def test_klocal_inputs_vs_oracle(n, k, per, seed):
+    """k-local (structured, dependency-heavy) Hamiltonians through the sparse path"""
+    S = sgs()
+    text = G.klocal_text(n, k, per, seed)
+    ref = O.sparse(text=text, threads=4)
+    for depth in (0, 1, 3):
+        r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=depth)
+        check_same(r, ref)
+
+
+def _tie_text(n, T, seed):
+    """weights from {±1, ±0.5}: sums are exact in fp64, so ties are exact and the tie-break is tested"""
+    rng = np.random.default_rng(seed)
+    lines = G.sparse_text(n, T, seed).splitlines()
+    out = [lines[0]]
+    for ln in lines[1:]:
+        parts = ln.split()
+        w = rng.choice([-1.0, 1.0, -0.5, 0.5])
+        out.append(f"{w: .10f} " + ' '.join(parts[1:]))
+    return '\n'.join(out) + '\n'
+
+
+@pytest.mark.parametrize('n,T,seed', [(4, 10, 0), (5, 14, 1), (6, 16, 2), (8, 24, 3), (10, 28, 4)])
+def test_exact_ties_follow_documented_order(n, T, seed):
+    S = sgs()
+    text = _tie_text(n, T, seed)
+    ref = O.sparse(text=text)
+    for depth in (0, 1, 2):
+        r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=depth)
+        check_same(r, ref)
+
+
+def test_edge_cases():
+    S = sgs()
+    # a single term; a single qubit; duplicate strings; an identity-letter term; zero weights
+    cases = [
+        "1 1\n 0.5 Z 0\n",
+        "1 1\n 0.5 Z 0\n -0.25 X 0\n 0.75 Y 0\n",
+        "3 3\n 0.5 ZZ 0 1\n 0.25 ZZ 0 1\n -1.0 XX 0 1\n 0.3 IZ 1 2\n",
+        "3 3\n 0.0 ZZ 0 1\n 0.0 XX 0 1\n 1.0 YY 0 1\n 0.0 Z 2\n",
+        "2 2\n 1.0 II 0 1\n -1.0 ZZ 0 1\n 0.5 XX 0 1\n",
+    ]
+    for text in cases:
+        ref = O.sparse(text=text)
+        for depth in (0, 1, 2):
+            r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=depth)
+            check_same(r, ref)
+
+
+def test_two_word_rows_vs_oracle():
+    """n > 32 exercises the W = 2 kernels: few terms on many qubits"""
+    S = sgs()
+    for n, T, seed in [(40, 16, 0), (48, 18, 1), (33, 20, 2)]:
+        text = G.sparse_text(n, T, seed)
+        ref = O.sparse(text=text, threads=4)
+        for depth in (0, 2):
+            r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=depth)
+            check_same(r, ref)
+
+
+def test_virtual_shards_partition_the_search():
+    """rank r of world w without a communicator returns that shard only: counts add up, the minimum over
+    shards is the global answer (what the NCCL argmin combines)."""
+    S = sgs()
+    text = G.sparse_text(10, 34, 21)
+    full = S.sparse_search(S.HamHandle.from_text(text))
+    for world in (2, 3, 8):
+        parts = [S.sparse_search(S.HamHandle.from_text(text), rank=r, world=world) for r in range(world)]
+        assert sum(p['candidates'] for p in parts) == full['candidates']
+        best = min(parts, key=lambda p: p['energy'])
+        assert best['energy'] == full['energy'] and best['generators'] == full['generators']
+
+
+def _check_invariants(S, text, r):
+    H = S.HamHandle.from_text(text)
+    rows, w, b, e = H.terms()
+    assert r['energy'] == pytest.approx(sum(wi * si for wi, si in zip(w, r['term_signs'])), rel=1e-10)
+    # generators pairwise commute and are in RREF order (strictly increasing pivots)
+    gens = r['generators']
+    def bits(s):
+        v = 0
+        for j, ch in enumerate(s[1:]):
+            v |= {'I': 0, 'Z': 1, 'X': 2, 'Y': 3}[ch] << (2 * j)
+        return v
+    gb = [bits(s) for s in gens]
+    ev = int('01' * 128, 2)
+    sw = lambda x: ((x >> 1) & ev) | ((x & ev) << 1)
+    for i in range(len(gb)):
+        for j in range(i):
+            assert bin(gb[i] & sw(gb[j])).count('1') % 2 == 0
+    piv = [(x & -x).bit_length() - 1 for x in gb]
+    assert piv == sorted(piv) and len(set(piv)) == len(piv)
+    for i, p in enumerate(piv):
+        for j, x in enumerate(gb):
+            if i != j:
+                assert not (x >> p) & 1
+
+
+def test_full_size_config4_properties():
+    """BASELINE config 4 (n=24, T=300): size-independent properties + invariance under the work split"""
+    S = sgs()
+    text = G.sparse_text(24, 300, 0)
+    r = S.sparse_search(S.HamHandle.from_text(text))
+    _check_invariants(S, text, r)
+    assert r['slow_nodes'] <= 600000          # the exact kernel only handles the top of the tree here
+    r2 = S.sparse_search(S.HamHandle.from_text(text), expand_depth=2)
+    assert r2['candidates'] == r['candidates'] and r2['rank_hist'] == r['rank_hist']
+    assert r2['energy'] == r['energy'] and r2['generators'] == r['generators']
+    parts = [S.sparse_search(S.HamHandle.from_text(text), rank=k, world=4) for k in range(4)]
+    assert sum(p['candidates'] for p in parts) == r['candidates']
+    assert min(p['energy'] for p in parts) == r['energy']
+    # the expected size of the search space (~8.0e7)
+    assert 4e7 < r['candidates'] < 2e8
+
+
+def test_plan_reuse_is_deterministic():
+    S = sgs()
+    text = G.sparse_text(14, 60, 5)
+    plan = S.SparsePlan(S.HamHandle.from_text(text))
+    a = plan.run()
+    b = plan.run()
+    plan.close()
+    for k in ('energy', 'generators', 'term_signs', 'candidates', 'rank_hist'):
+        assert a[k] == b[k]
+    _check_invariants(S, text, a)
+
+
+def test_errors():
+    S = sgs()
+    with pytest.raises(S.SgsError):
+        S.HamHandle.load('/nonexistent/file.txt')
+    with pytest.raises(S.SgsError):
+        S.HamHandle.from_text("2 2\n 1.0 QZ 0 1\n")
+    with pytest.raises(S.SgsError):
+        S.HamHandle.from_text("2 2\n 1.0 ZZ 0\n")
