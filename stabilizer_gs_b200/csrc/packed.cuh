@@ -101,6 +101,7 @@ SGS_HD bool row_is_zero(const uint64_t *r)
 template <int W>
 SGS_HD int row_lowbit(const uint64_t *r)   // index of the lowest set bit; row must be non-zero
 {
+    if (W == 1) return ctz64(r[0]);
 #pragma unroll
     for (int i = 0; i < W; i++)
         if (r[i]) return i * 64 + ctz64(r[i]);
@@ -108,7 +109,14 @@ SGS_HD int row_lowbit(const uint64_t *r)   // index of the lowest set bit; row m
 }
 
 template <int W>
-SGS_HD int row_bit(const uint64_t *r, int c) { return (int)((r[c >> 6] >> (c & 63)) & 1); }
+SGS_HD int row_bit(const uint64_t *r, int c)
+{
+    if (W == 1) return (int)((r[0] >> c) & 1);
+    uint64_t w = r[0];                       // select without dynamic indexing (keeps rows in registers)
+#pragma unroll
+    for (int i = 1; i < W; i++) w = ((c >> 6) == i) ? r[i] : w;
+    return (int)((w >> (c & 63)) & 1);
+}
 
 template <int W>
 SGS_HD bool row_equal(const uint64_t *a, const uint64_t *b)

@@ -417,51 +417,190 @@ __host__ __device__ inline size_t dfs_smem_bytes(int cap)
 {
     size_t b = 0;
     b += (size_t)cap * W * 8;          // residues
-    b += (size_t)kMaxG * W * 8;        // basis (subtree-root setup)
+    b += (size_t)cap * 8;              // |w| of each list entry
+    b += (size_t)32 * W * 8;           // basis (subtree-root setup)
+    b += (size_t)64 * 8;               // level-B commutation bit-matrix
     b += (size_t)kMaxFrames * 8;       // frame E
     b += (size_t)kMaxFrames * 4 * 3;   // frame base, a, q
     b += (size_t)(kMaxG + 1) * 4 + 4;  // hist
     b += (size_t)cap * 2;              // term indices
     b += (size_t)kMaxG * 2 * 2;        // path, best tuple
-    b += kMaxG;                        // pivots
+    b += 32;                           // basis pivots
     return (b + 15) & ~(size_t)15;
 }
 
 // any two equal residues among R[0..n)?  (no zero residue can occur: see the caller)
+// Rows of 32 entries: __match_any_sync inside a row, broadcast-compare against the lower rows.
 template <int W>
 SGS_D bool has_duplicate(const uint64_t *R, int n, int lane)
 {
-    if (n <= 32) {
-        bool dup = false;
-        if (lane < n) {
-            const unsigned mask = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+    bool dup = false;
+#pragma unroll 1
+    for (int r0 = 0; r0 < n; r0 += 32) {
+        const int cnt = min(32, n - r0);
+        if (lane < cnt) {
+            const unsigned mask = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
             unsigned mm = 0xffffffffu;
 #pragma unroll
-            for (int k = 0; k < W; k++) mm &= __match_any_sync(mask, R[(size_t)lane * W + k]);
-            dup = (mm & (mm - 1)) != 0;
+            for (int k = 0; k < W; k++) mm &= __match_any_sync(mask, R[(r0 + lane) * W + k]);
+            dup |= (mm & (mm - 1)) != 0;
         }
-        return __any_sync(0xffffffffu, dup);
-    }
-    bool dup = false;
-    for (int e = 0; e + 1 < n; e++) {
-        uint64_t ref[W];
+        if (r0 > 0) {
+#pragma unroll 1
+            for (int e = r0; e < r0 + cnt; e++) {
+                uint64_t ref[W];
 #pragma unroll
-        for (int k = 0; k < W; k++) ref[k] = R[(size_t)e * W + k];
-        for (int i = e + 1 + lane; i < n; i += 32) dup |= row_equal<W>(R + (size_t)i * W, ref);
+                for (int k = 0; k < W; k++) ref[k] = R[e * W + k];
+#pragma unroll 1
+                for (int i = lane; i < r0; i += 32) dup |= row_equal<W>(R + i * W, ref);
+            }
+        }
     }
     return __any_sync(0xffffffffu, dup);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Level B of the walk: a frame (compacted list of the n <= 64 terms still commuting with the group, their
+// residues mod the group) whose residues are LINEARLY INDEPENDENT over GF(2) cannot produce a dependent
+// term anywhere below it: no alive term can fall into a descendant group and no two can merge into one
+// coset.  Every descendant is then "group + a clique of the commutation graph of the list", its members are
+// exactly its generators and E_min = E_frame - sum |w|.  The warp (1) certifies independence by Gaussian
+// elimination across lanes (pivot row broadcast with shuffles, lowest-set-bit pivot, XOR elimination),
+// (2) builds the list's commutation bit-matrix with POPC + __ballot_sync, then (3) every lane walks the
+// cliques that start at "its" vertices privately with 64-bit masks.
+// Returns false (nothing counted) if the residues are dependent.
+constexpr int kMaxLB = 64;
+
+constexpr int kMaxDep = 6;
+
 template <int W>
-__global__ void __launch_bounds__(256)
+SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, int n, int nlow, int depth,
+                   uint32_t *hc, double &bw, uint64_t &bm, int lane)
+{
+    // own rows: entries lane and lane + 32 (o = original residue for commutation, e = elimination copy,
+    // cmb = which original residues have been XORed into e)
+    const bool two = n > 32;
+    uint64_t o0[W], o1[W], e0[W], e1[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+        o0[k] = lane < n ? R[lane * W + k] : 0;
+        o1[k] = lane + 32 < n ? R[(lane + 32) * W + k] : 0;
+        e0[k] = o0[k]; e1[k] = o1[k];
+    }
+    uint64_t cmb0 = lane < n ? (1ULL << lane) : 0, cmb1 = lane + 32 < n ? (1ULL << (lane + 32)) : 0;
+    uint64_t adj0 = 0, adj1 = 0;
+    uint64_t deps[kMaxDep];
+    int ndep = 0;
+    bool fail = false;
+#pragma unroll 1
+    for (int u = 0; u < n; u++) {
+        // commutation column u = row u (the form is symmetric): one ballot per 32 entries
+        uint64_t sw[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) sw[k] = swapzx(R[u * W + k]);
+        const bool c0 = lane < n && lane != u && !row_anticommute_sw<W>(o0, sw);
+        uint64_t col = __ballot_sync(0xffffffffu, c0);
+        if (two) {
+            const bool c1 = lane + 32 < n && lane + 32 != u && !row_anticommute_sw<W>(o1, sw);
+            col |= (uint64_t)__ballot_sync(0xffffffffu, c1) << 32;
+        }
+        if (lane == (u & 31)) { if (u < 32) adj0 = col; else adj1 = col; }
+        // elimination step: pivot row = current (reduced) copy of entry u
+        uint64_t cu[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) cu[k] = __shfl_sync(0xffffffffu, u < 32 ? e0[k] : e1[k], u & 31);
+        const uint64_t cmu = __shfl_sync(0xffffffffu, u < 32 ? cmb0 : cmb1, u & 31);
+        if (row_is_zero<W>(cu)) {                 // entry u is a combination of earlier ones: a dependency
+            if (ndep == kMaxDep) { fail = true; break; }
+#pragma unroll
+            for (int k = 0; k < kMaxDep; k++) if (k == ndep) deps[k] = cmu;
+            ndep++;
+            continue;
+        }
+        const int pv = row_lowbit<W>(cu);
+        if (lane > u && row_bit<W>(e0, pv)) {
+#pragma unroll
+            for (int k = 0; k < W; k++) e0[k] ^= cu[k];
+            cmb0 ^= cmu;
+        }
+        if (two && lane + 32 > u && row_bit<W>(e1, pv)) {
+#pragma unroll
+            for (int k = 0; k < W; k++) e1[k] ^= cu[k];
+            cmb1 ^= cmu;
+        }
+    }
+    if (fail) return false;
+    if (ndep > 0) {
+        // The residues are dependent, but a dependent term can only ever appear below this frame if the
+        // support of some kernel vector (XOR of recorded dependencies) is a CLIQUE of the commutation
+        // graph: the terms of a dependency inside one group commute pairwise.  Check all 2^ndep - 1.
+#pragma unroll 1
+        for (int gcode = 1; gcode < (1 << ndep); gcode++) {
+            uint64_t S = 0;
+#pragma unroll
+            for (int k = 0; k < kMaxDep; k++) if ((gcode >> k) & 1) S ^= deps[k];
+            const bool in0 = (S >> lane) & 1, in1 = (S >> (lane + 32)) & 1;
+            const bool bad = (in0 && (S & ~adj0 & ~(1ULL << lane)) != 0) || (in1 && (S & ~adj1 & ~(1ULL << (lane + 32))) != 0);
+            if (!__any_sync(0xffffffffu, bad)) return false;      // a commuting dependency: not certified
+        }
+    }
+    // keep only higher-position neighbours: cliques are built in ascending position order
+    AD[lane] = adj0 & ~((2ULL << lane) - 1ULL);
+    AD[lane + 32] = lane == 31 ? 0ULL : (adj1 & ~((2ULL << (lane + 32)) - 1ULL));
+    __syncwarp();
+
+    // lane l starts the cliques whose lowest vertex is nlow + l and, for lists with more than 32
+    // candidates, nlow + 63 - l (big subtrees are paired with small ones)
+    const int ncand = n - nlow;
+    uint64_t cand[kMaxLB], cm[kMaxLB];
+    double ws[kMaxLB];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const int f = pass == 0 ? nlow + lane : nlow + 63 - lane;
+        if (pass == 0 ? lane >= ncand : (63 - lane >= ncand || 63 - lane < 32)) continue;
+        const uint64_t c = AD[f];
+        const double w = WA[f];
+        hc[depth + 1] += 1;
+        if (c == 0) {
+            if (w > bw || (w == bw && (1ULL << f) < (bm & (0 - bm)))) { bw = w; bm = 1ULL << f; }
+            continue;
+        }
+        int d = 0;
+        cand[0] = c; ws[0] = w; cm[0] = 1ULL << f;
+        hc[depth + 2] += popc64(c);
+        while (d >= 0) {
+            const uint64_t cc = cand[d];
+            if (cc == 0) { d--; continue; }
+            const int v = ctz64(cc);
+            cand[d] = cc & (cc - 1);
+            const uint64_t nc = cc & AD[v];
+            const double nw = ws[d] + WA[v];
+            if (nc == 0) {
+                if (nw > bw || (nw == bw && f < ctz64(bm))) { bw = nw; bm = cm[d] | (1ULL << v); }
+            } else {
+                hc[depth + 3 + d] += popc64(nc);
+                cm[d + 1] = cm[d] | (1ULL << v);
+                d++;
+                cand[d] = nc; ws[d] = nw;
+            }
+        }
+    }
+    return true;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256, 3)
 k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned int *item_counter,
       int shard, int nshards, int cap, int smem_per_warp)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const unsigned ltmask = lanemask_lt();
     unsigned char *p = smem_raw + (size_t)warp * smem_per_warp;
     uint64_t *R = (uint64_t *)p;        p += (size_t)cap * W * 8;
-    uint64_t *B = (uint64_t *)p;        p += (size_t)kMaxG * W * 8;
+    double *WA = (double *)p;           p += (size_t)cap * 8;
+    uint64_t *B = (uint64_t *)p;        p += (size_t)32 * W * 8;
+    uint64_t *AD = (uint64_t *)p;       p += (size_t)64 * 8;
     double *fE = (double *)p;           p += (size_t)kMaxFrames * 8;
     int *fbase = (int *)p;              p += (size_t)kMaxFrames * 4;
     int *fa = (int *)p;                 p += (size_t)kMaxFrames * 4;
@@ -474,31 +613,64 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
 
     const unsigned gw = blockIdx.x * wpb + warp;
     BestRec *myrec = D.wbest + gw;
-    double bestE = myrec->valid ? myrec->E : 1e300;
+    double bestE = myrec->valid ? myrec->E : 1e300;     // 1e300: no incumbent
     int bestM = myrec->valid ? myrec->m : 0;
-    int haveBest = myrec->valid;
     for (int i = lane; i < bestM; i += 32) bestG[i] = myrec->g[i];
     for (int i = lane; i <= kMaxG; i += 32) hist[i] = 0;
     __syncwarp();
 
-    // record (path[0..len-1] ++ [last]) as the best tuple if E beats the incumbent
-#define SGS_TRY_BEST(Eval, len, lastTerm, withLast)                                                     \
-    do {                                                                                                \
-        bool better_ = !haveBest || (Eval) < bestE;                                                     \
-        if (!better_ && (Eval) == bestE) {                                                              \
-            if (withLast) path[len] = (uint16_t)(lastTerm);                                             \
-            __syncwarp();                                                                               \
-            better_ = tuple_before(path, (len) + ((withLast) ? 1 : 0), bestG, bestM);                   \
-        }                                                                                               \
-        if (better_) {                                                                                  \
-            haveBest = 1; bestE = (Eval); bestM = (len) + ((withLast) ? 1 : 0);                         \
-            __syncwarp();                                                                               \
-            for (int i_ = lane; i_ < (len); i_ += 32) bestG[i_] = path[i_];                             \
-            if ((withLast) && lane == 0) bestG[len] = (uint16_t)(lastTerm);                             \
-            __syncwarp();                                                                               \
-        }                                                                                               \
-    } while (0)
+    // record path[0..len) as the best tuple if Eval beats the incumbent (ties: tuple order)
+    auto try_best = [&](double Eval, int len) {
+        if (Eval > bestE) return;
+        __syncwarp();
+        if (Eval == bestE && !tuple_before(path, len, bestG, bestM)) return;
+        bestE = Eval; bestM = len;
+        for (int i = lane; i < len; i += 32) bestG[i] = path[i];
+        __syncwarp();
+    };
 
+    uint32_t hc[kMaxG + 4];                              // per-lane candidate counts by rank (level B)
+#pragma unroll 1
+    for (int i = 0; i < kMaxG + 4; i++) hc[i] = 0;
+
+    // run level B on the list at lb (n entries, candidates from position nlow, group rank `depth`,
+    // energy Ef); false if the residues are linearly dependent
+    auto run_level_b = [&](int lb, int n, int nlow, int depth, double Ef) -> bool {
+        double bw = -1.0;
+        uint64_t bm = 0;
+        if (!level_b<W>(R + lb * W, WA + lb, AD, n, nlow, depth, hc, bw, bm, lane)) return false;
+        // does any lane's best clique reach the incumbent?
+        const bool cand = bm != 0 && (Ef - bw) <= bestE;
+        if (__any_sync(0xffffffffu, cand)) {
+            // warp argmax of (weight, then lowest first vertex)
+            double w = bm ? bw : -1.0;
+            int key = bm ? ctz64(bm) : 64;
+            int src = lane;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const double ow = __shfl_xor_sync(0xffffffffu, w, d);
+                const int ok = __shfl_xor_sync(0xffffffffu, key, d);
+                const int os = __shfl_xor_sync(0xffffffffu, src, d);
+                if (ow > w || (ow == w && ok < key)) { w = ow; key = ok; src = os; }
+            }
+            const uint64_t mask = __shfl_sync(0xffffffffu, bm, src);
+            const double Eb = Ef - w;
+            if (Eb <= bestE) {
+                int len = depth;
+                if (lane == 0) {
+                    uint64_t mm = mask;
+                    int l2 = depth;
+                    while (mm) { path[l2++] = TT[lb + ctz64(mm)]; mm &= mm - 1; }
+                }
+                len = depth + popc64(mask);
+                __syncwarp();
+                try_best(Eb, len);
+            }
+        }
+        return true;
+    };
+
+#pragma unroll 1
     for (;;) {
         // ---- fetch the next subtree root owned by this shard ----
         unsigned it = 0;
@@ -512,66 +684,86 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         __syncwarp();
         for (int i = lane; i < m0; i += 32) path[i] = rec[2 + i];
         __syncwarp();
-        if (flags & kFlagUnclean) { push_slow(D, path, m0, flags, lane); continue; }
+        if ((flags & kFlagUnclean) || m0 > 32) { push_slow(D, path, m0, flags, lane); continue; }
 
-        // ---- root: basis of the m0 generators (bits only), alive list, residues ----
-        double E0 = 0.0;
-        for (int i = 0; i < m0; i++) {
-            uint64_t v[W];
-            const int t = path[i];
+        // ---- root: echelon basis of the m0 generators.  Lane i owns generator i; step b broadcasts
+        // the (already reduced) row b and clears its pivot bit from the later rows. ----
+        uint64_t bv[W];
+        double wsum = 0.0;
+        if (lane < m0) {
+            const int t = path[lane];
 #pragma unroll
-            for (int k = 0; k < W; k++) v[k] = D.rows[(size_t)t * W + k];
-            for (int b = 0; b < i; b++)
-                if (row_bit<W>(v, pivB[b])) {
+            for (int k = 0; k < W; k++) bv[k] = D.rows[t * W + k];
+            wsum = D.wabs[t];
+        } else {
 #pragma unroll
-                    for (int k = 0; k < W; k++) v[k] ^= B[b * W + k];
-                }
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < W; k++) B[i * W + k] = v[k];
-                pivB[i] = (uint8_t)row_lowbit<W>(v);
-            }
-            E0 -= D.wabs[t];
-            __syncwarp();
+            for (int k = 0; k < W; k++) bv[k] = 0;
         }
+#pragma unroll 1
+        for (int b = 0; b < m0; b++) {
+            uint64_t rb[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) rb[k] = __shfl_sync(0xffffffffu, bv[k], b);
+            const int pv = row_lowbit<W>(rb);
+            if (lane == b) pivB[b] = (uint8_t)pv;
+            if (lane > b && lane < m0 && row_bit<W>(bv, pv)) {
+#pragma unroll
+                for (int k = 0; k < W; k++) bv[k] ^= rb[k];
+            }
+        }
+        if (lane < m0) {
+#pragma unroll
+            for (int k = 0; k < W; k++) B[lane * W + k] = bv[k];
+        }
+        __syncwarp();
+        // E0 = -sum |w_g| in generator order (deterministic: same order on every shard)
+        double E0 = 0.0;
+#pragma unroll 1
+        for (int b = 0; b < m0; b++) E0 -= __shfl_sync(0xffffffffu, wsum, b);
+
         int a = alive_list(D, path, m0, TT, cap, lane);
         if (a < 0) { push_slow(D, path, m0, flags, lane); continue; }
         bool member = false;
+        int q0 = 0;
+        const int core0 = m0 ? (int)path[m0 - 1] : -1;
+#pragma unroll 1
         for (int i = lane; i < a; i += 32) {
             uint64_t v[W];
             const int t = TT[i];
 #pragma unroll
-            for (int k = 0; k < W; k++) v[k] = D.rows[(size_t)t * W + k];
-            for (int b = 0; b < m0; b++)
+            for (int k = 0; k < W; k++) v[k] = D.rows[t * W + k];
+#pragma unroll 1
+            for (int b = 0; b < m0; b++) {
                 if (row_bit<W>(v, pivB[b])) {
 #pragma unroll
                     for (int k = 0; k < W; k++) v[k] ^= B[b * W + k];
                 }
+            }
             member |= row_is_zero<W>(v);
+            q0 += (t <= core0);
 #pragma unroll
-            for (int k = 0; k < W; k++) R[(size_t)i * W + k] = v[k];
+            for (int k = 0; k < W; k++) R[i * W + k] = v[k];
+            WA[i] = D.wabs[t];
         }
         __syncwarp();
         if (__any_sync(0xffffffffu, member)) { push_slow(D, path, m0, flags | kFlagUnclean, lane); continue; }
-
-        if (lane == 0) hist[m0]++;
-        const int core0 = m0 ? (int)path[m0 - 1] : -1;
-        int q0 = 0;                                         // first list position above the core
-        for (int i = lane; i < a; i += 32) q0 += ((int)TT[i] <= core0);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) q0 += __shfl_xor_sync(0xffffffffu, q0, d);
-        if (q0 >= a) { SGS_TRY_BEST(E0, m0, 0, false); continue; }        // no extension: a leaf
+
+        if (lane == 0) hist[m0]++;
+        if (q0 >= a) { try_best(E0, m0); continue; }                      // no extension: a leaf
+        if (a <= 64 && m0 + (a - q0) < kMaxG && run_level_b(0, a, q0, m0, E0)) continue;
         if (has_duplicate<W>(R, a, lane)) {
-            SGS_TRY_BEST(E0, m0, 0, false);
+            try_best(E0, m0);
             push_slow(D, path, m0, flags | kFlagExpandOnly, lane);
             continue;
         }
         if (lane == 0) hist[m0 + 1] += (uint32_t)(a - q0);
 
-        // ---- depth-first walk; the top frame lives in registers ----
+        // ---- depth-first walk; the current frame (base, a, q, E) lives in registers ----
         int fd = 0, base = 0, q = q0;
         double E = E0;
+#pragma unroll 1
         for (;;) {
             if (q >= a) {                                   // frame exhausted: pop
                 if (fd == 0) break;
@@ -579,53 +771,65 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                 base = fbase[fd]; a = fa[fd]; q = fq[fd]; E = fE[fd];
                 continue;
             }
-            const int depth = m0 + fd;                      // rank of the frame's group
             const int jq = q++;
             uint64_t rj[W], sw[W];
 #pragma unroll
-            for (int k = 0; k < W; k++) { rj[k] = R[(size_t)(base + jq) * W + k]; sw[k] = swapzx(rj[k]); }
-            const int tj = TT[base + jq];
-            const double Ec = E - D.wabs[tj];
+            for (int k = 0; k < W; k++) { rj[k] = R[(base + jq) * W + k]; sw[k] = swapzx(rj[k]); }
+            const double Ec = E - WA[base + jq];
 
             // pass 1: which list entries commute with the new generator (POPC), and is any above it?
             int nal = 0, nlow = 0;
-            unsigned hiAny = 0;
-            for (int r0 = 0; r0 < a; r0 += 32) {
-                const int i = r0 + lane;
+            unsigned hiAny;
+            if (a <= 32) {
                 bool com = false;
-                if (i < a && i != jq) com = !row_anticommute_sw<W>(R + (size_t)(base + i) * W, sw);
+                if (lane < a && lane != jq) com = !row_anticommute_sw<W>(R + (base + lane) * W, sw);
                 const unsigned bal = __ballot_sync(0xffffffffu, com);
-                const int rel = jq - r0;                    // position of jq inside this row
-                if (rel >= 32) nlow += __popc(bal);
-                else if (rel >= 0) { nlow += __popc(bal & ((1u << rel) - 1u)); hiAny |= (rel == 31) ? 0u : (bal >> (rel + 1)); }
-                else hiAny |= bal;
-                nal += __popc(bal);
+                hiAny = (bal >> jq) >> 1;
+                nal = __popc(bal);
+                nlow = nal - __popc(hiAny);
+            } else {
+                hiAny = 0;
+#pragma unroll 1
+                for (int r0 = 0; r0 < a; r0 += 32) {
+                    const int i = r0 + lane;
+                    bool com = false;
+                    if (i < a && i != jq) com = !row_anticommute_sw<W>(R + (base + i) * W, sw);
+                    const unsigned bal = __ballot_sync(0xffffffffu, com);
+                    const int rel = jq - r0;                // position of jq inside this row
+                    if (rel >= 32) nlow += __popc(bal);
+                    else if (rel >= 0) { nlow += __popc(bal & ((1u << rel) - 1u)); hiAny |= (bal >> rel) >> 1; }
+                    else hiAny |= bal;
+                    nal += __popc(bal);
+                }
             }
-            if (hiAny == 0) {                               // child is a leaf of the tree
-                SGS_TRY_BEST(Ec, depth, tj, true);
+            const int depth = m0 + fd;                      // rank of the frame's group
+            if (hiAny == 0) {                               // the child has no extension: a leaf of the tree
+                if (Ec <= bestE) {
+                    if (lane == 0) path[depth] = TT[base + jq];
+                    try_best(Ec, depth + 1);
+                }
                 continue;
             }
-            if (lane == 0) path[depth] = (uint16_t)tj;
+            if (lane == 0) path[depth] = TT[base + jq];
             const int cb = base + a;
             if (cb + nal > cap || depth + 1 >= kMaxG) {     // out of list space: the exact kernel takes over
                 __syncwarp();
-                SGS_TRY_BEST(Ec, depth + 1, 0, false);
+                try_best(Ec, depth + 1);
                 push_slow(D, path, depth + 1, kFlagExpandOnly, lane);
                 continue;
             }
             // pass 2: child list = surviving entries, reduced by the new generator at its pivot bit
             const int pv = row_lowbit<W>(rj);
-            int off = 0;
+            int off = cb;
+#pragma unroll 1
             for (int r0 = 0; r0 < a; r0 += 32) {
                 const int i = r0 + lane;
                 bool com = false;
                 uint64_t v[W];
-                int t = 0;
                 if (i < a && i != jq) {
 #pragma unroll
-                    for (int k = 0; k < W; k++) v[k] = R[(size_t)(base + i) * W + k];
+                    for (int k = 0; k < W; k++) v[k] = R[(base + i) * W + k];
                     com = !row_anticommute_sw<W>(v, sw);
-                    t = TT[base + i];
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, com);
                 if (com) {
@@ -633,34 +837,46 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
 #pragma unroll
                         for (int k = 0; k < W; k++) v[k] ^= rj[k];
                     }
-                    const int pos = cb + off + __popc(bal & lanemask_lt());
+                    const int pos = off + __popc(bal & ltmask);
 #pragma unroll
-                    for (int k = 0; k < W; k++) R[(size_t)pos * W + k] = v[k];
-                    TT[pos] = (uint16_t)t;
+                    for (int k = 0; k < W; k++) R[pos * W + k] = v[k];
+                    TT[pos] = TT[base + i];
+                    WA[pos] = WA[base + i];
                 }
                 off += __popc(bal);
             }
             __syncwarp();
+            if (nal <= 64 && depth + 1 + (nal - nlow) < kMaxG && run_level_b(cb, nal, nlow, depth + 1, Ec)) continue;
             // residues pairwise distinct ⇒ every child of this child is a new group whose only members
             // are its generators.  Otherwise the exact kernel expands it.
-            if (has_duplicate<W>(R + (size_t)cb * W, nal, lane)) {
-                SGS_TRY_BEST(Ec, depth + 1, 0, false);
+            if (has_duplicate<W>(R + cb * W, nal, lane)) {
+                try_best(Ec, depth + 1);
                 push_slow(D, path, depth + 1, kFlagExpandOnly, lane);
                 continue;
             }
-            if (lane == 0) hist[depth + 2] += (uint32_t)(nal - nlow);
-            fbase[fd] = base; fa[fd] = a; fq[fd] = q; fE[fd] = E;
+            if (lane == 0) {
+                hist[depth + 2] += (uint32_t)(nal - nlow);
+                fbase[fd] = base; fa[fd] = a; fq[fd] = q; fE[fd] = E;
+            }
+            __syncwarp();
             fd++;
             base = cb; a = nal; q = nlow; E = Ec;
         }
     }
-#undef SGS_TRY_BEST
 
     __syncwarp();
-    if (haveBest) {
+    if (bestE < 1e300) {
         if (lane == 0) { myrec->E = bestE; myrec->m = bestM; myrec->valid = 1; }
         for (int i = lane; i < bestM; i += 32) myrec->g[i] = bestG[i];
     }
+#pragma unroll 1
+    for (int i = 0; i <= kMaxG; i++) {
+        unsigned v = hc[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) hist[i] += v;
+    }
+    __syncwarp();
     for (int i = lane; i <= kMaxG; i += 32)
         if (hist[i]) atomicAdd(&D.stats->hist[i], (unsigned long long)hist[i]);
 }

@@ -119,9 +119,7 @@ Status SparsePlan::Impl::init()
     qcap = (unsigned)std::min<unsigned long long>(want, 1ull << 25);
     slow_cap = 1u << 22;
     chunk = 1u << 16;
-    int c = 64;
-    while (c < T / 2 && c < 1024) c <<= 1;
-    dfs_cap = c;
+    dfs_cap = 128;     // re-derived per search from the measured branching of the last expanded level
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -243,15 +241,22 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
     };
 
     // ---- breadth-first expansion of the top of the tree into subtree roots ----
-    const unsigned target = opts.expand_depth > 0 ? 0xffffffffu : (1u << 19) * (unsigned)std::min(nshards, 8);
-    const int dmax = opts.expand_depth > 0 ? opts.expand_depth : 8;
+    // Expand until (a) there are enough roots to keep every resident warp of every shard busy under
+    // dynamic fetch and (b) a root's list of alive terms is expected to fit the 64-entry level-B walk
+    // (alive(depth d) ~ ratio_{d-1} * d / 2 for clique-like growth), as far as the queue capacity allows.
+    const unsigned long long min_items = 8ull * c.sms * 24 * (unsigned long long)nshards;
+    const int dmax = opts.expand_depth > 0 ? std::min(opts.expand_depth, 24) : 10;
     uint16_t *cur = c.qA, *nxt = c.qB;
     unsigned count = 1;
     double ratio = (double)std::max(T, 1);
     int depth = 0;
     SparseStats hs{};
     unsigned hcnt[4];
-    while (count > 0 && depth < dmax && count < target) {
+    while (count > 0 && depth < dmax) {
+        if (opts.expand_depth <= 0) {
+            const double est_alive = ratio * std::max(depth, 1) / 2.0;
+            if (depth > 0 && count >= min_items && est_alive <= 64.0) break;
+        }
         const double bound = (double)count * std::min<double>((double)std::max(T, 1), ratio);
         if (bound > (double)qcap) break;
         SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, sizeof(unsigned), st));
@@ -270,16 +275,22 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
 
     // ---- the hot kernel: depth-first enumeration below every subtree root ----
     if (count > 0) {
-        const size_t pw = dfs_smem_bytes<W_>(dfs_cap);
-        const int wpb = 8;
-        SGS_CUDA_TRY(cudaFuncSetAttribute(k_dfs<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pw * wpb)));
-        int occ = 1;
-        SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dfs<W_>, wpb * 32, pw * wpb));
-        occ = std::max(1, occ);
-        unsigned grid = (unsigned)std::min<long long>((long long)c.sms * occ, c.nwbest / wpb);
-        grid = std::min<unsigned>(grid, (count + wpb - 1) / wpb);
+        // list arena per warp: a root holds about `ratio` alive terms (the measured mean number of
+        // children of the last expanded level) and the levels below it halve; 6x leaves room for spread
+        int cap = 128;
+        while (cap < 6.0 * ratio && cap < 2048) cap <<= 1;
+        dfs_cap = cap;
+        const size_t dfs_pw = dfs_smem_bytes<W_>(dfs_cap);
+        int dfs_wpb = 8;
+        while (dfs_wpb > 1 && dfs_pw * dfs_wpb > 200 * 1024) dfs_wpb >>= 1;
+        SGS_CUDA_TRY(cudaFuncSetAttribute(k_dfs<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dfs_pw * dfs_wpb)));
+        int dfs_occ = 1;
+        SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dfs_occ, k_dfs<W_>, dfs_wpb * 32, dfs_pw * dfs_wpb));
+        dfs_occ = std::max(1, dfs_occ);
+        const unsigned dfs_maxgrid = (unsigned)std::min<long long>((long long)c.sms * dfs_occ, c.nwbest / dfs_wpb);
+        const unsigned grid = std::min<unsigned>(dfs_maxgrid, (count + dfs_wpb - 1) / dfs_wpb);
         SGS_CUDA_TRY(cudaEventRecord(c.evh0, st));
-        k_dfs<W_><<<grid, wpb * 32, pw * wpb, st>>>(D, cur, count, c.counters + 1, c.shard, nshards, dfs_cap, (int)pw);
+        k_dfs<W_><<<grid, dfs_wpb * 32, dfs_pw * dfs_wpb, st>>>(D, cur, count, c.counters + 1, c.shard, nshards, dfs_cap, (int)dfs_pw);
         c.launches++;
         SGS_CUDA_TRY(cudaGetLastError());
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));

