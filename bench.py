@@ -1,0 +1,251 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: stabilizer candidates evaluated per second.
+
+Workload (BASELINE.json configs[3], the one quoted for 1/2/4/8 GPUs): the synthetic sparse random Pauli
+Hamiltonian n=24, T=300 (tests/gen_hamiltonians.sparse_text(24, 300, 0)); one STEP = one complete exact
+ground-state search of it (every closed commuting group enumerated and minimised over signs, ~8.1e7
+candidates), sharded over the N GPUs and combined by one NCCL all-gather/all-reduce inside libsgs.so.
+Total work is fixed as N grows → "scaling": "strong".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+value  = candidates / (max over ranks of the CUDA-event time of the search kernels), term tables resident
+e2e    = the same through the public one-shot C-ABI call with HOST buffers (sgs_ham_from_arrays +
+         sgs_sparse_search: device allocation, upload, search, result download inside the timed region)
+--impl reference times the CPU implementation (the oracle port of the reference's FullState::evolve,
+since cpp/ needs Eigen + Boost which are not in the image) on a bounded sample of the same instance.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+N_QUBITS, N_TERMS, SEED = 24, 300, 0
+WORKLOAD = f"sparse random Pauli Hamiltonian n={N_QUBITS} T={N_TERMS} seed={SEED} (BASELINE configs[3]), full enumeration"
+
+
+def survey_ops(rank_hist, T, n):
+    """ALGORITHMIC 32-bit integer ops of a from-scratch evaluation of every candidate:
+    ops(m) = 2*T*m*W32 + m^2*W32/2, W32 = ceil(2n/32)."""
+    W32 = (2 * n + 31) // 32
+    return sum(c * (2 * T * m * W32 + m * m * W32 / 2.0) for m, c in rank_hist.items())
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.device}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 5 + i and r[5 + i].lower().startswith('active'):
+                    reasons.add(nm)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of FullState::evolve (cpp/state.cpp:636-687) with all host threads, each
+    step a bounded sample (wall-time limited) of the same n=24/T=300 search."""
+    if rank != 0:
+        return
+    import gen_hamiltonians as G
+    import oracle_py as O
+    text = G.sparse_text(N_QUBITS, N_TERMS, SEED)
+    cores = os.cpu_count() or 1
+    sample_s = 8.0
+    for _ in range(min(args.warmup, 1)):
+        O.sparse_sample(text=text, threads=cores, seconds=1.0)
+    cand, secs = 0, 0.0
+    for _ in range(args.steps):
+        r = O.sparse_sample(text=text, threads=cores, seconds=sample_s)
+        cand += r['candidates']
+        secs += r['seconds']
+    value = cand / secs
+    line = dict(metric='stabilizer candidates evaluated/sec', value=value, unit='candidates/s', n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * secs / args.steps, higher_is_better=True,
+                scaling='strong', vs_baseline=None, dtype='u64 bit algebra + f64 energies', data='synthetic',
+                impl='reference', config=dict(workload=WORKLOAD),
+                cpu_baseline=dict(value=value, unit='candidates/s', cores=cores, kind='port',
+                                  sample=f'{sample_s:.0f} s wall-time-bounded include-first walk of the same instance per step '
+                                         '(oracle/sparse.c, OpenMP tasks); cpp/ of the reference needs Eigen+Boost, absent here'),
+                e2e=dict(value=value, unit='candidates/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import gen_hamiltonians as G
+    import stabilizer_gs_b200 as S
+    C = S._capi
+    L = C.lib()
+    text = G.sparse_text(N_QUBITS, N_TERMS, SEED)
+    ham = S.HamHandle.from_text(text)
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # the library owns its own NCCL communicator: rank 0 creates the id, torch.distributed is only the courier
+        ids = [C.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nccl_id = ids[0]
+    device = local_rank if world > 1 else 0
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peaks = C.measure_int_peaks(device) if rank == 0 else None
+    plan = S.SparsePlan(ham, device=device, rank=rank, world=world, nccl_id=nccl_id)
+    for _ in range(max(args.warmup, 3)):
+        C.flush_l2(device)
+        plan.run()
+    sampler = ClockSampler(device) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    dev_s, hot_s, wall0, launches, res = 0.0, 0.0, time.perf_counter(), 0, None
+    for _ in range(args.steps):
+        C.flush_l2(device)            # untimed: term tables start each step cold in L2, resident in HBM
+        res = plan.run()
+        dev_s += res['seconds_device']
+        hot_s += res['seconds_hot_kernel']
+        launches += res['kernel_launches']
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    dev_s = allmax(dev_s)
+    hot_s = allmax(hot_s)
+    plan.close()
+
+    # ---- e2e: the one-shot public call with host buffers, everything inside the timed region ----
+    rows, w, b, e = ham.terms()
+    T, W = ham.nterms, ham.words
+    zx = (ctypes.c_uint64 * (T * W))(*[x for r in rows for x in r])
+    wv = (ctypes.c_double * T)(*w)
+    o, keep = C.make_opts(device=device, rank=rank, world=world, nccl_id=nccl_id)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def one_shot():
+        hp = ctypes.c_void_p()
+        C.check(L.sgs_ham_from_arrays(N_QUBITS, N_QUBITS, T, zx, wv, None, None, ctypes.byref(hp)))
+        r = C.Result()
+        C.check(L.sgs_sparse_search(hp, ctypes.byref(o), ctypes.byref(r)))
+        out = (r.energy, int(r.candidates), int(r.kernel_launches))
+        L.sgs_result_free(ctypes.byref(r))
+        L.sgs_ham_free(hp)
+        return out
+
+    one_shot()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        Ee, cand_e, ln = one_shot()
+    barrier()
+    e2e_s = allmax(time.perf_counter() - t0)
+
+    if rank == 0:
+        cand = res['candidates']
+        hist = res['rank_hist']
+        ops = survey_ops(hist, T, N_QUBITS)
+        h2d = T * W * 8 + T * 8 * 2 + T * 4
+        d2h = res['m'] * W * 8 + res['m'] + T + 8 + 8 * 65
+        peak = peaks['lop3_ops_per_s']
+        achieved = ops / (hot_s / args.steps)
+        line = dict(metric='stabilizer candidates evaluated/sec', value=cand / (dev_s / args.steps), unit='candidates/s',
+                    n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=1e3 * dev_s / args.steps,
+                    higher_is_better=True, scaling='strong', vs_baseline=None,
+                    dtype='u64 bit algebra + f64 energies', data='synthetic',
+                    config=dict(workload=WORKLOAD, candidates_per_step=cand, parallelism=f'shard{world}',
+                                l2='flushed between steps (512 MB memset); inputs are L2-resident by design (KBs)',
+                                energy=res['energy'], rank=res['m'], wall_ms_per_step=1e3 * wall / args.steps),
+                    time_to_ground_state_ms=1e3 * e2e_s / e2e_steps,
+                    e2e=dict(value=cand_e / (e2e_s / e2e_steps), unit='candidates/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             ms_per_step=1e3 * e2e_s / e2e_steps, steps=e2e_steps,
+                             call='sgs_ham_from_arrays + sgs_sparse_search (host buffers in, host result out)'),
+                    gpu_launches=launches,
+                    roofline=dict(bound='int_alu', achieved=achieved / 1e12, peak=peak / 1e12, unit='Tops/s (32-bit LOP3/IADD/POPC)',
+                                  frac=achieved / peak, traffic=None,
+                                  note='achieved = SURVEY §8(d) ALGORITHMIC ops of a from-scratch evaluation of every candidate '
+                                       '(2*T*m*W32 + m^2*W32/2 each) / k_dfs time; the kernel evaluates candidates incrementally so frac > 1 '
+                                       'is expected — executed-instruction pipe utilisation is in profiles/; peak = LOP3 issue rate measured '
+                                       'in this run (sgs_measure_int_peaks); HBM traffic is ~0 by design (tables are KBs)',
+                                  popc_peak=peaks['popc_ops_per_s'] / 1e12, implied_sm_mhz=peaks['sm_mhz'],
+                                  hot_kernel='k_dfs', hot_kernel_ms=1e3 * hot_s / args.steps),
+                    clocks=clocks)
+        # CPU baseline (rank 0, N=1 only): bounded sample of the same workload with the oracle port
+        if world == 1:
+            import oracle_py as O
+            cores = os.cpu_count() or 1
+            r = O.sparse_sample(text=text, threads=cores, seconds=12.0)
+            line['cpu_baseline'] = dict(value=r['candidates'] / r['seconds'], unit='candidates/s', cores=cores, kind='port',
+                                        sample='12 s wall-time-bounded include-first walk of the same n=24/T=300 instance '
+                                               '(oracle/sparse.c = restatement of FullState::evolve, OpenMP tasks)')
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -175,6 +175,8 @@ const char *sgs_version(void);
 /* integer-pipe issue-rate microbenchmarks (roofline denominators):
  * 32-bit LOP3 and POPC ops per second over the whole chip at the running clock */
 int sgs_measure_int_peaks(int device, double *lop3_ops_per_s, double *popc_ops_per_s, double *sm_mhz);
+/* benchmark hygiene: overwrite a buffer larger than the L2 (evicts the term tables between timed steps) */
+int sgs_device_flush_l2(int device);
 
 #ifdef __cplusplus
 }

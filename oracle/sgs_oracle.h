@@ -73,6 +73,8 @@ void ores_free(ores *r);
 
 /* sparse search: FullState::evolve (cpp/state.cpp:636-687).  threads<=1 → serial like the reference. */
 ores *oracle_sparse(const oham *H, int threads);
+/* same walk, stopped after max_leaves leaves or `seconds` (bench.py's bounded CPU sample) */
+ores *oracle_sparse_sample(const oham *H, int threads, uint64_t max_leaves, double seconds);
 /* k-local DP: StateMachine (cpp/state.cpp:445-550) + generate_Sright_all (:218-238) */
 ores *oracle_klocal(const oham *H, int threads);
 

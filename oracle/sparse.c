@@ -45,6 +45,10 @@ typedef struct {
     oste best;
     int nbest, *bestseq;
     int par_depth;
+    /* bounded sampling (bench.py cpu_baseline): stop after max_leaves leaves or at the deadline */
+    uint64_t max_leaves;
+    double deadline;
+    volatile int stop;
 } octx;
 
 static void ofull_free(ofull *s) { oste_free(&s->st); free(s->p); free(s->ex); free(s->inc); }
@@ -113,6 +117,8 @@ static int seq_before(const int *a, int na, const int *b, int nb)
     }
 }
 
+static double now_s(void);
+
 static void leaf(octx *c, const ofull *s)
 {
     int m = s->st.s.m;
@@ -126,6 +132,7 @@ static void leaf(octx *c, const ofull *s)
         c->sum_2m += (double)sz;
         int better = !c->have || mn < c->bestE ||
                      (mn == c->bestE && seq_before(s->inc, s->ninc, c->bestseq, c->nbest));
+        if ((c->max_leaves && c->candidates >= c->max_leaves) || (c->deadline > 0 && now_s() > c->deadline)) c->stop = 1;
         if (better) {
             if (c->have) oste_free(&c->best);
             oste_copy(&c->best, &s->st);
@@ -139,6 +146,7 @@ static void leaf(octx *c, const ofull *s)
 /* FullState::evolve (cpp/state.cpp:636-662) as a recursion; takes ownership of s */
 static void walk(octx *c, ofull *s, int depth)
 {
+    if (c->stop) { ofull_free(s); free(s); return; }
     if (s->np == 0) { leaf(c, s); ofull_free(s); free(s); return; }
     int t = s->p[0];
     ofull *inc = (ofull *)malloc(sizeof(ofull)), *exc = (ofull *)malloc(sizeof(ofull));
@@ -163,7 +171,7 @@ static double now_s(void)
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
-ores *oracle_sparse(const oham *H, int threads)
+static ores *oracle_sparse_impl(const oham *H, int threads, uint64_t max_leaves, double seconds)
 {
     double t0 = now_s();
     int T = H->T;
@@ -176,6 +184,8 @@ ores *oracle_sparse(const oham *H, int threads)
     c.P = P; c.w = w;
     c.bestseq = (int *)malloc(sizeof(int) * (T + 1));
     c.par_depth = threads > 1 ? 12 : 0;
+    c.max_leaves = max_leaves;
+    c.deadline = seconds > 0 ? t0 + seconds : 0.0;
 
     ofull *root = (ofull *)malloc(sizeof(ofull));
     oste_init(&root->st, 0, H->n, 0);          /* FullState ctor, cpp/state.cpp:555-564 */
@@ -214,4 +224,13 @@ ores *oracle_sparse(const oham *H, int threads)
     free(c.bestseq); free(P); free(w);
     r->seconds = now_s() - t0;
     return r;
+}
+
+ores *oracle_sparse(const oham *H, int threads) { return oracle_sparse_impl(H, threads, 0, 0.0); }
+
+/* bounded sample of the same search: stops after max_leaves leaves or `seconds` of wall time; the
+ * result's `candidates` / `seconds` give the CPU rate, its energy is only the best of the sample */
+ores *oracle_sparse_sample(const oham *H, int threads, uint64_t max_leaves, double seconds)
+{
+    return oracle_sparse_impl(H, threads, max_leaves, seconds);
 }

@@ -93,6 +93,7 @@ SYMBOLS = {
     'sgs_device_count': (C.c_int, []),
     'sgs_last_error': (C.c_char_p, []),
     'sgs_version': (C.c_char_p, []),
+    'sgs_device_flush_l2': (C.c_int, [C.c_int]),
     'sgs_measure_int_peaks': (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -279,6 +280,10 @@ def nccl_unique_id():
     buf = C.create_string_buffer(SGS_NCCL_ID_BYTES)
     check(lib().sgs_nccl_unique_id(buf))
     return buf.raw
+
+
+def flush_l2(device=0):
+    check(lib().sgs_device_flush_l2(device))
 
 
 def measure_int_peaks(device=0):

@@ -272,6 +272,13 @@ int sgs_nccl_unique_id(void *id_out)
 
 int sgs_device_count(void) { return device_count(); }
 
+int sgs_device_flush_l2(int device)
+{
+    SGS_GUARD_BEGIN
+    return done(device_flush_l2(device));
+    SGS_GUARD_END
+}
+
 int sgs_measure_int_peaks(int device, double *lop3, double *popc, double *sm_mhz)
 {
     SGS_GUARD_BEGIN

@@ -231,6 +231,19 @@ Status pauli_commute_batch(int device, int n, int B, const uint64_t *a, const ui
     return Status();
 }
 
+Status device_flush_l2(int device)
+{
+    static void *buf[16] = {nullptr};
+    const size_t bytes = 512ull << 20;       // > 126 MB L2
+    if (device < 0 || device >= 16) return Status::fail(SGS_ERR_ARG, "device out of range");
+    SGS_CUDA_TRY(cudaSetDevice(device));
+    if (!buf[device]) SGS_CUDA_TRY(cudaMalloc(&buf[device], bytes));
+    static int tick = 0;
+    SGS_CUDA_TRY(cudaMemset(buf[device], ++tick & 0xff, bytes));
+    SGS_CUDA_TRY(cudaDeviceSynchronize());
+    return Status();
+}
+
 Status measure_int_peaks(int device, double *lop3, double *popc, double *sm_mhz)
 {
     SGS_CUDA_TRY(cudaSetDevice(device));
@@ -264,7 +277,9 @@ Status measure_int_peaks(int device, double *lop3, double *popc, double *sm_mhz)
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (lop3) *lop3 = best[0];
     if (popc) *popc = best[1];
-    if (sm_mhz) *sm_mhz = mhz;
+    // running SM clock implied by the LOP3 rate: 64 INT32 lanes per SM per clock (alu pipe, rt_SMSP = 2)
+    (void)mhz;
+    if (sm_mhz) *sm_mhz = best[0] / ((double)prop.multiProcessorCount * 64.0) / 1e6;
     return Status();
 }
 

@@ -12,6 +12,7 @@ Status group_canonicalize(int device, int n, int m, uint64_t *rows, int8_t *sign
 Status group_energy(int device, int n, int m, const uint64_t *rows, const int8_t *signs, int B, const uint64_t *P,
                     const int8_t *Psigns, int8_t *out);
 Status pauli_commute_batch(int device, int n, int B, const uint64_t *a, const uint64_t *b, uint8_t *out);
+Status device_flush_l2(int device);
 Status measure_int_peaks(int device, double *lop3_ops_per_s, double *popc_ops_per_s, double *sm_mhz);
 
 }  // namespace sgs

@@ -74,6 +74,8 @@ def lib():
         L.oham_free.argtypes = [C.POINTER(OHam)]
         L.oracle_sparse.restype = C.POINTER(ORes)
         L.oracle_sparse.argtypes = [C.POINTER(OHam), C.c_int]
+        L.oracle_sparse_sample.restype = C.POINTER(ORes)
+        L.oracle_sparse_sample.argtypes = [C.POINTER(OHam), C.c_int, C.c_uint64, C.c_double]
         L.oracle_klocal.restype = C.POINTER(ORes)
         L.oracle_klocal.argtypes = [C.POINTER(OHam), C.c_int]
         L.ores_free.argtypes = [C.POINTER(ORes)]
@@ -144,6 +146,17 @@ def _res(H, r, klocal):
 def sparse(text=None, path=None, threads=1):
     H = _load(text, path)
     r = lib().oracle_sparse(H, threads)
+    try:
+        return _res(H, r, False)
+    finally:
+        lib().ores_free(r)
+        lib().oham_free(H)
+
+
+def sparse_sample(text=None, path=None, threads=1, max_leaves=0, seconds=0.0):
+    """bounded sample of the sparse walk: returns candidates visited and seconds"""
+    H = _load(text, path)
+    r = lib().oracle_sparse_sample(H, threads, max_leaves, seconds)
     try:
         return _res(H, r, False)
     finally:

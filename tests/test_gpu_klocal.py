@@ -1,0 +1,116 @@
+"""GPU parity tests of the k-local DP and the periodic chain search (through the C ABI) against the CPU
+oracle and the golden vectors of the Python reference."""
+import glob
+import hashlib
+import json
+import os
+
+import pytest
+
+import gen_hamiltonians as G
+import oracle_py as O
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+KLOCAL = sorted(f for f in glob.glob(os.path.join(GOLDEN, '*.json')) if 'klocal' in json.load(open(f)))
+
+
+def _name(p):
+    return os.path.basename(p)[:-5]
+
+
+def sgs():
+    import stabilizer_gs_b200 as S
+    return S
+
+
+@pytest.mark.parametrize('path', KLOCAL, ids=_name)
+def test_golden_python_reference(path):
+    S = sgs()
+    g = json.load(open(path))
+    ref = g['klocal']
+    n = g['n']
+    r = S.klocal_search(S.HamHandle.load(os.path.join(GOLDEN, g['file'])))
+    assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12)
+    assert r['generators'] == ref['generators']
+    assert r['term_signs'] == ref['term_signs']
+    assert r['sright_counts'] == [ref['sright_counts'][str(m)] for m in range(n + 1)]
+    assert r['states_per_site'] == ref['states_per_site']
+    assert r['transitions'] == ref['transitions']
+
+
+def test_config3_golden():
+    """BASELINE config 3: gen_klocal(64,4,3,0): E = -30.9918743342, 47 generators, md5 of the printed group"""
+    S = sgs()
+    r = S.klocal_search(S.HamHandle.from_text(G.klocal_text(64, 4, 3, 0)))
+    assert r['energy'] == pytest.approx(-30.9918743342, abs=1e-9)
+    assert len(r['generators']) == 47
+    line = 'qubit 0-63 size (47,) ' + ' '.join(r['generators']) + '\n'
+    assert hashlib.md5(line.encode()).hexdigest() == 'a715783786513531b60e5877f72a9f30'
+    assert max(r['states_per_site']) == 113 and r['transitions'] == 2850
+
+
+@pytest.mark.parametrize('n,k,per,seed', [(8, 2, 2, 0), (10, 3, 2, 1), (10, 3, 3, 2), (12, 4, 2, 3), (9, 4, 4, 4), (14, 3, 3, 5),
+                                          (8, 4, 6, 3), (16, 5, 2, 6), (20, 4, 3, 7), (6, 6, 5, 8), (12, 1, 2, 9)])
+def test_random_vs_oracle(n, k, per, seed):
+    S = sgs()
+    per = min(per, 4 ** k - 1)
+    text = G.klocal_text(n, k, per, seed)
+    ref = O.klocal(text=text, threads=4)
+    r = S.klocal_search(S.HamHandle.from_text(text))
+    assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12)
+    assert r['generators'] == ref['generators']
+    assert r['term_signs'] == ref['term_signs']
+    assert r['sright_counts'] == ref['sright_counts']
+    assert r['states_per_site'] == ref['states_per_site']
+    assert r['transitions'] == ref['transitions']
+
+
+@pytest.mark.parametrize('n,k,per,seed', [(8, 3, 2, 0), (10, 3, 2, 1), (9, 2, 2, 4)])
+def test_klocal_equals_sparse_on_gpu(n, k, per, seed):
+    S = sgs()
+    text = G.klocal_text(n, k, per, seed)
+    a = S.sparse_search(S.HamHandle.from_text(text))
+    b = S.klocal_search(S.HamHandle.from_text(text))
+    assert a['energy'] == pytest.approx(b['energy'], rel=1e-10)
+    assert a['generators'] == b['generators'] and a['term_signs'] == b['term_signs']
+
+
+def test_full_size_properties_n64_k4_dense_windows():
+    """n = 64, k = 4 with 6 terms per window: no oracle golden; E must equal sum w * sign and the signs must be
+    those of a commuting group built from Hamiltonian terms"""
+    S = sgs()
+    text = G.klocal_text(64, 4, 6, 1)
+    H = S.HamHandle.from_text(text)
+    r = S.klocal_search(H)
+    rows, w, b, e = H.terms()
+    assert r['energy'] == pytest.approx(sum(wi * si for wi, si in zip(w, r['term_signs'])), rel=1e-10)
+    ref = O.klocal(text=text, threads=8)
+    assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10)
+    assert r['generators'] == ref['generators'] and r['states_per_site'] == ref['states_per_site']
+
+
+def test_periodic_matches_python_reference():
+    S = sgs()
+    g = json.load(open(os.path.join(GOLDEN, 'periodic_example.json')))['periodic']
+    r = S.klocal_periodic(os.path.join(ROOT, 'examples', 'hamiltonian_periodic.txt'), cmax=g['cmax'], c=g['c'])
+    assert (r['l'], r['k'], r['n'], r['nterms']) == (g['l'], g['k'], g['n'], g['nterms'])
+    assert r['sright_log'] == g['sright_log']
+    assert r['fixed_point_sizes'] == g['fixed_point_sizes']
+    key = lambda o: (o['energy'], o['begin'], o['end'], o['generators'])
+    assert sorted(map(key, r['results'])) == sorted(map(key, g['results']))
+    assert min(o['energy'] for o in r['results']) / g['c'] == pytest.approx(g['min_energy_per_period'])
+
+
+def test_periodic_vs_oracle_other_cells(tmp_path):
+    S = sgs()
+    cases = ["1 2\n -1.0 ZZ 0 1\n -0.5 X 0\n", "2 3\n -1.0 XZX 0 1 2\n 0.7 YY 1 2\n -0.3 ZZ 0 1\n", "1 3\n 1.0 XZX 0 1 2\n -1.0 YY 1 2\n"]
+    for i, text in enumerate(cases):
+        p = tmp_path / f'per{i}.txt'
+        p.write_text(text)
+        ref = O.periodic(str(p), cmax=10, c=2)
+        r = S.klocal_periodic(str(p), cmax=10, c=2)
+        assert r['sright_log'] == ref['sright_log'] and r['fixed_point_sizes'] == ref['fixed_point_sizes']
+        key = lambda o: (round(o['energy'], 9), o['begin'], o['end'], o['generators'])
+        assert sorted(map(key, r['results'])) == sorted(map(key, ref['results']))
