@@ -123,6 +123,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if world > 1:
+        import torch  # noqa: F401  (first, so that its bundled NCCL is the one the process uses)
     import gen_hamiltonians as G
     import stabilizer_gs_b200 as S
     C = S._capi

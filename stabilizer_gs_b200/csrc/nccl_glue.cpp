@@ -1,11 +1,72 @@
 // nccl_glue.cpp — see nccl_glue.hpp.
 #include "nccl_glue.hpp"
 
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include <cstring>
 
 namespace sgs {
+
+// NCCL is bound at run time, not link time: inside a process that already carries an NCCL (e.g. a
+// torch.distributed launcher, whose bundled libnccl.so.2 is newer than the system one) the loaded copy is
+// used; otherwise libnccl.so.2 is opened on first use.  Single-GPU searches never touch NCCL.
+namespace {
+struct NcclApi {
+    decltype(&::ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&::ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&::ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&::ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&::ncclGroupStart) GroupStart = nullptr;
+    decltype(&::ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&::ncclAllGather) AllGather = nullptr;
+    decltype(&::ncclAllReduce) AllReduce = nullptr;
+    decltype(&::ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+NcclApi &api()
+{
+    static NcclApi a;
+    static bool tried = false;
+    if (tried) return a;
+    tried = true;
+    void *h = nullptr;
+    if (!dlsym(RTLD_DEFAULT, "ncclGetUniqueId")) {
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { a.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return a; }
+    }
+    auto sym = [&](const char *name) -> void * {
+        void *p = h ? dlsym(h, name) : dlsym(RTLD_DEFAULT, name);
+        if (!p) a.why = std::string("NCCL symbol missing: ") + name;
+        return p;
+    };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+    a.CommInitAll = (decltype(a.CommInitAll))sym("ncclCommInitAll");
+    a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+    a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+    a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+    a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitAll && a.CommInitRank && a.CommDestroy && a.GroupStart && a.GroupEnd && a.AllGather &&
+           a.AllReduce && a.GetErrorString;
+    return a;
+}
+}  // namespace
+
+#define ncclGetUniqueId api().GetUniqueId
+#define ncclCommInitAll api().CommInitAll
+#define ncclCommInitRank api().CommInitRank
+#define ncclCommDestroy api().CommDestroy
+#define ncclGroupStart api().GroupStart
+#define ncclGroupEnd api().GroupEnd
+#define ncclAllGather api().AllGather
+#define ncclAllReduce api().AllReduce
+#define ncclGetErrorString api().GetErrorString
+#define SGS_NEED_NCCL() do { if (!api().ok) return Status::fail(SGS_ERR_NCCL, api().why.empty() ? "NCCL unavailable" : api().why); } while (0)
 
 struct NcclWorld::Impl {
     std::vector<ncclComm_t> comms;
@@ -23,7 +84,8 @@ NcclWorld::NcclWorld() : impl_(new Impl()) {}
 
 NcclWorld::~NcclWorld()
 {
-    for (size_t i = 0; i < impl_->comms.size(); i++) {
+    for (size_t i = 0; api().ok && i < impl_->comms.size(); i++) {
+        if (!impl_->comms[i]) continue;
         cudaSetDevice(impl_->devices[i]);
         ncclCommDestroy(impl_->comms[i]);
     }
@@ -33,6 +95,7 @@ NcclWorld::~NcclWorld()
 Status NcclWorld::unique_id(void *out128)
 {
     static_assert(sizeof(ncclUniqueId) <= SGS_NCCL_ID_BYTES, "ncclUniqueId larger than SGS_NCCL_ID_BYTES");
+    SGS_NEED_NCCL();
     ncclUniqueId id;
     SGS_NCCL_TRY(ncclGetUniqueId(&id));
     memset(out128, 0, SGS_NCCL_ID_BYTES);
@@ -42,6 +105,7 @@ Status NcclWorld::unique_id(void *out128)
 
 Status NcclWorld::init(const std::vector<int> &devices, int rank, int world, const void *unique_id)
 {
+    SGS_NEED_NCCL();
     impl_->devices = devices;
     const int ng = (int)devices.size();
     impl_->comms.assign(ng, nullptr);

@@ -164,6 +164,13 @@ SGS_D int alive_list(const SparseDev &D, const uint16_t *g, int m, uint16_t *tt,
 // ------------------------------------------------------------------------------------------------
 // k_general: exact from-scratch evaluation of one closed commuting group per warp.
 // smem per warp (bytes): see general_smem_bytes().
+__host__ __device__ inline int general_hash_slots(int T)
+{
+    int s = 64;
+    while (s < 2 * T) s <<= 1;
+    return s;
+}
+
 template <int W>
 __host__ __device__ inline size_t general_smem_bytes(int T)
 {
@@ -177,14 +184,59 @@ __host__ __device__ inline size_t general_smem_bytes(int T)
     b += (size_t)((T + 3) / 4) * 8;  // alive term indices (u16)
     b += kMaxG * 2 + 64;             // pivots, phases, vpos
     b += kMaxG * 2;                  // best tuple
-    b += (kMaxG + 1) * 4 + 4;        // hist
+    b += (kMaxG + 1) * 4 + 8;        // hist
+    b += (size_t)general_hash_slots(T) * 4;   // residue hash table (coset classes)
+    b += (size_t)((T + 7) / 8) * 8;           // class-has-another-member flags
     return (b + 15) & ~(size_t)15;
+}
+
+// Coset classes of the alive residues in O(na): an open-addressing table maps each distinct residue to the
+// LOWEST list index carrying it.  leader[i] = that index; multi[j] != 0 iff class j has more than one member.
+template <int W>
+SGS_D uint32_t residue_hash(const uint64_t *r)
+{
+    uint64_t h = 0x9E3779B97F4A7C15ULL;
+#pragma unroll
+    for (int k = 0; k < W; k++) { h ^= r[k]; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 29; }
+    return (uint32_t)(h ^ (h >> 32));
+}
+
+template <int W>
+SGS_D void residue_classes(const uint64_t *R, int na, uint32_t *tab, int slots, uint8_t *multi, int lane)
+{
+    for (int i = lane; i < slots; i += 32) tab[i] = 0xffffffffu;
+    for (int i = lane; i < na; i += 32) multi[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < na; i += 32) {
+        uint32_t s = residue_hash<W>(R + (size_t)i * W) & (uint32_t)(slots - 1);
+        for (;;) {
+            uint32_t cur = tab[s];
+            if (cur == 0xffffffffu) {
+                cur = atomicCAS(&tab[s], 0xffffffffu, (uint32_t)i);
+                if (cur == 0xffffffffu) break;                       // first of its class in this slot
+            }
+            if (row_equal<W>(R + (size_t)cur * W, R + (size_t)i * W)) { atomicMin(&tab[s], (uint32_t)i); break; }
+            s = (s + 1) & (uint32_t)(slots - 1);
+        }
+    }
+    __syncwarp();
+}
+
+template <int W>
+SGS_D int residue_leader(const uint64_t *R, int i, const uint32_t *tab, int slots)
+{
+    uint32_t s = residue_hash<W>(R + (size_t)i * W) & (uint32_t)(slots - 1);
+    for (;;) {
+        const uint32_t cur = tab[s];
+        if (row_equal<W>(R + (size_t)cur * W, R + (size_t)i * W)) return (int)cur;
+        s = (s + 1) & (uint32_t)(slots - 1);
+    }
 }
 
 template <int W>
 __global__ void __launch_bounds__(128)
 k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *__restrict__ out,
-          unsigned int *out_count, unsigned out_cap, int shard, int nshards, int smem_per_warp)
+          unsigned int *out_count, unsigned out_cap, int shard, int nshards, int smem_per_warp, int own_only)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -202,7 +254,10 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
     uint8_t *qB = (uint8_t *)p;             p += kMaxG;
     uint8_t *vpos = (uint8_t *)p;           p += 64;
     uint16_t *bestG = (uint16_t *)p;        p += kMaxG * 2;
-    uint32_t *hist = (uint32_t *)p;
+    uint32_t *hist = (uint32_t *)p;         p += (kMaxG + 1) * 4 + 8;
+    uint32_t *htab = (uint32_t *)p;         p += (size_t)general_hash_slots(T) * 4;
+    uint8_t *multi = (uint8_t *)p;
+    const int hslots = general_hash_slots(T);
 
     const unsigned gw = blockIdx.x * wpb + warp, nw = gridDim.x * wpb;
     BestRec *myrec = D.wbest + gw;
@@ -220,6 +275,7 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
         const unsigned flags = rec[1];
         const uint16_t *g = rec + 2;
         const bool mine = nshards <= 1 || (int)(tuple_hash(g, m) % (unsigned)nshards) == shard;
+        if (own_only && !mine) continue;          // parent-sharded level: the owner evaluates and expands it
 
         // ---- 1. echelon basis of the generators with phase and coefficient tracking (K1) ----
         // basis[i] = exact operator product of the generator terms selected by cB[i]; pivot = its
@@ -365,19 +421,20 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
         // ---- 5. children: alive terms above the core whose coset holds no lower-index term ----
         const int core = m ? (int)g[m - 1] : -1;
         const bool parentUnclean = (flags & kFlagUnclean) || nmem > 0;
+        // coset classes of the alive residues: child i is valid iff it is the lowest index of its class;
+        // a class with further members brings dependent terms into the child (it is then "unclean")
+        residue_classes<W>(R, na, htab, hslots, multi, lane);
+        for (int i = lane; i < na; i += 32) {
+            const int lead = residue_leader<W>(R, i, htab, hslots);
+            if (lead != i) multi[lead] = 1;
+        }
+        __syncwarp();
         for (int i0 = 0; i0 < na; i0 += 32) {
             const int i = i0 + lane;
             bool valid = false, higher = false;
             if (i < na && (int)tt[i] > core) {
-                uint64_t mineR[W];
-#pragma unroll
-                for (int k = 0; k < W; k++) mineR[k] = R[(size_t)i * W + k];
-                bool lower = false;
-                for (int e = 0; e < na; e++) {
-                    if (e == i) continue;
-                    if (row_equal<W>(R + (size_t)e * W, mineR)) { if (e < i) lower = true; else higher = true; }
-                }
-                valid = !lower;
+                valid = residue_leader<W>(R, i, htab, hslots) == i;
+                higher = multi[i] != 0;
             }
             const unsigned vb = __ballot_sync(0xffffffffu, valid);
             if (vb == 0) continue;
@@ -591,11 +648,12 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, int n, int
 template <int W>
 __global__ void __launch_bounds__(256, 3)
 k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned int *item_counter,
-      int shard, int nshards, int cap, int smem_per_warp)
+      int shard, int nshards, int cap, int smem_per_warp, const unsigned int *nitems_dev)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const unsigned ltmask = lanemask_lt();
+    if (nitems_dev) nitems = *nitems_dev;          // queue length produced by a parent-sharded expansion
     unsigned char *p = smem_raw + (size_t)warp * smem_per_warp;
     uint64_t *R = (uint64_t *)p;        p += (size_t)cap * W * 8;
     double *WA = (double *)p;           p += (size_t)cap * 8;
@@ -882,27 +940,31 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
 }
 
 // ------------------------------------------------------------------------------------------------
-// deterministic argmin over the per-warp records: minimum energy, ties by tuple order.  One warp.
-__global__ void k_reduce_best(const BestRec *__restrict__ recs, int nrecs, BestRec *__restrict__ out)
+// deterministic argmin over the per-warp records: minimum energy, ties by tuple order.  One block; the
+// order (E, tuple) is total, so the tree reduction gives the same winner whatever the pairing.
+SGS_D bool rec_better(const BestRec *recs, int a, int b)     // is record a strictly better than b?
 {
-    const int lane = threadIdx.x;
+    if (a < 0) return false;
+    if (b < 0) return true;
+    if (recs[a].E != recs[b].E) return recs[a].E < recs[b].E;
+    return a != b && tuple_before(recs[a].g, recs[a].m, recs[b].g, recs[b].m);
+}
+
+__global__ void __launch_bounds__(1024) k_reduce_best(const BestRec *__restrict__ recs, int nrecs, BestRec *__restrict__ out)
+{
+    __shared__ int sbest[1024];
+    const int tid = threadIdx.x;
     int best = -1;
-    for (int i = lane; i < nrecs; i += 32) {
-        if (!recs[i].valid) continue;
-        if (best < 0 || recs[i].E < recs[best].E ||
-            (recs[i].E == recs[best].E && tuple_before(recs[i].g, recs[i].m, recs[best].g, recs[best].m)))
-            best = i;
+    for (int i = tid; i < nrecs; i += blockDim.x)
+        if (recs[i].valid && rec_better(recs, i, best)) best = i;
+    sbest[tid] = best;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (tid < s && rec_better(recs, sbest[tid + s], sbest[tid])) sbest[tid] = sbest[tid + s];
+        __syncthreads();
     }
-    for (int d = 16; d > 0; d >>= 1) {
-        const int other = __shfl_xor_sync(0xffffffffu, best, d);
-        if (other >= 0 &&
-            (best < 0 || recs[other].E < recs[best].E ||
-             (recs[other].E == recs[best].E && other != best &&
-              tuple_before(recs[other].g, recs[other].m, recs[best].g, recs[best].m))))
-            best = other;
-    }
-    if (lane == 0) {
-        if (best >= 0) *out = recs[best];
+    if (tid == 0) {
+        if (sbest[0] >= 0) *out = recs[sbest[0]];
         else { out->valid = 0; out->m = 0; out->E = 0.0; }
     }
 }

@@ -50,6 +50,7 @@ struct DevCtx {
     BestRec hbest{};
     float ms_device = 0.f, ms_hot = 0.f;
     unsigned launches = 0;
+    bool had_slow = false;
     Status status;
 };
 
@@ -92,13 +93,26 @@ struct SparsePlan::Impl {
     unsigned qcap = 0, slow_cap = 0, chunk = 0;
     int dfs_cap = 0;
     std::vector<DevCtx> devs;
-    std::unique_ptr<NcclWorld> nccl;
+    std::shared_ptr<NcclWorld> nccl;
+    // Replay: the launch sequence of a first (adaptive, host-synchronised) run that needed no work from
+    // the exact kernel below the subtree roots is deterministic, so later runs of the same plan enqueue it
+    // back to back — expansion levels, walk, reduction, collective, finalisation — and synchronise once.
+    struct Replay {
+        bool ok = false;
+        int depth = 0;
+        std::vector<unsigned> counts;    // nodes per expanded level; counts[depth] = subtree roots
+        int dfs_cap = 0, dfs_wpb = 8, gen_wpb = 4;
+        size_t dfs_pw = 0, gen_pw = 0;
+        unsigned dfs_grid = 0, gen_maxgrid = 0;
+    } rp;
 
     ~Impl();
     Status init();
     Status init_device(DevCtx &c);
     template <int W_> Status search_local(DevCtx &c);
-    template <int W_> Status finalize(DevCtx &c, const BestRec &best, sgs_result *out);
+    template <int W_> Status finalize(DevCtx &c, const BestRec *host_best, sgs_result *out);
+    template <int W_> Status run_replay(sgs_result *out);
+    void fill_stats(const SparseStats &tot, sgs_result *out);
     Status run(sgs_result *out);
     SparseDev dev_view(const DevCtx &c) const;
 };
@@ -163,11 +177,25 @@ Status SparsePlan::Impl::init()
         if (!s.ok()) return s;
     }
     if (nshards > 1 && (opts.nccl_id != nullptr || (world == 1 && ng > 1))) {
+        // communicators are cached for the life of the process, keyed by (unique id, rank, world, devices):
+        // repeated one-shot searches with the same id reuse the communicator (an id can bootstrap only one)
         std::vector<int> ids;
         for (auto &d : devs) ids.push_back(d.device);
-        nccl.reset(new NcclWorld());
-        Status s = nccl->init(ids, std::max(0, opts.rank), world, opts.nccl_id);
-        if (!s.ok()) return s;
+        std::string key(opts.nccl_id ? (const char *)opts.nccl_id : "", opts.nccl_id ? SGS_NCCL_ID_BYTES : 0);
+        key += "|" + std::to_string(std::max(0, opts.rank)) + "|" + std::to_string(world);
+        for (int d : ids) key += "," + std::to_string(d);
+        static std::mutex mu;
+        static std::map<std::string, std::shared_ptr<NcclWorld>> cache;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) nccl = it->second;
+        else {
+            std::shared_ptr<NcclWorld> w(new NcclWorld());
+            Status s = w->init(ids, std::max(0, opts.rank), world, opts.nccl_id);
+            if (!s.ok()) return s;
+            cache[key] = w;
+            nccl = w;
+        }
     }
     return Status();
 }
@@ -272,7 +300,7 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
                               int shard, int nsh) {
         unsigned grid = std::min<unsigned>((nin + gen_wpb - 1) / gen_wpb, gen_maxgrid);
         if (grid == 0) return;
-        k_general<W_><<<grid, gen_wpb * 32, gen_pw * gen_wpb, st>>>(D, in, nin, out, out_count, out_cap, shard, nsh, (int)gen_pw);
+        k_general<W_><<<grid, gen_wpb * 32, gen_pw * gen_wpb, st>>>(D, in, nin, out, out_count, out_cap, shard, nsh, (int)gen_pw, 0);
         c.launches++;
     };
 
@@ -288,6 +316,8 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
     int depth = 0;
     SparseStats hs{};
     unsigned hcnt[4];
+    std::vector<unsigned> level_counts{1};
+    c.had_slow = false;
     while (count > 0 && depth < dmax) {
         if (opts.expand_depth <= 0) {
             const double est_alive = ratio * std::max(depth, 1) / 2.0;
@@ -305,6 +335,7 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
                                           "sparse search: device limit hit while expanding the tree (queue overflow or rank/table limit)");
         ratio = std::max(1.0, (double)hcnt[0] / (double)count);
         count = hcnt[0];
+        level_counts.push_back(count);
         std::swap(cur, nxt);
         depth++;
     }
@@ -325,8 +356,12 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         dfs_occ = std::max(1, dfs_occ);
         const unsigned dfs_maxgrid = (unsigned)std::min<long long>((long long)c.sms * dfs_occ, c.nwbest / dfs_wpb);
         const unsigned grid = std::min<unsigned>(dfs_maxgrid, (count + dfs_wpb - 1) / dfs_wpb);
+        if (&c == &devs[0]) {
+            rp.depth = depth; rp.counts = level_counts; rp.dfs_cap = dfs_cap; rp.dfs_wpb = dfs_wpb; rp.dfs_pw = dfs_pw;
+            rp.dfs_grid = grid; rp.gen_wpb = gen_wpb; rp.gen_pw = gen_pw; rp.gen_maxgrid = gen_maxgrid;
+        }
         SGS_CUDA_TRY(cudaEventRecord(c.evh0, st));
-        k_dfs<W_><<<grid, dfs_wpb * 32, dfs_pw * dfs_wpb, st>>>(D, cur, count, c.counters + 1, c.shard, nshards, dfs_cap, (int)dfs_pw);
+        k_dfs<W_><<<grid, dfs_wpb * 32, dfs_pw * dfs_wpb, st>>>(D, cur, count, c.counters + 1, c.shard, nshards, dfs_cap, (int)dfs_pw, nullptr);
         c.launches++;
         SGS_CUDA_TRY(cudaGetLastError());
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
@@ -344,6 +379,7 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
                                           "sparse search: device limit hit (work-stack overflow, or a group whose sign table exceeds the limit)");
         const unsigned sc = hcnt[2];
         if (sc == 0) break;
+        c.had_slow = true;
         const unsigned take = std::min(sc, chunk);
         SGS_CUDA_TRY(cudaMemcpyAsync(c.work, c.slow + (size_t)(sc - take) * S, (size_t)take * S * 2, cudaMemcpyDeviceToDevice, st));
         const unsigned left = sc - take;
@@ -352,7 +388,7 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         SGS_CUDA_TRY(cudaGetLastError());
     }
 
-    k_reduce_best<<<1, 32, 0, st>>>(c.wbest, c.nwbest, c.gbest);
+    k_reduce_best<<<1, 1024, 0, st>>>(c.wbest, c.nwbest, c.gbest);
     c.launches++;
     SGS_CUDA_TRY(cudaGetLastError());
     SGS_CUDA_TRY(cudaEventRecord(c.ev1, st));
@@ -365,12 +401,12 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
 }
 
 template <int W_>
-Status SparsePlan::Impl::finalize(DevCtx &c, const BestRec &best, sgs_result *out)
+Status SparsePlan::Impl::finalize(DevCtx &c, const BestRec *host_best, sgs_result *out)
 {
     SGS_CUDA_TRY(cudaSetDevice(c.device));
     const SparseDev D = dev_view(c);
     cudaStream_t st = c.stream;
-    SGS_CUDA_TRY(cudaMemcpyAsync(c.gbest, &best, sizeof(BestRec), cudaMemcpyHostToDevice, st));
+    if (host_best) SGS_CUDA_TRY(cudaMemcpyAsync(c.gbest, host_best, sizeof(BestRec), cudaMemcpyHostToDevice, st));
     k_finalize<W_><<<1, 256, 0, st>>>(D, c.gbest, c.order, c.fin, c.term_signs, c.memX, c.memA, c.memT, c.memCount);
     c.launches++;
     SGS_CUDA_TRY(cudaGetLastError());
@@ -394,10 +430,129 @@ Status SparsePlan::Impl::finalize(DevCtx &c, const BestRec &best, sgs_result *ou
     return Status();
 }
 
+void SparsePlan::Impl::fill_stats(const SparseStats &tot, sgs_result *out)
+{
+    out->candidates = 0;
+    out->sum_2m = 0.0;
+    for (int i = 0; i <= kMaxG && i <= SGS_MAX_RANK; i++) {
+        out->rank_hist[i] = tot.hist[i];
+        out->candidates += tot.hist[i];
+        out->sum_2m += (double)tot.hist[i] * std::ldexp(1.0, i);
+    }
+    out->slow_nodes = tot.slow_nodes;
+}
+
+template <int W_>
+Status SparsePlan::Impl::run_replay(sgs_result *out)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    for (auto &c : devs) {
+        SGS_CUDA_TRY(cudaSetDevice(c.device));
+        const SparseDev D = dev_view(c);
+        cudaStream_t st = c.stream;
+        c.launches = 0;
+        SGS_CUDA_TRY(cudaMemsetAsync(c.wbest, 0, sizeof(BestRec) * c.nwbest, st));
+        SGS_CUDA_TRY(cudaMemsetAsync(c.stats, 0, sizeof(SparseStats), st));
+        SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, 4 * sizeof(unsigned), st));
+        SGS_CUDA_TRY(cudaMemsetAsync(c.qA, 0, (size_t)S * 2, st));          // root record: the empty group
+        SGS_CUDA_TRY(cudaEventRecord(c.ev0, st));
+        uint16_t *cur = c.qA, *nxt = c.qB;
+        for (int d = 0; d < rp.depth; d++) {
+            const unsigned nin = rp.counts[d];
+            const unsigned grid = std::min<unsigned>((nin + rp.gen_wpb - 1) / rp.gen_wpb, rp.gen_maxgrid);
+            SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, sizeof(unsigned), st));
+            // the last level is expanded by the owner of each parent only: its children land in the owner's
+            // queue and k_dfs walks all of them (no shard filter), so the expansion work shards too
+            const int own_only = (nshards > 1 && d == rp.depth - 1) ? 1 : 0;
+            k_general<W_><<<grid, rp.gen_wpb * 32, rp.gen_pw * rp.gen_wpb, st>>>(D, cur, nin, nxt, c.counters, qcap, c.shard, nshards,
+                                                                                 (int)rp.gen_pw, own_only);
+            c.launches++;
+            std::swap(cur, nxt);
+        }
+        SGS_CUDA_TRY(cudaEventRecord(c.evh0, st));
+        // with a parent-sharded last level the queue length is only known on the device: counters[0]
+        k_dfs<W_><<<rp.dfs_grid, rp.dfs_wpb * 32, rp.dfs_pw * rp.dfs_wpb, st>>>(D, cur, rp.counts[rp.depth], c.counters + 1, c.shard,
+                                                                              (nshards > 1 && rp.depth > 0) ? 1 : nshards, rp.dfs_cap, (int)rp.dfs_pw,
+                                                                              (nshards > 1 && rp.depth > 0) ? c.counters : nullptr);
+        SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
+        k_reduce_best<<<1, 1024, 0, st>>>(c.wbest, c.nwbest, c.gbest);
+        c.launches += 2;
+        SGS_CUDA_TRY(cudaGetLastError());
+    }
+    if (nccl) {
+        std::vector<void *> sendb, recvb, sumb;
+        std::vector<cudaStream_t> sts;
+        for (auto &c : devs) { sendb.push_back(c.gbest); recvb.push_back(c.allbest); sumb.push_back(c.stats); sts.push_back(c.stream); }
+        Status s = nccl->all_gather_bytes(sendb, recvb, sizeof(BestRec), sts);
+        if (!s.ok()) return s;
+        s = nccl->all_reduce_sum_u64(sumb, kMaxG + 2, sts);          // hist[0..kMaxG] and slow_nodes are contiguous u64
+        if (!s.ok()) return s;
+        for (auto &c : devs) {
+            SGS_CUDA_TRY(cudaSetDevice(c.device));
+            k_reduce_best<<<1, 1024, 0, c.stream>>>(c.allbest, nshards, c.gbest);
+            c.launches++;
+        }
+    }
+    DevCtx &c0 = devs[0];
+    SGS_CUDA_TRY(cudaSetDevice(c0.device));
+    {
+        const SparseDev D = dev_view(c0);
+        k_finalize<W_><<<1, 256, 0, c0.stream>>>(D, c0.gbest, c0.order, c0.fin, c0.term_signs, c0.memX, c0.memA, c0.memT, c0.memCount);
+        c0.launches++;
+        SGS_CUDA_TRY(cudaGetLastError());
+    }
+    FinalOut fo;
+    std::vector<int8_t> ts(std::max(T, 1));
+    unsigned hcnt[4] = {0, 0, 0, 0};
+    SGS_CUDA_TRY(cudaMemcpyAsync(&fo, c0.fin, sizeof(FinalOut), cudaMemcpyDeviceToHost, c0.stream));
+    SGS_CUDA_TRY(cudaMemcpyAsync(ts.data(), c0.term_signs, std::max(T, 1), cudaMemcpyDeviceToHost, c0.stream));
+    SGS_CUDA_TRY(cudaMemcpyAsync(&c0.hstats, c0.stats, sizeof(SparseStats), cudaMemcpyDeviceToHost, c0.stream));
+    SGS_CUDA_TRY(cudaMemcpyAsync(&c0.hbest, c0.gbest, sizeof(BestRec), cudaMemcpyDeviceToHost, c0.stream));
+    SGS_CUDA_TRY(cudaMemcpyAsync(hcnt, c0.counters, sizeof(hcnt), cudaMemcpyDeviceToHost, c0.stream));
+    for (auto &c : devs) { SGS_CUDA_TRY(cudaSetDevice(c.device)); SGS_CUDA_TRY(cudaEventRecord(c.ev1, c.stream)); }
+    float msd = 0.f, msh = 0.f;
+    unsigned launches = 0;
+    for (auto &c : devs) {
+        SGS_CUDA_TRY(cudaSetDevice(c.device));
+        SGS_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        float a = 0.f, b = 0.f;
+        SGS_CUDA_TRY(cudaEventElapsedTime(&a, c.ev0, c.ev1));
+        SGS_CUDA_TRY(cudaEventElapsedTime(&b, c.evh0, c.evh1));
+        msd = std::max(msd, a); msh = std::max(msh, b); launches += c.launches;
+    }
+    if (c0.hstats.error || hcnt[2] != 0 || !c0.hbest.valid || fo.error) {
+        rp.ok = false;      // should not happen (the sequence is deterministic); fall back to the adaptive path
+        return Status::fail(SGS_ERR_CUDA, "sparse search: replayed launch sequence diverged from the recorded run");
+    }
+    const int Wout = (2 * n + 63) / 64;
+    out->energy = fo.energy;
+    out->n = n; out->m = fo.m; out->W = Wout; out->T = T;
+    out->gens = (uint64_t *)calloc((size_t)std::max(fo.m, 1) * Wout, 8);
+    out->gen_signs = (int8_t *)calloc(std::max(fo.m, 1), 1);
+    out->term_signs = (int8_t *)calloc(std::max(T, 1), 1);
+    for (int i = 0; i < fo.m; i++) {
+        for (int k = 0; k < Wout; k++) out->gens[(size_t)i * Wout + k] = fo.rows[i * W_ + k];
+        out->gen_signs[i] = fo.signs[i];
+    }
+    memcpy(out->term_signs, ts.data(), T);
+    fill_stats(c0.hstats, out);
+    out->seconds_device = msd * 1e-3;
+    out->seconds_hot_kernel = msh * 1e-3;
+    out->kernel_launches = launches;
+    out->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return Status();
+}
+
 Status SparsePlan::Impl::run(sgs_result *out)
 {
     const auto t0 = std::chrono::steady_clock::now();
     memset(out, 0, sizeof(*out));
+    if (rp.ok) {
+        Status s = W == 1 ? run_replay<1>(out) : (W == 2 ? run_replay<2>(out) : run_replay<4>(out));
+        if (s.ok() || rp.ok) return s;
+        sgs_result_free(out);          // replay diverged: redo adaptively
+        memset(out, 0, sizeof(*out));
+    }
     auto local = [&](DevCtx &c) {
         if (W == 1) c.status = search_local<1>(c);
         else if (W == 2) c.status = search_local<2>(c);
@@ -435,7 +590,7 @@ Status SparsePlan::Impl::run(sgs_result *out)
         if (!s.ok()) return s;
         for (auto &c : devs) {
             cudaSetDevice(c.device);
-            k_reduce_best<<<1, 32, 0, c.stream>>>(c.allbest, nshards, c.gbest);
+            k_reduce_best<<<1, 1024, 0, c.stream>>>(c.allbest, nshards, c.gbest);
             c.launches++;
         }
         DevCtx &c0 = devs[0];
@@ -456,23 +611,20 @@ Status SparsePlan::Impl::run(sgs_result *out)
 
     DevCtx &c0 = devs[0];
     Status s;
-    if (W == 1) s = finalize<1>(c0, best, out);
-    else if (W == 2) s = finalize<2>(c0, best, out);
-    else s = finalize<4>(c0, best, out);
+    if (W == 1) s = finalize<1>(c0, &best, out);
+    else if (W == 2) s = finalize<2>(c0, &best, out);
+    else s = finalize<4>(c0, &best, out);
     if (!s.ok()) return s;
     float ms_merge = 0.f;
     cudaEventRecord(c0.ev1, c0.stream);
     cudaEventSynchronize(c0.ev1);
     cudaEventElapsedTime(&ms_merge, c0.ev0, c0.ev1);
 
-    out->candidates = 0;
-    out->sum_2m = 0.0;
-    for (int i = 0; i <= kMaxG && i <= SGS_MAX_RANK; i++) {
-        out->rank_hist[i] = tot.hist[i];
-        out->candidates += tot.hist[i];
-        out->sum_2m += (double)tot.hist[i] * std::ldexp(1.0, i);
-    }
-    out->slow_nodes = tot.slow_nodes;
+    fill_stats(tot, out);
+    // replay is valid when no device needed the exact kernel below the roots and there were roots at all
+    bool can = !rp.counts.empty() && rp.dfs_grid > 0 && opts.expand_depth >= 0;
+    for (auto &c : devs) can = can && !c.had_slow;
+    rp.ok = can;
     float msd = 0.f, msh = 0.f;
     unsigned launches = 0;
     for (auto &c : devs) { msd = std::max(msd, c.ms_device); msh = std::max(msh, c.ms_hot); launches += c.launches; }
