@@ -89,7 +89,7 @@ def run_reference(args, rank, world):
     import oracle_py as O
     text = G.sparse_text(N_QUBITS, N_TERMS, SEED)
     cores = os.cpu_count() or 1
-    sample_s = 8.0
+    sample_s = float(os.environ.get('SGS_BENCH_SAMPLE_S', '8.0'))
     for _ in range(min(args.warmup, 1)):
         O.sparse_sample(text=text, threads=cores, seconds=1.0)
     cand, secs = 0, 0.0
