@@ -377,7 +377,7 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
         // ---- 4. exact minimum over generator signs (K5) ----
         // E(s) = cst + sum_k lin[k] s_k + sum_e exA[e] prod_{k in exC[e]} s_k, s_k = sign of generator term k.
         // Variables outside V = union of the extras' supports minimise independently.
-        if (!(flags & kFlagExpandOnly)) {
+        if (!(flags & kFlagExpandOnly) && out != nullptr) {       // out == nullptr: count-only pass (children are only counted)
             uint64_t V = 0;
             for (int e = 0; e < ne; e++) V |= exC[e];
             double E = cst;
@@ -438,6 +438,7 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
             }
             const unsigned vb = __ballot_sync(0xffffffffu, valid);
             if (vb == 0) continue;
+            if (out == nullptr) { if (lane == 0) atomicAdd(out_count, (unsigned)__popc(vb)); continue; }
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(out_count, (unsigned)__popc(vb));
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -476,7 +477,7 @@ __host__ __device__ inline size_t dfs_smem_bytes(int cap)
     b += (size_t)cap * W * 8;          // residues
     b += (size_t)cap * 8;              // |w| of each list entry
     b += (size_t)32 * W * 8;           // basis (subtree-root setup)
-    b += (size_t)64 * 8;               // level-B commutation bit-matrix
+    b += (size_t)64 * 8 + 32 * 4;      // level-B commutation bit-matrix (64-bit and 32-bit forms)
     b += (size_t)kMaxFrames * 8;       // frame E
     b += (size_t)kMaxFrames * 4 * 3;   // frame base, a, q
     b += (size_t)(kMaxG + 1) * 4 + 4;  // hist
@@ -527,70 +528,151 @@ SGS_D bool has_duplicate(const uint64_t *R, int n, int lane)
 // cliques that start at "its" vertices privately with 64-bit masks.
 // Returns false (nothing counted) if the residues are dependent.
 constexpr int kMaxLB = 64;
-
 constexpr int kMaxDep = 6;
 
-template <int W>
-SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, int n, int nlow, int depth,
-                   uint32_t *hc, double &bw, uint64_t &bm, int lane)
+SGS_D int ctz_mask(uint32_t v) { return __ffs((int)v) - 1; }
+SGS_D int ctz_mask(uint64_t v) { return __ffsll((long long)v) - 1; }
+SGS_D int popc_mask(uint32_t v) { return __popc(v); }
+SGS_D int popc_mask(uint64_t v) { return __popcll(v); }
+
+// lane-private walk over the cliques of the candidates (vertices 0..ncand-1 = list positions nlow..n-1,
+// ADm[v] = neighbours of v with a higher index): lane l starts the cliques whose lowest vertex is l and, with
+// more than 32 candidates, 63 - l (big subtrees are paired with small ones).  Counts candidates per rank in
+// hc[], keeps the heaviest clique (ties: lowest first vertex, then first found = lexicographic order).
+template <typename M>
+SGS_D void lb_walk(const M *ADm, const double *WAc, int ncand, int depth, uint32_t *hc, double &bw, M &bm, int lane)
 {
-    // own rows: entries lane and lane + 32 (o = original residue for commutation, e = elimination copy,
-    // cmb = which original residues have been XORed into e)
-    const bool two = n > 32;
-    uint64_t o0[W], o1[W], e0[W], e1[W];
-#pragma unroll
-    for (int k = 0; k < W; k++) {
-        o0[k] = lane < n ? R[lane * W + k] : 0;
-        o1[k] = lane + 32 < n ? R[(lane + 32) * W + k] : 0;
-        e0[k] = o0[k]; e1[k] = o1[k];
-    }
-    uint64_t cmb0 = lane < n ? (1ULL << lane) : 0, cmb1 = lane + 32 < n ? (1ULL << (lane + 32)) : 0;
-    uint64_t adj0 = 0, adj1 = 0;
-    uint64_t deps[kMaxDep];
-    int ndep = 0;
-    bool fail = false;
+    M cand[kMaxLB], cm[kMaxLB];
+    double ws[kMaxLB];
 #pragma unroll 1
-    for (int u = 0; u < n; u++) {
-        // commutation column u = row u (the form is symmetric): one ballot per 32 entries
-        uint64_t sw[W];
-#pragma unroll
-        for (int k = 0; k < W; k++) sw[k] = swapzx(R[u * W + k]);
-        const bool c0 = lane < n && lane != u && !row_anticommute_sw<W>(o0, sw);
-        uint64_t col = __ballot_sync(0xffffffffu, c0);
-        if (two) {
-            const bool c1 = lane + 32 < n && lane + 32 != u && !row_anticommute_sw<W>(o1, sw);
-            col |= (uint64_t)__ballot_sync(0xffffffffu, c1) << 32;
-        }
-        if (lane == (u & 31)) { if (u < 32) adj0 = col; else adj1 = col; }
-        // elimination step: pivot row = current (reduced) copy of entry u
-        uint64_t cu[W];
-#pragma unroll
-        for (int k = 0; k < W; k++) cu[k] = __shfl_sync(0xffffffffu, u < 32 ? e0[k] : e1[k], u & 31);
-        const uint64_t cmu = __shfl_sync(0xffffffffu, u < 32 ? cmb0 : cmb1, u & 31);
-        if (row_is_zero<W>(cu)) {                 // entry u is a combination of earlier ones: a dependency
-            if (ndep == kMaxDep) { fail = true; break; }
-#pragma unroll
-            for (int k = 0; k < kMaxDep; k++) if (k == ndep) deps[k] = cmu;
-            ndep++;
+    for (int pass = 0; pass < 2; pass++) {
+        const int f = pass == 0 ? lane : 63 - lane;
+        if (f >= ncand || (pass == 1 && f < 32)) continue;
+        const M c = ADm[f];
+        const double w = WAc[f];
+        hc[depth + 1] += 1;
+        if (c == 0) {
+            if (w > bw) { bw = w; bm = (M)1 << f; }
             continue;
         }
-        const int pv = row_lowbit<W>(cu);
-        if (lane > u && row_bit<W>(e0, pv)) {
-#pragma unroll
-            for (int k = 0; k < W; k++) e0[k] ^= cu[k];
-            cmb0 ^= cmu;
-        }
-        if (two && lane + 32 > u && row_bit<W>(e1, pv)) {
-#pragma unroll
-            for (int k = 0; k < W; k++) e1[k] ^= cu[k];
-            cmb1 ^= cmu;
+        int d = 0;
+        cand[0] = c; ws[0] = w; cm[0] = (M)1 << f;
+        hc[depth + 2] += popc_mask(c);
+        while (d >= 0) {
+            const M cc = cand[d];
+            if (cc == 0) { d--; continue; }
+            const int v = ctz_mask(cc);
+            cand[d] = cc & (cc - 1);
+            const M nc = cc & ADm[v];
+            const double nw = ws[d] + WAc[v];
+            if (nc == 0) {
+                if (nw > bw) { bw = nw; bm = cm[d] | ((M)1 << v); }
+            } else {
+                hc[depth + 3 + d] += popc_mask(nc);
+                cm[d + 1] = cm[d] | ((M)1 << v);
+                d++;
+                cand[d] = nc; ws[d] = nw;
+            }
         }
     }
-    if (fail) return false;
-    if (ndep > 0) {
-        // The residues are dependent, but a dependent term can only ever appear below this frame if the
-        // support of some kernel vector (XOR of recorded dependencies) is a CLIQUE of the commutation
-        // graph: the terms of a dependency inside one group commute pairwise.  Check all 2^ndep - 1.
+}
+
+template <int W>
+SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, int n, int nlow, int depth,
+                   uint32_t *hc, double &bw, uint64_t &bm, int lane)
+{
+    // own rows: entries lane and lane + 32 (o = residue, s = its z/x-swapped copy for the symmetric
+    // commutation test popc(s_i & r_u), e = elimination copy)
+    const bool two = n > 32;
+    uint64_t s0[W], s1[W], e0[W], e1[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+        e0[k] = lane < n ? R[lane * W + k] : 0;
+        e1[k] = lane + 32 < n ? R[(lane + 32) * W + k] : 0;
+        s0[k] = swapzx(e0[k]); s1[k] = swapzx(e1[k]);
+    }
+    uint64_t adj0 = 0, adj1 = 0;
+    bool dependent = false;
+#pragma unroll 1
+    for (int u = 0; u < n; u++) {
+        uint64_t ru[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) ru[k] = R[u * W + k];
+        // commutation row bits (the form is symmetric: popc(swap(a) & b) = popc(a & swap(b)))
+        adj0 |= (uint64_t)(row_anticommute_sw<W>(ru, s0) ^ 1) << u;
+        if (two) adj1 |= (uint64_t)(row_anticommute_sw<W>(ru, s1) ^ 1) << u;
+        // elimination step: pivot row = current (reduced) copy of entry u, pivot = its lowest set bit
+        uint64_t cu[W], lm[W];
+        bool nz = false;
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            cu[k] = __shfl_sync(0xffffffffu, u < 32 ? e0[k] : e1[k], u & 31);
+            lm[k] = nz ? 0 : (cu[k] & (0 - cu[k]));
+            nz |= cu[k] != 0;
+        }
+        if (!nz) { dependent = true; continue; }
+        uint64_t h0 = 0, h1 = 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) { h0 |= e0[k] & lm[k]; h1 |= e1[k] & lm[k]; }
+        if (lane > u && h0) {
+#pragma unroll
+            for (int k = 0; k < W; k++) e0[k] ^= cu[k];
+        }
+        if (two && lane + 32 > u && h1) {
+#pragma unroll
+            for (int k = 0; k < W; k++) e1[k] ^= cu[k];
+        }
+    }
+    const uint64_t vmask = n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL);
+    adj0 = lane < n ? (adj0 & vmask & ~(1ULL << lane)) : 0;
+    adj1 = lane + 32 < n ? (adj1 & vmask & ~(1ULL << (lane + 32))) : 0;
+    if (dependent) {
+        // Second elimination, now tracking which original residues are XORed into each row, to obtain the
+        // dependencies themselves.  A dependent term can only ever appear below this frame if the support of
+        // some kernel vector (XOR of dependencies) is a CLIQUE of the commutation graph: the terms of a
+        // dependency inside one group commute pairwise.  Check all 2^ndep - 1 of them.
+        uint64_t cmb0 = lane < n ? (1ULL << lane) : 0, cmb1 = lane + 32 < n ? (1ULL << (lane + 32)) : 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            e0[k] = lane < n ? R[lane * W + k] : 0;
+            e1[k] = lane + 32 < n ? R[(lane + 32) * W + k] : 0;
+        }
+        uint64_t deps[kMaxDep];
+        int ndep = 0;
+        bool fail = false;
+#pragma unroll 1
+        for (int u = 0; u < n; u++) {
+            uint64_t cu[W], lm[W];
+            bool nz = false;
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                cu[k] = __shfl_sync(0xffffffffu, u < 32 ? e0[k] : e1[k], u & 31);
+                lm[k] = nz ? 0 : (cu[k] & (0 - cu[k]));
+                nz |= cu[k] != 0;
+            }
+            const uint64_t cmu = __shfl_sync(0xffffffffu, u < 32 ? cmb0 : cmb1, u & 31);
+            if (!nz) {
+                if (ndep == kMaxDep) { fail = true; break; }
+#pragma unroll
+                for (int k = 0; k < kMaxDep; k++) if (k == ndep) deps[k] = cmu;
+                ndep++;
+                continue;
+            }
+            uint64_t h0 = 0, h1 = 0;
+#pragma unroll
+            for (int k = 0; k < W; k++) { h0 |= e0[k] & lm[k]; h1 |= e1[k] & lm[k]; }
+            if (lane > u && h0) {
+#pragma unroll
+                for (int k = 0; k < W; k++) e0[k] ^= cu[k];
+                cmb0 ^= cmu;
+            }
+            if (lane + 32 > u && h1) {
+#pragma unroll
+                for (int k = 0; k < W; k++) e1[k] ^= cu[k];
+                cmb1 ^= cmu;
+            }
+        }
+        if (fail) return false;
 #pragma unroll 1
         for (int gcode = 1; gcode < (1 << ndep); gcode++) {
             uint64_t S = 0;
@@ -601,47 +683,28 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, int n, int
             if (!__any_sync(0xffffffffu, bad)) return false;      // a commuting dependency: not certified
         }
     }
-    // keep only higher-position neighbours: cliques are built in ascending position order
-    AD[lane] = adj0 & ~((2ULL << lane) - 1ULL);
-    AD[lane + 32] = lane == 31 ? 0ULL : (adj1 & ~((2ULL << (lane + 32)) - 1ULL));
-    __syncwarp();
-
-    // lane l starts the cliques whose lowest vertex is nlow + l and, for lists with more than 32
-    // candidates, nlow + 63 - l (big subtrees are paired with small ones)
+    // candidates = list positions nlow..n-1; keep only higher-position neighbours (cliques grow upward)
     const int ncand = n - nlow;
-    uint64_t cand[kMaxLB], cm[kMaxLB];
-    double ws[kMaxLB];
-#pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        const int f = pass == 0 ? nlow + lane : nlow + 63 - lane;
-        if (pass == 0 ? lane >= ncand : (63 - lane >= ncand || 63 - lane < 32)) continue;
-        const uint64_t c = AD[f];
-        const double w = WA[f];
-        hc[depth + 1] += 1;
-        if (c == 0) {
-            if (w > bw || (w == bw && (1ULL << f) < (bm & (0 - bm)))) { bw = w; bm = 1ULL << f; }
-            continue;
-        }
-        int d = 0;
-        cand[0] = c; ws[0] = w; cm[0] = 1ULL << f;
-        hc[depth + 2] += popc64(c);
-        while (d >= 0) {
-            const uint64_t cc = cand[d];
-            if (cc == 0) { d--; continue; }
-            const int v = ctz64(cc);
-            cand[d] = cc & (cc - 1);
-            const uint64_t nc = cc & AD[v];
-            const double nw = ws[d] + WA[v];
-            if (nc == 0) {
-                if (nw > bw || (nw == bw && f < ctz64(bm))) { bw = nw; bm = cm[d] | (1ULL << v); }
-            } else {
-                hc[depth + 3 + d] += popc64(nc);
-                cm[d + 1] = cm[d] | (1ULL << v);
-                d++;
-                cand[d] = nc; ws[d] = nw;
-            }
-        }
+    const uint64_t up0 = adj0 & ~((2ULL << lane) - 1ULL);
+    const uint64_t up1 = lane == 31 ? 0ULL : (adj1 & ~((2ULL << (lane + 32)) - 1ULL));
+    if (ncand <= 32) {
+        // 32-bit masks relative to nlow
+        if (lane >= nlow && lane < n) AD32[lane - nlow] = (uint32_t)(up0 >> nlow);
+        if (lane + 32 >= nlow && lane + 32 < n) AD32[lane + 32 - nlow] = (uint32_t)(up1 >> nlow);
+        __syncwarp();
+        uint32_t bm32 = 0;
+        lb_walk<uint32_t>(AD32, WA + nlow, ncand, depth, hc, bw, bm32, lane);
+        bm = (uint64_t)bm32 << nlow;
+    } else {
+        // 64-bit masks, vertices = positions - nlow
+        if (lane >= nlow && lane < n) AD[lane - nlow] = up0 >> nlow;
+        if (lane + 32 >= nlow && lane + 32 < n) AD[lane + 32 - nlow] = up1 >> nlow;
+        __syncwarp();
+        uint64_t bmr = 0;
+        lb_walk<uint64_t>(AD, WA + nlow, ncand, depth, hc, bw, bmr, lane);
+        bm = bmr << nlow;
     }
+    __syncwarp();
     return true;
 }
 
@@ -659,6 +722,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     double *WA = (double *)p;           p += (size_t)cap * 8;
     uint64_t *B = (uint64_t *)p;        p += (size_t)32 * W * 8;
     uint64_t *AD = (uint64_t *)p;       p += (size_t)64 * 8;
+    uint32_t *AD32 = (uint32_t *)p;     p += (size_t)32 * 4;
     double *fE = (double *)p;           p += (size_t)kMaxFrames * 8;
     int *fbase = (int *)p;              p += (size_t)kMaxFrames * 4;
     int *fa = (int *)p;                 p += (size_t)kMaxFrames * 4;
@@ -696,7 +760,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     auto run_level_b = [&](int lb, int n, int nlow, int depth, double Ef) -> bool {
         double bw = -1.0;
         uint64_t bm = 0;
-        if (!level_b<W>(R + lb * W, WA + lb, AD, n, nlow, depth, hc, bw, bm, lane)) return false;
+        if (!level_b<W>(R + lb * W, WA + lb, AD, AD32, n, nlow, depth, hc, bw, bm, lane)) return false;
         // does any lane's best clique reach the incumbent?
         const bool cand = bm != 0 && (Ef - bw) <= bestE;
         if (__any_sync(0xffffffffu, cand)) {

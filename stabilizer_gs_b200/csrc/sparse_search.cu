@@ -323,8 +323,20 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
             const double est_alive = ratio * std::max(depth, 1) / 2.0;
             if (depth > 0 && count >= min_items && est_alive <= 64.0) break;
         }
+        // worst case: the branching cannot grow (ratio is non-increasing for clique-like trees)
         const double bound = (double)count * std::min<double>((double)std::max(T, 1), ratio);
-        if (bound > (double)qcap) break;
+        if (bound > (double)qcap) {
+            // likely case: clique-like growth, ratio_d ~ ratio_{d-1} * d / (2 (d+1)).  If that fits, measure the
+            // exact size of the next level with a count-only pass before writing it.
+            const double predicted = (double)count * ratio * std::max(depth, 1) / (2.0 * (depth + 1));
+            if (opts.expand_depth > 0 || predicted * 1.5 > (double)qcap) break;
+            SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, sizeof(unsigned), st));
+            launch_general(cur, count, nullptr, c.counters, qcap, c.shard, nshards);
+            SGS_CUDA_TRY(cudaGetLastError());
+            SGS_CUDA_TRY(cudaMemcpyAsync(hcnt, c.counters, sizeof(hcnt), cudaMemcpyDeviceToHost, st));
+            SGS_CUDA_TRY(cudaStreamSynchronize(st));
+            if (hcnt[0] > qcap) break;
+        }
         SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, sizeof(unsigned), st));
         launch_general(cur, count, nxt, c.counters, qcap, c.shard, nshards);
         SGS_CUDA_TRY(cudaGetLastError());
