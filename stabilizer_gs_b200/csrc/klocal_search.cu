@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -508,6 +510,7 @@ Status klocal_search(const Hamiltonian &H, const sgs_opts &opts, sgs_result *out
     std::unique_ptr<KlocalMachine> M;
     Status s = KlocalMachine::create(H, opts, -1, M);
     if (!s.ok()) return s;
+    const auto t1 = std::chrono::steady_clock::now();
     std::vector<int> sr(H.n + 1), sp(H.n + 1);
     for (int m = 0; m <= H.n; m++) sr[m] = M->sright_count(m);
     sp[0] = M->nstates();
@@ -516,8 +519,15 @@ Status klocal_search(const Hamiltonian &H, const sgs_opts &opts, sgs_result *out
         if (!s.ok()) return s;
         sp[M->m()] = M->nstates();
     }
+    const auto t2 = std::chrono::steady_clock::now();
     s = M->ground_state(out);
     if (!s.ok()) return s;
+    if (getenv("SGS_DP_TRACE")) {
+        const auto t3 = std::chrono::steady_clock::now();
+        fprintf(stderr, "klocal_search: right environments %.3f ms, DP %.3f ms, ground state %.3f ms\n",
+                std::chrono::duration<double>(t1 - t0).count() * 1e3, std::chrono::duration<double>(t2 - t1).count() * 1e3,
+                std::chrono::duration<double>(t3 - t2).count() * 1e3);
+    }
     out->nsites = H.n;
     out->sright_counts = (int *)malloc(sizeof(int) * (H.n + 1));
     out->states_per_site = (int *)malloc(sizeof(int) * (H.n + 1));
