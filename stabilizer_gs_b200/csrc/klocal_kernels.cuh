@@ -194,27 +194,31 @@ SGS_D void group_project_site0(uint64_t *g, int &r, double *E, DpBack *bk)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_dp_move: State::move_to_next + project_to(k-1) (cpp/state.cpp:382-413, :460-466), one thread per state.
-// Output: the moved state (rows relative to o_{m+1}, valid bits relative to boff[m+1]), its table and
-// back-pointers in slab `s`, the terms it added, dead flag.
+// Device-resident control block of the DP: the host enqueues every site step back to back without
+// reading anything; the kernels take the batch sizes from here (grid-stride loops under fixed grids).
+struct DpCtl {
+    int nin;                 // states entering the current step
+    int total;               // children emitted by the current step
+    int nuniq;               // merged states = nin of the next step
+    int err;                 // 0 ok, 1 rank/table limit, 2 valid-set width, 5 state capacity, 6 child capacity, 7 history capacity
+    int hm_off, hb_off;      // bump offsets into the history pools
+    int step;                // steps logged so far
+    int caps, capc, hm_cap, hb_cap, log_cap;
+};
+struct DpStepLog { int m, nin, total, nuniq, hm_off, hb_off; };
+struct DpHistAdd { int nadd; uint16_t added[kDpMaxAdd]; };      // what one parent state added at one site
+
 struct DpMoved {
     uint64_t g[kDpRows];
     uint64_t valid[kDpVW];
     int r, sright, dead, nadd;
-    int added[kDpMaxAdd];          // term positions added at this site, in order
 };
 
-__global__ void k_dp_move(DpTerms H, int m, const DpState *__restrict__ in, const double *__restrict__ inE, int nin,
-                          int tstride, const DpGroup *__restrict__ level, DpMoved *__restrict__ out, double *slabE,
-                          DpBack *slabB, int slab_stride, int *err)
+// State::move_to_next + project_to(k-1) (cpp/state.cpp:382-413, :460-466) for one state.
+SGS_D void dp_move_one(const DpTerms &H, int m, int s, const DpState &st, const double *inE, int tstride,
+                       const DpGroup *level, DpMoved &mv, double *E, double *tE, DpBack *B, DpBack *tB, DpHistAdd *hist, int *err)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nin) return;
     const int k = H.k, o = m - k + 1;
-    const DpState &st = in[s];
-    DpMoved &mv = out[s];
-    double *E = slabE + (size_t)s * 2 * slab_stride, *tE = E + slab_stride;
-    DpBack *B = slabB + (size_t)s * 2 * slab_stride, *tB = B + slab_stride;
     uint64_t g[kDpRows + 1];
     int r = st.r;
     for (int i = 0; i < r; i++) g[i] = st.g[i];
@@ -222,7 +226,8 @@ __global__ void k_dp_move(DpTerms H, int m, const DpState *__restrict__ in, cons
     for (int i = 0; i < kDpVW; i++) valid[i] = st.valid[i];
     for (int e = 0; e < (1 << r); e++) { E[e] = inE[(size_t)s * tstride + e]; B[e].state = s; B[e].entry = (uint16_t)e; B[e].signs = 0; }
     const DpGroup &sr = level[st.sright];
-    mv.sright = st.sright; mv.dead = 0; mv.nadd = 0;
+    mv.sright = st.sright; mv.dead = 0; mv.nadd = 0; mv.r = 0;
+    if (hist) hist->nadd = 0;
 
     // stab_tmp = <stab, Sright> (cpp/state.cpp:384-390), bits only
     Ech tmp; tmp.n = 0;
@@ -237,7 +242,8 @@ __global__ void k_dp_move(DpTerms H, int m, const DpState *__restrict__ in, cons
         if (in_rref(g, r, P)) continue;
         if (r + 1 > kDpTab || r + 1 > kDpRows || nadd >= kDpMaxAdd) { atomicMax(err, 1); mv.dead = 1; return; }
         group_add(g, r, P, E, B, tE, tB, nadd);                        // State::add, cpp/state.cpp:367-380
-        mv.added[nadd++] = pos;
+        if (hist) hist->added[nadd] = (uint16_t)pos;
+        nadd++;
         const int qhi = min(m + k, H.n);
         for (int t = b0; t < H.boff[qhi]; t++) {
             if (!vget(valid, t - b0)) continue;
@@ -248,6 +254,7 @@ __global__ void k_dp_move(DpTerms H, int m, const DpState *__restrict__ in, cons
         }
     }
     mv.nadd = nadd;
+    if (hist) hist->nadd = nadd;
     for (int pos = b0; pos < b1; pos++) {                               // cpp/state.cpp:405-410
         const uint64_t P = rel_row(H.rows + (size_t)pos * H.W, H.W, o);
         if (in_rref(g, r, P)) group_add_energy(g, r, P, H.w[pos], E);
@@ -264,72 +271,108 @@ __global__ void k_dp_move(DpTerms H, int m, const DpState *__restrict__ in, cons
     for (int i = 0; i < kDpVW; i++) mv.valid[i] = valid[i];
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_dp_fanout: evolve_single's loop over compatible next right environments (cpp/state.cpp:467-479) with
-// State::check_Sright_validity (:347-365).  One thread per moved state; accept[s * maxfan + j] = 1 if the
-// j-th candidate of its map list is valid.
-__global__ void k_dp_fanout(DpTerms H, int m, const DpMoved *__restrict__ mv, int nin, const int *__restrict__ map_off,
-                            const int *__restrict__ map_idx, const DpGroup *__restrict__ next_level, int maxfan,
-                            unsigned char *__restrict__ accept, int *__restrict__ nacc)
+// k_dp_move: one thread per state (grid-stride over ctl->nin)
+__global__ void k_dp_move(DpTerms H, int m, const DpState *__restrict__ in, const double *__restrict__ inE, DpCtl *ctl,
+                          int tstride, const DpGroup *__restrict__ level, DpMoved *__restrict__ out, double *slabE,
+                          DpBack *slabB, int slab_stride, DpHistAdd *hm)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nin) return;
-    nacc[s] = 0;
-    if (mv[s].dead) return;
-    const int k = H.k, o1 = m - k + 2;                     // origin of level m+1
-    // span of the valid terms with last site in [m+1, min(m+k+1, n)) truncated to [max(m-k+2,0), m+2)
-    const uint64_t wmask = (2 * k >= 64) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
-    Ech e; e.n = 0;
-    const int b1 = H.boff[m + 1], t1 = H.boff[min(m + k + 1, H.n)];
-    for (int t = b1; t < t1; t++) {
-        if (!vget(mv[s].valid, t - b1)) continue;
-        ech_add(e, rel_row(H.rows + (size_t)t * H.W, H.W, o1) & wmask);
+    const int nin = ctl->nin;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nin; s += gridDim.x * blockDim.x) {
+        double *E = slabE + (size_t)s * 2 * slab_stride;
+        DpBack *B = slabB + (size_t)s * 2 * slab_stride;
+        DpHistAdd *h = nullptr;
+        if (ctl->hm_off + s < ctl->hm_cap) h = hm + ctl->hm_off + s; else atomicMax(&ctl->err, 7);
+        dp_move_one(H, m, s, in[s], inE, tstride, level, out[s], E, E + slab_stride, B, B + slab_stride, h, &ctl->err);
     }
-    int cnt = 0;
-    const int sr = mv[s].sright;
-    for (int j = map_off[sr]; j < map_off[sr + 1]; j++) {
-        const DpGroup &G = next_level[map_idx[j]];
-        bool ok = true;
-        for (int i = 0; i < G.r && ok; i++) ok = ech_reduce(e, G.g[i]) == 0;
-        accept[(size_t)s * maxfan + (j - map_off[sr])] = ok ? 1 : 0;
-        cnt += ok;
-    }
-    nacc[s] = cnt;
 }
 
-// exclusive scan of nacc → child offsets; one thread (the lists are a few hundred entries)
-__global__ void k_dp_scan(const int *__restrict__ nacc, int nin, int *__restrict__ off, int *total)
+// span of the valid terms with last site in [m+1, min(m+k+1, n)) truncated to [max(m-k+2,0), m+2):
+// State::check_Sright_validity (cpp/state.cpp:347-365)
+SGS_D void dp_valid_span(const DpTerms &H, int m, const DpMoved &mv, Ech &e)
 {
-    if (threadIdx.x || blockIdx.x) return;
+    const int k = H.k, o1 = m - k + 2;                     // origin of level m+1
+    const uint64_t wmask = (2 * k >= 64) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
+    e.n = 0;
+    const int b1 = H.boff[m + 1], t1 = H.boff[min(m + k + 1, H.n)];
+    for (int t = b1; t < t1; t++) {
+        if (!vget(mv.valid, t - b1)) continue;
+        ech_add(e, rel_row(H.rows + (size_t)t * H.W, H.W, o1) & wmask);
+    }
+}
+SGS_D bool dp_accepts(const Ech &e, const DpGroup &G)
+{
+    for (int i = 0; i < G.r; i++) if (ech_reduce(e, G.g[i]) != 0) return false;
+    return true;
+}
+
+// k_dp_fanout: evolve_single's loop over compatible next right environments (cpp/state.cpp:467-479):
+// nacc[s] = number of accepted candidates of state s
+__global__ void k_dp_fanout(DpTerms H, int m, const DpMoved *__restrict__ mv, const DpCtl *ctl, const int *__restrict__ map_off,
+                            const int *__restrict__ map_idx, const DpGroup *__restrict__ next_level, int *__restrict__ nacc)
+{
+    const int nin = ctl->nin;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nin; s += gridDim.x * blockDim.x) {
+        int cnt = 0;
+        if (!mv[s].dead) {
+            Ech e;
+            dp_valid_span(H, m, mv[s], e);
+            const int sr = mv[s].sright;
+            for (int j = map_off[sr]; j < map_off[sr + 1]; j++) cnt += dp_accepts(e, next_level[map_idx[j]]);
+        }
+        nacc[s] = cnt;
+    }
+}
+
+// exclusive scan of nacc → child offsets; one block
+__global__ void k_dp_scan(const int *__restrict__ nacc, DpCtl *ctl, int *__restrict__ off)
+{
+    __shared__ int part[1024];
+    const int nin = ctl->nin, tid = threadIdx.x, nt = blockDim.x;
+    const int per = (nin + nt - 1) / nt, lo = min(tid * per, nin), hi = min(lo + per, nin);
     int acc = 0;
-    for (int i = 0; i < nin; i++) { off[i] = acc; acc += nacc[i]; }
-    off[nin] = acc;
-    *total = acc;
+    for (int i = lo; i < hi; i++) acc += nacc[i];
+    part[tid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < nt; i++) { const int v = part[i]; part[i] = run; run += v; }
+        ctl->total = run;
+        if (run > ctl->capc) { ctl->err = max(ctl->err, 6); ctl->total = 0; }
+        off[nin] = run;
+    }
+    __syncthreads();
+    acc = part[tid];
+    for (int i = lo; i < hi; i++) { off[i] = acc; acc += nacc[i]; }
 }
 
 // children in deterministic (parent, map order): key + reference to the moved state
-__global__ void k_dp_emit(DpTerms H, int m, const DpMoved *__restrict__ mv, int nin, const int *__restrict__ map_off,
-                          const int *__restrict__ map_idx, int maxfan, const unsigned char *__restrict__ accept,
-                          const int *__restrict__ off, DpKey *__restrict__ keys, int *__restrict__ parent)
+__global__ void k_dp_emit(DpTerms H, int m, const DpMoved *__restrict__ mv, const DpCtl *ctl, const int *__restrict__ map_off,
+                          const int *__restrict__ map_idx, const DpGroup *__restrict__ next_level, const int *__restrict__ off,
+                          DpKey *__restrict__ keys, int *__restrict__ parent)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nin || mv[s].dead) return;
+    const int nin = ctl->nin;
+    if (ctl->total == 0) return;
     const int k = H.k, m1 = m + 1;
     // key: valid bits for last site in [m1+1, min(m1+k-1, n)), positions relative to boff[m1]
     const int lo = H.boff[min(m1 + 1, H.n + 1)] - H.boff[m1];
     const int hi = H.boff[min(max(m1 + k - 1, m1 + 1), H.n)] - H.boff[m1];
-    int c = off[s];
-    const int sr = mv[s].sright;
-    for (int j = map_off[sr]; j < map_off[sr + 1]; j++) {
-        if (!accept[(size_t)s * maxfan + (j - map_off[sr])]) continue;
-        DpKey &K = keys[c];
-        for (int i = 0; i < kDpRows; i++) K.g[i] = mv[s].g[i];
-        for (int i = 0; i < kDpVW; i++) K.v[i] = 0;
-        for (int b = lo; b < hi; b++) if (vget(mv[s].valid, b)) K.v[b >> 6] |= 1ULL << (b & 63);
-        K.r = mv[s].r;
-        K.sright = map_idx[j];
-        parent[c] = s;
-        c++;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nin; s += gridDim.x * blockDim.x) {
+        if (mv[s].dead) continue;
+        Ech e;
+        dp_valid_span(H, m, mv[s], e);
+        int c = off[s];
+        const int sr = mv[s].sright;
+        for (int j = map_off[sr]; j < map_off[sr + 1]; j++) {
+            if (!dp_accepts(e, next_level[map_idx[j]])) continue;
+            DpKey &K = keys[c];
+            for (int i = 0; i < kDpRows; i++) K.g[i] = mv[s].g[i];
+            for (int i = 0; i < kDpVW; i++) K.v[i] = 0;
+            for (int b = lo; b < hi; b++) if (vget(mv[s].valid, b)) K.v[b >> 6] |= 1ULL << (b & 63);
+            K.r = mv[s].r;
+            K.sright = map_idx[j];
+            parent[c] = s;
+            c++;
+        }
     }
 }
 
@@ -350,65 +393,112 @@ SGS_D int key_cmp(const DpGroup &a, const DpGroup &b)
     return 0;
 }
 
-// leader[c] = first entry with the same key (the lists are a few hundred entries: all-pairs compare)
+// leader[c] = first entry with the same key (the lists are a few hundred to a few thousand entries:
+// all-pairs compare); the list length is read from the device
 template <typename K>
-__global__ void k_group_leader(const K *__restrict__ keys, int nc, int *__restrict__ leader)
+__global__ void k_group_leader(const K *__restrict__ keys, const int *nc_dev, int *__restrict__ leader)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nc) return;
-    int lead = c;
-    for (int j = 0; j < c; j++) if (key_cmp(keys[j], keys[c]) == 0) { lead = j; break; }
-    leader[c] = lead;
+    const int nc = *nc_dev;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        int lead = c;
+        for (int j = 0; j < c; j++) if (key_cmp(keys[j], keys[c]) == 0) { lead = j; break; }
+        leader[c] = lead;
+    }
 }
 
 // rank[c] (leaders only, else -1) = number of distinct smaller keys: the deterministic total order that
 // replaces the reference's std::map-on-a-boost-hash iteration order
 template <typename K>
-__global__ void k_group_rank(const K *__restrict__ keys, int nc, const int *__restrict__ leader, int *__restrict__ rank, int *nuniq)
+__global__ void k_group_rank(const K *__restrict__ keys, const int *nc_dev, const int *__restrict__ leader, int *__restrict__ rank, int *nuniq)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nc) return;
-    if (leader[c] != c) { rank[c] = -1; return; }
-    int rk = 0;
-    for (int j = 0; j < nc; j++) if (leader[j] == j && key_cmp(keys[j], keys[c]) < 0) rk++;
-    rank[c] = rk;
-    atomicAdd(nuniq, 1);
+    const int nc = *nc_dev;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        if (leader[c] != c) { rank[c] = -1; continue; }
+        int rk = 0;
+        for (int j = 0; j < nc; j++) if (leader[j] == j && key_cmp(keys[j], keys[c]) < 0) rk++;
+        rank[c] = rk;
+        atomicAdd(nuniq, 1);
+    }
 }
 
 // merged states of site m+1, in key order: element-wise minimum over the children of a key, exact ties
 // won by the later child (merge_gs keeps the newcomer unless the incumbent is strictly lower,
-// cpp/stab.cpp:832).  One thread per (leader, table entry).
+// cpp/stab.cpp:832).  One block per leader (grid-stride), one thread per table entry.
 __global__ void k_dp_merge(const DpKey *__restrict__ keys, const int *__restrict__ parent, const int *__restrict__ leader,
-                           const int *__restrict__ rank, int nc, const double *__restrict__ slabE, const DpBack *__restrict__ slabB,
+                           const int *__restrict__ rank, DpCtl *ctl, const double *__restrict__ slabE, const DpBack *__restrict__ slabB,
                            int slab_stride, int tstride, DpState *__restrict__ outS, double *__restrict__ outE,
-                           DpBack *__restrict__ outB, const DpMoved *__restrict__ mv)
+                           DpBack *__restrict__ hb, const DpMoved *__restrict__ mv)
 {
-    const int c = blockIdx.x;
-    if (c >= nc || leader[c] != c) return;
-    const int dst = rank[c];
-    const int r = keys[c].r;
-    for (int e = threadIdx.x; e < (1 << r); e += blockDim.x) {
-        double best = 0.0;
-        DpBack bb;
-        bb.state = -1; bb.entry = 0; bb.signs = 0;
-        bool have = false;
-        for (int j = c; j < nc; j++) {
-            if (leader[j] != c) continue;
-            const int p = parent[j];
-            const double v = slabE[(size_t)p * 2 * slab_stride + e];
-            if (!have || !(best < v)) { best = v; bb = slabB[(size_t)p * 2 * slab_stride + e]; have = true; }
+    const int nc = ctl->total;
+    if (ctl->nuniq > ctl->caps) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&ctl->err, 5); return; }
+    const bool hist_ok = (long long)ctl->hb_off + (long long)ctl->nuniq * tstride <= (long long)ctl->hb_cap;
+    if (!hist_ok && threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&ctl->err, 7);
+    for (int c = blockIdx.x; c < nc; c += gridDim.x) {
+        if (leader[c] != c) continue;
+        const int dst = rank[c];
+        const int r = keys[c].r;
+        for (int e = threadIdx.x; e < (1 << r); e += blockDim.x) {
+            double best = 0.0;
+            DpBack bb;
+            bb.state = -1; bb.entry = 0; bb.signs = 0;
+            bool have = false;
+            for (int j = c; j < nc; j++) {
+                if (leader[j] != c) continue;
+                const int p = parent[j];
+                const double v = slabE[(size_t)p * 2 * slab_stride + e];
+                if (!have || !(best < v)) { best = v; bb = slabB[(size_t)p * 2 * slab_stride + e]; have = true; }
+            }
+            outE[(size_t)dst * tstride + e] = best;
+            if (hist_ok) hb[(size_t)ctl->hb_off + (size_t)dst * tstride + e] = bb;
         }
-        outE[(size_t)dst * tstride + e] = best;
-        outB[(size_t)dst * tstride + e] = bb;
+        if (threadIdx.x == 0) {
+            DpState &S = outS[dst];
+            const int p = parent[c];
+            for (int i = 0; i < kDpRows; i++) S.g[i] = keys[c].g[i];
+            for (int i = 0; i < kDpVW; i++) S.valid[i] = mv[p].valid[i];
+            S.r = r;
+            S.sright = keys[c].sright;
+        }
     }
-    if (threadIdx.x == 0) {
-        DpState &S = outS[dst];
-        const int p = parent[c];
-        for (int i = 0; i < kDpRows; i++) S.g[i] = keys[c].g[i];
-        for (int i = 0; i < kDpVW; i++) S.valid[i] = mv[p].valid[i];
-        S.r = r;
-        S.sright = keys[c].sright;
+}
+
+// end of a site step: log it, advance the history offsets, the merged states become the next input
+__global__ void k_dp_advance(DpCtl *ctl, DpStepLog *log, int m, int tstride)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    if (ctl->step < ctl->log_cap) {
+        DpStepLog &L = log[ctl->step];
+        L.m = m; L.nin = ctl->nin; L.total = ctl->total; L.nuniq = ctl->nuniq; L.hm_off = ctl->hm_off; L.hb_off = ctl->hb_off;
+    } else ctl->err = max(ctl->err, 7);
+    if (ctl->err) ctl->nuniq = 0;          // a failed step leaves no state: later steps become no-ops, the host sees err
+    ctl->step++;
+    ctl->hm_off += ctl->nin;
+    ctl->hb_off += ctl->nuniq * tstride;
+    ctl->nin = ctl->nuniq;
+    ctl->total = 0;
+    ctl->nuniq = 0;
+}
+
+// history of (state, entry) of the current site back to step `floor`: (term position, sign) pairs in the order
+// the reference appends them (Ps_indices / Ps_signs, cpp/stab.cpp:752-759).  One thread.
+__global__ void k_dp_trace(const DpCtl *ctl, const DpStepLog *log, const DpHistAdd *hm, const DpBack *hb, int tstride, int floor_step,
+                           int state, int entry, int *out_pos, int *out_sign, int *out_n, int cap)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    int n = 0, s = state, e = entry;
+    for (int t = ctl->step - 1; t >= floor_step; t--) {
+        const DpStepLog &L = log[t];
+        const DpBack b = hb[(size_t)L.hb_off + (size_t)s * tstride + e];
+        if (b.state < 0) break;
+        const DpHistAdd &h = hm[L.hm_off + b.state];
+        for (int a = h.nadd - 1; a >= 0 && n < cap; a--) { out_pos[n] = h.added[a]; out_sign[n] = ((b.signs >> a) & 1) ? -1 : 1; n++; }
+        s = b.state; e = b.entry;
     }
+    for (int i = 0; i < n / 2; i++) {       // collected newest-first: reverse to chronological order
+        int t = out_pos[i]; out_pos[i] = out_pos[n - 1 - i]; out_pos[n - 1 - i] = t;
+        t = out_sign[i]; out_sign[i] = out_sign[n - 1 - i]; out_sign[n - 1 - i] = t;
+    }
+    *out_n = n;
 }
 
 // valid bits outside the key range may differ between the children of one key (the reference keeps the
@@ -506,6 +596,58 @@ __global__ void k_sr_evolve(DpTerms H, int m, const DpGroup *__restrict__ next, 
         }
     }
     nout[p] = nbr;
+}
+
+// children of all parents, compacted in parent order: flat[], par[] and the per-parent offsets; one block
+__global__ void k_sr_flatten(const DpGroup *__restrict__ strided, const int *__restrict__ nout, int nnext, int maxbranch,
+                             DpGroup *__restrict__ flat, int *__restrict__ par, int *__restrict__ offp, int *total)
+{
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int p = 0; p < nnext; p++) { offp[p] = run; run += nout[p]; }
+        offp[nnext] = run;
+        *total = run;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < nnext; p += blockDim.x) {
+        const int o = offp[p], c = offp[p + 1] - o;
+        for (int j = 0; j < c; j++) { flat[o + j] = strided[(size_t)p * maxbranch + j]; par[o + j] = p; }
+    }
+}
+
+// get_map_from_stabs (cpp/state.cpp:187-216) on the device: distinct groups in rank order and, per group, the
+// ascending list of distinct parents (py/state.py:523 uses a set).  info = {nuniq, nlinks, maxfan}.  One block.
+__global__ void k_sr_build(const DpGroup *__restrict__ flat, const int *__restrict__ par, const int *__restrict__ offp,
+                           const int *__restrict__ leader, const int *__restrict__ rank, const int *total_dev, const int *nuniq_dev,
+                           DpGroup *__restrict__ groups, int *__restrict__ map_off, int *__restrict__ map_idx, int *__restrict__ cnt, int *info)
+{
+    const int total = *total_dev, nuniq = *nuniq_dev;
+    for (int g = threadIdx.x; g <= nuniq; g += blockDim.x) cnt[g] = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < total; c += blockDim.x) {
+        const int g = rank[leader[c]];
+        if (leader[c] == c) groups[g] = flat[c];
+        bool first = true;                       // first child of this parent in this group?
+        for (int j = offp[par[c]]; j < c; j++) if (leader[j] == leader[c]) { first = false; break; }
+        if (first) atomicAdd(&cnt[g], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0, mf = 0;
+        for (int g = 0; g < nuniq; g++) { map_off[g] = run; run += cnt[g]; mf = max(mf, cnt[g]); }
+        map_off[nuniq] = run;
+        info[0] = nuniq; info[1] = run; info[2] = mf;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < nuniq; g += blockDim.x) {
+        int k = map_off[g];
+        for (int c = 0; c < total; c++) {
+            if (rank[leader[c]] != g) continue;
+            bool first = true;
+            for (int j = offp[par[c]]; j < c; j++) if (leader[j] == leader[c]) { first = false; break; }
+            if (first) map_idx[k++] = par[c];
+        }
+    }
 }
 
 }  // namespace sgs

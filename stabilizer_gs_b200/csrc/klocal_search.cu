@@ -13,6 +13,7 @@
 #include <map>
 #include <vector>
 
+#include "arena.hpp"
 #include "common.hpp"
 #include "group_ops.hpp"
 #include "klocal_kernels.cuh"
@@ -22,33 +23,65 @@ namespace sgs {
 
 namespace {
 
-template <typename T>
-struct DBuf {                       // growable device buffer
-    T *p = nullptr;
-    size_t cap = 0;
-    ~DBuf() { if (p) cudaFree(p); }
-    cudaError_t need(size_t n)
+// Bump allocator over one cached device arena (arena.hpp); when the arena is exhausted further chunks are
+// cudaMalloc'ed and freed with the machine.  Nothing is freed individually: a machine lives for one search.
+struct DevPool {
+    int device = 0;
+    void *arena = nullptr;
+    std::vector<void *> extra;
+    char *cur = nullptr;
+    size_t left = 0;
+    ~DevPool()
     {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        cap = std::max<size_t>(n, cap * 2 + 64);
-        return cudaMalloc((void **)&p, cap * sizeof(T));
+        if (arena) klocal_arena().release(device, arena);
+        for (void *c : extra) cudaFree(c);
+    }
+    cudaError_t open(int dev, size_t bytes)
+    {
+        device = dev;
+        size_t got = 0;
+        cudaError_t e = klocal_arena().acquire(dev, bytes, &arena, &got);
+        if (e != cudaSuccess) return e;
+        cur = (char *)arena; left = got;
+        return cudaSuccess;
+    }
+    cudaError_t take(void **out, size_t bytes)
+    {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes > left) {
+            const size_t sz = std::max<size_t>(bytes, (size_t)64 << 20);
+            void *c = nullptr;
+            cudaError_t e = cudaMalloc(&c, sz);
+            if (e != cudaSuccess) return e;
+            extra.push_back(c);
+            cur = (char *)c; left = sz;
+        }
+        *out = cur; cur += bytes; left -= bytes;
+        return cudaSuccess;
     }
 };
 
-struct Level {                      // type_Sright (cpp/state.hpp:49-51) of one site
-    std::vector<DpGroup> groups;    // sorted by content
-    std::vector<int> map_off, map_idx;   // per group: indices into the next level's list
-    int maxfan = 0;
-    DpGroup *d_groups = nullptr;
-    int *d_map_off = nullptr, *d_map_idx = nullptr;
-    void free_dev() { cudaFree(d_groups); cudaFree(d_map_off); cudaFree(d_map_idx); d_groups = nullptr; d_map_off = d_map_idx = nullptr; }
+template <typename T>
+struct DBuf {                       // growable device buffer carved from the pool (an outgrown region is abandoned)
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(DevPool &pool, size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        const size_t want = std::max<size_t>(n, cap * 2 + 64);
+        void *q = nullptr;
+        cudaError_t e = pool.take(&q, want * sizeof(T));
+        if (e != cudaSuccess) return e;
+        p = (T *)q; cap = want;
+        return cudaSuccess;
+    }
 };
 
-struct Step {                       // history of one site step (what the reference keeps per table entry)
-    std::vector<int> nadd;          // per parent state
-    std::vector<int> added;         // per parent state, kDpMaxAdd term positions
-    std::vector<DpBack> back;       // per new state * tstride
+struct Level {                      // type_Sright (cpp/state.hpp:49-51) of one site, device resident
+    int count = 0, nlinks = 0, maxfan = 0;
+    DpGroup *d_groups = nullptr;
+    int *d_map_off = nullptr, *d_map_idx = nullptr;
+    std::vector<DpGroup> groups;    // host copy (periodic driver only)
 };
 
 bool group_equal(const DpGroup &a, const DpGroup &b)
@@ -67,70 +100,83 @@ struct KlocalMachine::Impl {
     sgs_opts opts{};
     int device = 0;
     int n = 0, k = 0, T = 0, W = 1;
+    bool keep_host_levels = false;
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool seg_open = false;
     uint64_t *d_rows = nullptr;
     double *d_w = nullptr;
-    int *d_boff = nullptr, *d_fidx = nullptr, *d_err = nullptr, *d_cnt = nullptr;
+    int *d_boff = nullptr, *d_fidx = nullptr, *d_info = nullptr;
+    DpCtl *d_ctl = nullptr;
+    DpStepLog *d_log = nullptr;
+    int log_cap = 1 << 14;
     std::vector<int> boff;
     DpTerms terms{};
+    DevPool pool;
     std::map<int, Level> lv;
-    int m_ = 0, nstates_ = 0, tstride = 1, slab_stride = 1;
-    DBuf<DpState> states, nstates_buf;
-    DBuf<double> tabE, ntabE, slabE;
-    DBuf<DpBack> tabB, ntabB, slabB;
+    int m_ = 0, tstride = 1, slab_stride = 1;
+    // capacities of the DP batch buffers (grown x4 and the run restarted on overflow)
+    int caps = 0, capc = 0, hm_cap = 0, hb_cap = 0;
+    DBuf<DpState> statesA, statesB;
+    DBuf<double> tabEA, tabEB, slabE;
+    DBuf<DpBack> slabB, hb;
+    DBuf<DpHistAdd> hm;
     DBuf<DpMoved> moved;
-    DBuf<unsigned char> accept;
-    DBuf<int> nacc, off, parent, leader, rank;
+    DBuf<int> nacc, off, parent, leader, rank, trace;
     DBuf<DpKey> keys;
+    // right-environment scratch
     DBuf<SrBranch> srscratch;
-    DBuf<DpGroup> srout;
-    std::vector<Step> steps;
+    DBuf<DpGroup> srout, srflat, srgroups;
+    DBuf<int> srcnt, srpar, sroffp, srleader, srrank, srmapoff, srmapidx, srgcnt;
+    bool cur_is_A = true;
     int hist_floor = 0;
-    uint64_t transitions = 0;
+    DpCtl hctl{};                  // last host copy of the control block
+    bool hctl_valid = false;
     unsigned launches = 0;
     double dev_seconds = 0.0;
+    Status pending;                // error met inside a const accessor, returned by the next call
 
     ~Impl();
-    Status init(int periodic_cmax);
-    Status upload_level(Level &L);
+    Status init();
+    Status ensure_caps(int scale);
     Status gen_level(int m, const Level &next, Level &out);
     Status gen_sright_all();
+    Status write_ctl(int nin, bool reset_history);
+    Status sync_ctl();
     Status init_states();
     Status evolve();
-    Status set_states(const std::vector<HostState> &hs, int m);
+    Status set_states(const std::vector<HostState> &hs, int m, bool reset_history);
     Status get_states(std::vector<HostState> &hs);
     Status ground_state(sgs_result *out);
-    std::vector<std::pair<int, int>> traceback(int state, int entry) const;   // (file index, sign) in history order
-    Status check_err(const char *what);
+    Status traceback(int state, int entry, std::vector<std::pair<int, int>> &out);   // (file index, sign) in history order
+    Status fetch_log(std::vector<DpStepLog> &log);
+    DpState *cur_states() { return cur_is_A ? statesA.p : statesB.p; }
+    DpState *nxt_states() { return cur_is_A ? statesB.p : statesA.p; }
+    double *cur_E() { return cur_is_A ? tabEA.p : tabEB.p; }
+    double *nxt_E() { return cur_is_A ? tabEB.p : tabEA.p; }
 };
 
 KlocalMachine::Impl::~Impl()
 {
     cudaSetDevice(device);
-    for (auto &kv : lv) kv.second.free_dev();
-    cudaFree(d_rows); cudaFree(d_w); cudaFree(d_boff); cudaFree(d_fidx); cudaFree(d_err); cudaFree(d_cnt);
+    cudaFree(d_rows); cudaFree(d_w); cudaFree(d_boff); cudaFree(d_fidx); cudaFree(d_info); cudaFree(d_ctl); cudaFree(d_log);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
 }
 
-Status KlocalMachine::Impl::check_err(const char *what)
+static Status ctl_error(int err, const char *what)
 {
-    int err = 0;
-    SGS_CUDA_TRY(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SGS_CUDA_TRY(cudaStreamSynchronize(st));
-    if (err == 0) return Status();
     const char *why = err == 1 ? "window group rank exceeds the table limit (k too large)"
                       : err == 2 ? "more than 256 terms in k+2 consecutive last-site buckets"
                       : err == 3 ? "more than 30 terms share one last site"
-                                 : "right-environment branch capacity exceeded";
-    return Status::fail(SGS_ERR_LIMIT, std::string(what) + ": " + why);
+                      : err == 4 ? "right-environment branch capacity exceeded"
+                                 : "batch capacity exceeded";
+    return Status::fail(err >= 5 ? SGS_ERR_OVERFLOW : SGS_ERR_LIMIT, std::string(what) + ": " + why);
 }
 
-Status KlocalMachine::Impl::init(int periodic_cmax)
+Status KlocalMachine::Impl::init()
 {
-    (void)periodic_cmax;
     n = H.n; k = H.k; T = H.T();
     if (k < 1 || k > kDpMaxK) return Status::fail(SGS_ERR_LIMIT, "k-local DP supports 1 <= k <= 15");
     for (int t = 0; t < T; t++)
@@ -163,153 +209,187 @@ Status KlocalMachine::Impl::init(int periodic_cmax)
     SGS_CUDA_TRY(cudaMalloc((void **)&d_w, w.size() * 8));
     SGS_CUDA_TRY(cudaMalloc((void **)&d_boff, boff.size() * 4));
     SGS_CUDA_TRY(cudaMalloc((void **)&d_fidx, fidx.size() * 4));
-    SGS_CUDA_TRY(cudaMalloc((void **)&d_err, 4));
-    SGS_CUDA_TRY(cudaMalloc((void **)&d_cnt, 16));
-    SGS_CUDA_TRY(cudaMemcpy(d_rows, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice));
-    SGS_CUDA_TRY(cudaMemcpy(d_w, w.data(), w.size() * 8, cudaMemcpyHostToDevice));
-    SGS_CUDA_TRY(cudaMemcpy(d_boff, boff.data(), boff.size() * 4, cudaMemcpyHostToDevice));
-    SGS_CUDA_TRY(cudaMemcpy(d_fidx, fidx.data(), fidx.size() * 4, cudaMemcpyHostToDevice));
-    SGS_CUDA_TRY(cudaMemset(d_err, 0, 4));
+    SGS_CUDA_TRY(cudaMalloc((void **)&d_info, 64));
+    SGS_CUDA_TRY(cudaMalloc((void **)&d_ctl, sizeof(DpCtl)));
+    SGS_CUDA_TRY(cudaMalloc((void **)&d_log, sizeof(DpStepLog) * log_cap));
+    SGS_CUDA_TRY(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(d_w, w.data(), w.size() * 8, cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(d_boff, boff.data(), boff.size() * 4, cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(d_fidx, fidx.data(), fidx.size() * 4, cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaMemsetAsync(d_info, 0, 64, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
     terms.n = n; terms.k = k; terms.T = T; terms.W = W;
     terms.rows = d_rows; terms.w = d_w; terms.boff = d_boff; terms.file_index = d_fidx;
     tstride = 1 << std::min(k, kDpTab);
     slab_stride = 1 << std::min(k, kDpTab);
-    return Status();
+    {   // one cached arena for the DP batch buffers, the right-environment scratch and the level tables
+        const size_t c0 = (size_t)std::max<long long>(2048, (1ll << 22) / ((long long)slab_stride * 16));
+        const size_t est = c0 * (2 * sizeof(DpState) + sizeof(DpMoved) + 8 * sizeof(DpKey) + 64 * sizeof(DpHistAdd) + 64) +
+                           c0 * (size_t)tstride * 16 + c0 * 2 * (size_t)slab_stride * 16 +
+                           c0 * 64 * (size_t)std::min(tstride, 64) * sizeof(DpBack) + ((size_t)96 << 20);
+        SGS_CUDA_TRY(pool.open(device, est));
+    }
+    return ensure_caps(1);
 }
 
-Status KlocalMachine::Impl::upload_level(Level &L)
+// batch buffers of the DP; scale = 1 on creation, x4 per retry after an overflow
+Status KlocalMachine::Impl::ensure_caps(int scale)
 {
-    L.free_dev();
-    const size_t ng = std::max<size_t>(L.groups.size(), 1);
-    SGS_CUDA_TRY(cudaMalloc((void **)&L.d_groups, ng * sizeof(DpGroup)));
-    SGS_CUDA_TRY(cudaMalloc((void **)&L.d_map_off, (L.groups.size() + 1) * sizeof(int)));
-    SGS_CUDA_TRY(cudaMalloc((void **)&L.d_map_idx, std::max<size_t>(L.map_idx.size(), 1) * sizeof(int)));
-    if (!L.groups.empty()) SGS_CUDA_TRY(cudaMemcpy(L.d_groups, L.groups.data(), L.groups.size() * sizeof(DpGroup), cudaMemcpyHostToDevice));
-    if (L.map_off.size() != L.groups.size() + 1) L.map_off.assign(L.groups.size() + 1, 0);
-    SGS_CUDA_TRY(cudaMemcpy(L.d_map_off, L.map_off.data(), L.map_off.size() * sizeof(int), cudaMemcpyHostToDevice));
-    if (!L.map_idx.empty()) SGS_CUDA_TRY(cudaMemcpy(L.d_map_idx, L.map_idx.data(), L.map_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
-    L.maxfan = 0;
-    for (size_t i = 0; i + 1 < L.map_off.size(); i++) L.maxfan = std::max(L.maxfan, L.map_off[i + 1] - L.map_off[i]);
+    const long long base = std::max<long long>(2048, (1ll << 22) / ((long long)slab_stride * 16));   // k=4: 16384 states
+    caps = (int)std::min<long long>(base * scale, 1ll << 22);
+    capc = (int)std::min<long long>((long long)caps * 8, 1ll << 24);
+    hm_cap = (int)std::min<long long>((long long)caps * 64, 1ll << 26);
+    hb_cap = (int)std::min<long long>((long long)caps * 64 * std::min(tstride, 64), 1ll << 28);
+    SGS_CUDA_TRY(statesA.need(pool, caps)); SGS_CUDA_TRY(statesB.need(pool, caps));
+    SGS_CUDA_TRY(tabEA.need(pool, (size_t)caps * tstride)); SGS_CUDA_TRY(tabEB.need(pool, (size_t)caps * tstride));
+    SGS_CUDA_TRY(slabE.need(pool, (size_t)caps * 2 * slab_stride)); SGS_CUDA_TRY(slabB.need(pool, (size_t)caps * 2 * slab_stride));
+    SGS_CUDA_TRY(moved.need(pool, caps)); SGS_CUDA_TRY(nacc.need(pool, caps + 1)); SGS_CUDA_TRY(off.need(pool, caps + 1));
+    SGS_CUDA_TRY(keys.need(pool, capc)); SGS_CUDA_TRY(parent.need(pool, capc)); SGS_CUDA_TRY(leader.need(pool, capc)); SGS_CUDA_TRY(rank.need(pool, capc));
+    SGS_CUDA_TRY(hm.need(pool, hm_cap)); SGS_CUDA_TRY(hb.need(pool, hb_cap));
+    SGS_CUDA_TRY(trace.need(pool, 2 * (size_t)(T + 16) + 32));
     return Status();
 }
 
-// one backward step of generate_Sright_all (cpp/state.cpp:222-236): level m from level m+1
+// one backward step of generate_Sright_all (cpp/state.cpp:222-236): level m from level m+1, all on the device;
+// the host only reads three integers (distinct groups, links, widest fan-out)
 Status KlocalMachine::Impl::gen_level(int m, const Level &next, Level &out)
 {
-    const int nnext = (int)next.groups.size();
+    const int nnext = next.count;
     const int nterm = boff[m + 1] - boff[m];
-    int maxbranch = 1;
-    for (int i = 0; i < nterm && maxbranch < (1 << 20); i++) maxbranch *= 2;
     if (nterm > 16) return Status::fail(SGS_ERR_LIMIT, "more than 16 terms share one last site (2^t right-environment branches)");
-    SGS_CUDA_TRY(srscratch.need((size_t)nnext * 2 * maxbranch));
-    SGS_CUDA_TRY(srout.need((size_t)nnext * maxbranch));
-    SGS_CUDA_TRY(nacc.need(nnext + 1));
-    k_sr_evolve<<<(nnext + 63) / 64, 64, 0, st>>>(terms, m, next.d_groups, nnext, maxbranch, srout.p, nacc.p, srscratch.p, d_err);
-    launches++;
+    const int maxbranch = 1 << nterm;
+    const size_t bound = (size_t)nnext * maxbranch;
+    SGS_CUDA_TRY(srscratch.need(pool, 2 * bound));
+    SGS_CUDA_TRY(srout.need(pool, bound)); SGS_CUDA_TRY(srflat.need(pool, bound)); SGS_CUDA_TRY(srgroups.need(pool, bound));
+    SGS_CUDA_TRY(srcnt.need(pool, nnext + 1)); SGS_CUDA_TRY(sroffp.need(pool, nnext + 1));
+    SGS_CUDA_TRY(srpar.need(pool, bound)); SGS_CUDA_TRY(srleader.need(pool, bound)); SGS_CUDA_TRY(srrank.need(pool, bound));
+    SGS_CUDA_TRY(srmapoff.need(pool, bound + 1)); SGS_CUDA_TRY(srmapidx.need(pool, bound)); SGS_CUDA_TRY(srgcnt.need(pool, bound + 1));
+    int *d_total = d_info + 4, *d_nuniq = d_info + 5, *d_err = d_info + 6;
+    SGS_CUDA_TRY(cudaMemsetAsync(d_info, 0, 32, st));
+    k_sr_evolve<<<(nnext + 63) / 64, 64, 0, st>>>(terms, m, next.d_groups, nnext, maxbranch, srout.p, srcnt.p, srscratch.p, d_err);
+    k_sr_flatten<<<1, 256, 0, st>>>(srout.p, srcnt.p, nnext, maxbranch, srflat.p, srpar.p, sroffp.p, d_total);
+    const int gb = (int)std::min<size_t>((bound + 63) / 64, 512);
+    k_group_leader<DpGroup><<<gb, 64, 0, st>>>(srflat.p, d_total, srleader.p);
+    k_group_rank<DpGroup><<<gb, 64, 0, st>>>(srflat.p, d_total, srleader.p, srrank.p, d_nuniq);
+    k_sr_build<<<1, 256, 0, st>>>(srflat.p, srpar.p, sroffp.p, srleader.p, srrank.p, d_total, d_nuniq, srgroups.p, srmapoff.p,
+                                  srmapidx.p, srgcnt.p, d_info);
+    launches += 5;
     SGS_CUDA_TRY(cudaGetLastError());
-    std::vector<int> cnt(nnext);
-    SGS_CUDA_TRY(cudaMemcpyAsync(cnt.data(), nacc.p, nnext * sizeof(int), cudaMemcpyDeviceToHost, st));
-    Status s = check_err("right environments");
-    if (!s.ok()) return s;
-    // gather the children contiguously (device-to-device), then group by content on the device
-    int total = 0;
-    for (int c : cnt) total += c;
-    DBuf<DpGroup> flat;
-    SGS_CUDA_TRY(flat.need(std::max(total, 1)));
-    std::vector<int> par;
-    par.reserve(total);
-    int at = 0;
-    for (int p = 0; p < nnext; p++) {
-        if (cnt[p]) SGS_CUDA_TRY(cudaMemcpyAsync(flat.p + at, srout.p + (size_t)p * maxbranch, cnt[p] * sizeof(DpGroup), cudaMemcpyDeviceToDevice, st));
-        for (int j = 0; j < cnt[p]; j++) par.push_back(p);
-        at += cnt[p];
-    }
-    SGS_CUDA_TRY(leader.need(std::max(total, 1)));
-    SGS_CUDA_TRY(rank.need(std::max(total, 1)));
-    SGS_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 16, st));
-    if (total) {
-        k_group_leader<DpGroup><<<(total + 63) / 64, 64, 0, st>>>(flat.p, total, leader.p);
-        k_group_rank<DpGroup><<<(total + 63) / 64, 64, 0, st>>>(flat.p, total, leader.p, rank.p, d_cnt);
-        launches += 2;
-    }
-    std::vector<int> hl(total), hr(total);
-    std::vector<DpGroup> hg(total);
-    if (total) {
-        SGS_CUDA_TRY(cudaMemcpyAsync(hl.data(), leader.p, total * sizeof(int), cudaMemcpyDeviceToHost, st));
-        SGS_CUDA_TRY(cudaMemcpyAsync(hr.data(), rank.p, total * sizeof(int), cudaMemcpyDeviceToHost, st));
-        SGS_CUDA_TRY(cudaMemcpyAsync(hg.data(), flat.p, total * sizeof(DpGroup), cudaMemcpyDeviceToHost, st));
-    }
+    int info[8];
+    SGS_CUDA_TRY(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
-    int nuniq = 0;
-    for (int c = 0; c < total; c++) if (hl[c] == c) nuniq++;
-    out.groups.assign(nuniq, DpGroup());
-    std::vector<std::vector<int>> parents(nuniq);
-    for (int c = 0; c < total; c++) {
-        const int g = hr[hl[c]];
-        if (hl[c] == c) out.groups[g] = hg[c];
-        parents[g].push_back(par[c]);
+    if (info[6]) return ctl_error(info[6], "right environments");
+    out.count = info[0]; out.nlinks = info[1]; out.maxfan = info[2];
+    SGS_CUDA_TRY(pool.take((void **)&out.d_groups, sizeof(DpGroup) * std::max(out.count, 1)));
+    SGS_CUDA_TRY(pool.take((void **)&out.d_map_off, sizeof(int) * (out.count + 1)));
+    SGS_CUDA_TRY(pool.take((void **)&out.d_map_idx, sizeof(int) * std::max(out.nlinks, 1)));
+    SGS_CUDA_TRY(cudaMemcpyAsync(out.d_groups, srgroups.p, sizeof(DpGroup) * out.count, cudaMemcpyDeviceToDevice, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(out.d_map_off, srmapoff.p, sizeof(int) * (out.count + 1), cudaMemcpyDeviceToDevice, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(out.d_map_idx, srmapidx.p, sizeof(int) * out.nlinks, cudaMemcpyDeviceToDevice, st));
+    if (keep_host_levels) {
+        out.groups.resize(out.count);
+        SGS_CUDA_TRY(cudaMemcpyAsync(out.groups.data(), srgroups.p, sizeof(DpGroup) * out.count, cudaMemcpyDeviceToHost, st));
+        SGS_CUDA_TRY(cudaStreamSynchronize(st));
     }
-    out.map_off.assign(nuniq + 1, 0);
-    out.map_idx.clear();
-    for (int g = 0; g < nuniq; g++) {        // duplicates removed, ascending (py/state.py:523 uses a set)
-        auto &v = parents[g];
-        std::sort(v.begin(), v.end());
-        v.erase(std::unique(v.begin(), v.end()), v.end());
-        out.map_idx.insert(out.map_idx.end(), v.begin(), v.end());
-        out.map_off[g + 1] = (int)out.map_idx.size();
-    }
-    return upload_level(out);
+    return Status();
 }
+
+static Status make_top_level(KlocalMachine::Impl &K, Level &top);
 
 Status KlocalMachine::Impl::gen_sright_all()
 {
     Level top;
-    DpGroup empty{};
-    top.groups.push_back(empty);                 // Stab::empty(H.k, H.n - H.k + 1), cpp/state.cpp:219
-    top.map_off = {0, 0};
-    lv[n] = top;
-    Status s = upload_level(lv[n]);
+    Status s = make_top_level(*this, top);     // Stab::empty(H.k, H.n - H.k + 1), cpp/state.cpp:219
     if (!s.ok()) return s;
+    lv[n] = top;
     for (int m = n - 1; m >= 0; m--) {
         Level L;
         s = gen_level(m, lv[m + 1], L);
         if (!s.ok()) return s;
         lv[m] = L;
-        L.d_groups = nullptr; L.d_map_off = L.d_map_idx = nullptr;     // ownership moved into the map
     }
     return Status();
 }
 
-Status KlocalMachine::Impl::set_states(const std::vector<HostState> &hs, int m)
+static Status make_top_level(KlocalMachine::Impl &K, Level &top)
 {
-    nstates_ = (int)hs.size();
+    DpGroup empty{};
+    const int zero2[2] = {0, 0};
+    top.count = 1; top.nlinks = 0; top.maxfan = 0;
+    SGS_CUDA_TRY(K.pool.take((void **)&top.d_groups, sizeof(DpGroup)));
+    SGS_CUDA_TRY(K.pool.take((void **)&top.d_map_off, sizeof(int) * 2));
+    SGS_CUDA_TRY(K.pool.take((void **)&top.d_map_idx, sizeof(int)));
+    SGS_CUDA_TRY(cudaMemcpy(top.d_groups, &empty, sizeof(DpGroup), cudaMemcpyHostToDevice));
+    SGS_CUDA_TRY(cudaMemcpy(top.d_map_off, zero2, sizeof(zero2), cudaMemcpyHostToDevice));
+    top.groups.assign(1, empty);
+    return Status();
+}
+
+Status KlocalMachine::Impl::write_ctl(int nin, bool reset_history)
+{
+    Status s = sync_ctl();
+    if (!s.ok()) return s;
+    DpCtl c = hctl;
+    c.nin = nin; c.total = 0; c.nuniq = 0; c.err = 0;
+    if (reset_history) { c.hm_off = 0; c.hb_off = 0; c.step = 0; hist_floor = 0; }
+    c.caps = caps; c.capc = capc; c.hm_cap = hm_cap; c.hb_cap = hb_cap; c.log_cap = log_cap;
+    hctl = c;
+    SGS_CUDA_TRY(cudaMemcpyAsync(d_ctl, &hctl, sizeof(DpCtl), cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    hctl_valid = true;
+    return Status();
+}
+
+// the one host synchronisation point of the DP: closes the timed segment and refreshes the control block
+Status KlocalMachine::Impl::sync_ctl()
+{
+    if (hctl_valid && !seg_open) return Status();
+    if (seg_open) SGS_CUDA_TRY(cudaEventRecord(e1, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(&hctl, d_ctl, sizeof(DpCtl), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    if (seg_open) {
+        float ms = 0.f;
+        SGS_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        dev_seconds += ms * 1e-3;
+        seg_open = false;
+    }
+    hctl_valid = true;
+    if (hctl.err) return ctl_error(hctl.err, "k-local DP");
+    return Status();
+}
+
+Status KlocalMachine::Impl::set_states(const std::vector<HostState> &hs, int m, bool reset_history)
+{
+    if ((int)hs.size() > caps) return Status::fail(SGS_ERR_OVERFLOW, "k-local DP: more states than the batch capacity");
     m_ = m;
     const size_t ns = std::max<size_t>(hs.size(), 1);
-    SGS_CUDA_TRY(states.need(ns));
-    SGS_CUDA_TRY(tabE.need(ns * tstride));
-    SGS_CUDA_TRY(tabB.need(ns * tstride));
     std::vector<DpState> ss(ns);
     std::vector<double> ee(ns * tstride, 0.0);
     for (size_t i = 0; i < hs.size(); i++) {
         ss[i] = hs[i].s;
         for (size_t e = 0; e < hs[i].E.size() && e < (size_t)tstride; e++) ee[i * tstride + e] = hs[i].E[e];
     }
-    SGS_CUDA_TRY(cudaMemcpyAsync(states.p, ss.data(), ns * sizeof(DpState), cudaMemcpyHostToDevice, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(tabE.p, ee.data(), ns * tstride * sizeof(double), cudaMemcpyHostToDevice, st));
+    Status s = write_ctl((int)hs.size(), reset_history);
+    if (!s.ok()) return s;
+    SGS_CUDA_TRY(cudaMemcpyAsync(cur_states(), ss.data(), ns * sizeof(DpState), cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(cur_E(), ee.data(), ns * tstride * sizeof(double), cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
     return Status();
 }
 
 Status KlocalMachine::Impl::get_states(std::vector<HostState> &hs)
 {
-    hs.assign(nstates_, HostState());
-    if (!nstates_) return Status();
-    std::vector<DpState> ss(nstates_);
-    std::vector<double> ee((size_t)nstates_ * tstride);
-    SGS_CUDA_TRY(cudaMemcpyAsync(ss.data(), states.p, nstates_ * sizeof(DpState), cudaMemcpyDeviceToHost, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(ee.data(), tabE.p, ee.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    Status s = sync_ctl();
+    if (!s.ok()) return s;
+    const int ns = hctl.nin;
+    hs.assign(ns, HostState());
+    if (!ns) return Status();
+    std::vector<DpState> ss(ns);
+    std::vector<double> ee((size_t)ns * tstride);
+    SGS_CUDA_TRY(cudaMemcpyAsync(ss.data(), cur_states(), ns * sizeof(DpState), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(ee.data(), cur_E(), ee.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
-    for (int i = 0; i < nstates_; i++) {
+    for (int i = 0; i < ns; i++) {
         hs[i].s = ss[i];
         hs[i].E.assign(ee.begin() + (size_t)i * tstride, ee.begin() + (size_t)i * tstride + ((size_t)1 << ss[i].r));
     }
@@ -319,7 +399,7 @@ Status KlocalMachine::Impl::get_states(std::vector<HostState> &hs)
 // StateMachine ctor (cpp/state.cpp:445-458): one state per right environment at site 0
 Status KlocalMachine::Impl::init_states()
 {
-    std::vector<HostState> hs(lv[0].groups.size());
+    std::vector<HostState> hs(lv[0].count);
     for (size_t i = 0; i < hs.size(); i++) {
         memset(&hs[i].s, 0, sizeof(DpState));
         for (int w = 0; w < kDpVW; w++) hs[i].s.valid[w] = ~0ULL;
@@ -327,103 +407,65 @@ Status KlocalMachine::Impl::init_states()
         hs[i].s.sright = (int)i;
         hs[i].E = {0.0};
     }
-    steps.clear();
-    hist_floor = 0;
-    return set_states(hs, 0);
+    cur_is_A = true;
+    return set_states(hs, 0, true);
 }
 
-// StateMachine::evolve (cpp/state.cpp:483-533): every state of site m → merged states of site m+1
+// StateMachine::evolve (cpp/state.cpp:483-533): every state of site m → merged states of site m+1.
+// Enqueue only: batch sizes live in the device control block, nothing is read back here.
 Status KlocalMachine::Impl::evolve()
 {
     if (lv.find(m_) == lv.end() || lv.find(m_ + 1) == lv.end()) return Status::fail(SGS_ERR_ARG, "no right-environment level for this site");
+    if (!pending.ok()) return pending;
     const Level &L = lv[m_], &Ln = lv[m_ + 1];
-    const int nin = nstates_;
-    Step step;
-    if (nin == 0) { steps.push_back(step); m_++; return Status(); }
-    const int maxfan = std::max(L.maxfan, 1);
-    SGS_CUDA_TRY(moved.need(nin));
-    SGS_CUDA_TRY(slabE.need((size_t)nin * 2 * slab_stride));
-    SGS_CUDA_TRY(slabB.need((size_t)nin * 2 * slab_stride));
-    SGS_CUDA_TRY(accept.need((size_t)nin * maxfan));
-    SGS_CUDA_TRY(nacc.need(nin + 1));
-    SGS_CUDA_TRY(off.need(nin + 1));
-    SGS_CUDA_TRY(cudaEventRecord(e0, st));
-    const int tb = 64, gb = (nin + tb - 1) / tb;
-    k_dp_move<<<gb, tb, 0, st>>>(terms, m_, states.p, tabE.p, nin, tstride, L.d_groups, moved.p, slabE.p, slabB.p, slab_stride, d_err);
-    k_dp_fanout<<<gb, tb, 0, st>>>(terms, m_, moved.p, nin, L.d_map_off, L.d_map_idx, Ln.d_groups, maxfan, accept.p, nacc.p);
-    k_dp_scan<<<1, 1, 0, st>>>(nacc.p, nin, off.p, d_cnt);
-    launches += 3;
+    if (!seg_open) { SGS_CUDA_TRY(cudaEventRecord(e0, st)); seg_open = true; }
+    hctl_valid = false;
+    const int tb = 64, gs = std::min((caps + tb - 1) / tb, 256), gc = std::min((capc + tb - 1) / tb, 512);
+    k_dp_move<<<gs, tb, 0, st>>>(terms, m_, cur_states(), cur_E(), d_ctl, tstride, L.d_groups, moved.p, slabE.p, slabB.p, slab_stride, hm.p);
+    k_dp_fanout<<<gs, tb, 0, st>>>(terms, m_, moved.p, d_ctl, L.d_map_off, L.d_map_idx, Ln.d_groups, nacc.p);
+    k_dp_scan<<<1, 1024, 0, st>>>(nacc.p, d_ctl, off.p);
+    k_dp_emit<<<gs, tb, 0, st>>>(terms, m_, moved.p, d_ctl, L.d_map_off, L.d_map_idx, Ln.d_groups, off.p, keys.p, parent.p);
+    k_group_leader<DpKey><<<gc, tb, 0, st>>>(keys.p, &d_ctl->total, leader.p);
+    k_group_rank<DpKey><<<gc, tb, 0, st>>>(keys.p, &d_ctl->total, leader.p, rank.p, &d_ctl->nuniq);
+    k_dp_merge<<<1024, 64, 0, st>>>(keys.p, parent.p, leader.p, rank.p, d_ctl, slabE.p, slabB.p, slab_stride, tstride, nxt_states(), nxt_E(),
+                                    hb.p, moved.p);
+    k_dp_advance<<<1, 1, 0, st>>>(d_ctl, d_log, m_, tstride);
+    launches += 8;
     SGS_CUDA_TRY(cudaGetLastError());
-    int total = 0;
-    SGS_CUDA_TRY(cudaMemcpyAsync(&total, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
-    Status s = check_err("k-local DP step");
-    if (!s.ok()) return s;
-    transitions += (uint64_t)nin;
-    // history of this step: what each parent added
-    std::vector<DpMoved> hm(nin);
-    SGS_CUDA_TRY(cudaMemcpyAsync(hm.data(), moved.p, nin * sizeof(DpMoved), cudaMemcpyDeviceToHost, st));
-    int nuniq = 0;
-    if (total > 0) {
-        SGS_CUDA_TRY(keys.need(total));
-        SGS_CUDA_TRY(parent.need(total));
-        SGS_CUDA_TRY(leader.need(total));
-        SGS_CUDA_TRY(rank.need(total));
-        SGS_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 16, st));
-        k_dp_emit<<<gb, tb, 0, st>>>(terms, m_, moved.p, nin, L.d_map_off, L.d_map_idx, maxfan, accept.p, off.p, keys.p, parent.p);
-        k_group_leader<DpKey><<<(total + 63) / 64, 64, 0, st>>>(keys.p, total, leader.p);
-        k_group_rank<DpKey><<<(total + 63) / 64, 64, 0, st>>>(keys.p, total, leader.p, rank.p, d_cnt);
-        launches += 3;
-        SGS_CUDA_TRY(cudaMemcpyAsync(&nuniq, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
-        SGS_CUDA_TRY(cudaStreamSynchronize(st));
-        SGS_CUDA_TRY(nstates_buf.need(nuniq));
-        SGS_CUDA_TRY(ntabE.need((size_t)nuniq * tstride));
-        SGS_CUDA_TRY(ntabB.need((size_t)nuniq * tstride));
-        k_dp_merge<<<total, 64, 0, st>>>(keys.p, parent.p, leader.p, rank.p, total, slabE.p, slabB.p, slab_stride, tstride,
-                                         nstates_buf.p, ntabE.p, ntabB.p, moved.p);
-        launches++;
-        SGS_CUDA_TRY(cudaGetLastError());
-        step.back.resize((size_t)nuniq * tstride);
-        SGS_CUDA_TRY(cudaMemcpyAsync(step.back.data(), ntabB.p, step.back.size() * sizeof(DpBack), cudaMemcpyDeviceToHost, st));
-    }
-    SGS_CUDA_TRY(cudaEventRecord(e1, st));
-    SGS_CUDA_TRY(cudaStreamSynchronize(st));
-    float ms = 0.f;
-    SGS_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    dev_seconds += ms * 1e-3;
-    step.nadd.resize(nin);
-    step.added.resize((size_t)nin * kDpMaxAdd);
-    for (int i = 0; i < nin; i++) {
-        step.nadd[i] = hm[i].dead ? 0 : hm[i].nadd;
-        for (int a = 0; a < kDpMaxAdd; a++) step.added[(size_t)i * kDpMaxAdd + a] = hm[i].added[a];
-    }
-    steps.push_back(std::move(step));
-    std::swap(states.p, nstates_buf.p); std::swap(states.cap, nstates_buf.cap);
-    std::swap(tabE.p, ntabE.p); std::swap(tabE.cap, ntabE.cap);
-    std::swap(tabB.p, ntabB.p); std::swap(tabB.cap, ntabB.cap);
-    nstates_ = nuniq;
+    cur_is_A = !cur_is_A;
     m_++;
     return Status();
 }
 
-// history of (state, entry) of the current site back to the last cleared point: (file index, sign) pairs in
-// the order the reference appends them (Ps_indices / Ps_signs, cpp/stab.cpp:752-759)
-std::vector<std::pair<int, int>> KlocalMachine::Impl::traceback(int state, int entry) const
+Status KlocalMachine::Impl::fetch_log(std::vector<DpStepLog> &log)
 {
-    std::vector<std::vector<std::pair<int, int>>> chunks;
-    int s = state, e = entry;
-    for (int t = (int)steps.size() - 1; t >= hist_floor; t--) {
-        const Step &S = steps[t];
-        const DpBack &b = S.back[(size_t)s * tstride + e];
-        if (b.state < 0) break;
-        std::vector<std::pair<int, int>> ch;
-        for (int a = 0; a < S.nadd[b.state]; a++)
-            ch.push_back({H.order[S.added[(size_t)b.state * kDpMaxAdd + a]], ((b.signs >> a) & 1) ? -1 : 1});
-        chunks.push_back(ch);
-        s = b.state; e = b.entry;
+    Status s = sync_ctl();
+    if (!s.ok()) return s;
+    log.resize(std::min(hctl.step, log_cap));
+    if (!log.empty()) SGS_CUDA_TRY(cudaMemcpy(log.data(), d_log, sizeof(DpStepLog) * log.size(), cudaMemcpyDeviceToHost));
+    return Status();
+}
+
+// history of (state, entry) of the current site back to the last cleared point, walked on the device
+Status KlocalMachine::Impl::traceback(int state, int entry, std::vector<std::pair<int, int>> &out)
+{
+    Status s = sync_ctl();
+    if (!s.ok()) return s;
+    const int cap = (int)(trace.cap / 2) - 8;
+    int *d_pos = trace.p, *d_sign = trace.p + cap, *d_n = trace.p + 2 * cap;
+    k_dp_trace<<<1, 1, 0, st>>>(d_ctl, d_log, hm.p, hb.p, tstride, hist_floor, state, entry, d_pos, d_sign, d_n, cap);
+    launches++;
+    int nn = 0;
+    SGS_CUDA_TRY(cudaMemcpyAsync(&nn, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<int> pos(std::max(nn, 1)), sg(std::max(nn, 1));
+    if (nn) {
+        SGS_CUDA_TRY(cudaMemcpy(pos.data(), d_pos, sizeof(int) * nn, cudaMemcpyDeviceToHost));
+        SGS_CUDA_TRY(cudaMemcpy(sg.data(), d_sign, sizeof(int) * nn, cudaMemcpyDeviceToHost));
     }
-    std::vector<std::pair<int, int>> out;
-    for (int i = (int)chunks.size() - 1; i >= 0; i--) out.insert(out.end(), chunks[i].begin(), chunks[i].end());
-    return out;
+    out.clear();
+    for (int i = 0; i < nn; i++) out.push_back({H.order[pos[i]], sg[i]});
+    return Status();
 }
 
 // StateMachine::generate_gs + State::get_stab_gs (cpp/state.cpp:421-442,535-550)
@@ -441,7 +483,14 @@ Status KlocalMachine::Impl::ground_state(sgs_result *out)
         for (size_t e = 1; e < hs[i].E.size(); e++) if (hs[i].E[e] < hs[i].E[arg]) arg = (int)e;
         if (bs < 0 || hs[i].E[arg] < bestE) { bestE = hs[i].E[arg]; bs = (int)i; be = arg; }
     }
-    auto hist = traceback(bs, be);
+    std::vector<DpStepLog> lg;
+    s = fetch_log(lg);
+    if (!s.ok()) return s;
+    uint64_t transitions = 0;                   // evolve_single calls = states entering each site step
+    for (const DpStepLog &e : lg) transitions += (uint64_t)e.nin;
+    std::vector<std::pair<int, int>> hist;
+    s = traceback(bs, be, hist);
+    if (!s.ok()) return s;
     const int Wout = (2 * n + 63) / 64;
     const int mg = (int)hist.size();
     std::vector<uint64_t> rows((size_t)std::max(mg, 1) * Wout, 0);
@@ -466,8 +515,8 @@ Status KlocalMachine::Impl::ground_state(sgs_result *out)
     memcpy(out->gens, rows.data(), (size_t)rankc * Wout * 8);
     memcpy(out->gen_signs, signs.data(), rankc);
     memcpy(out->term_signs, ts.data(), T);
-    out->transitions = transitions;
     out->kernel_launches = launches + 2;
+    out->transitions = transitions;
     out->seconds_device = dev_seconds;
     return Status();
 }
@@ -482,11 +531,17 @@ Status KlocalMachine::create(const Hamiltonian &H, const sgs_opts &opts, int per
     std::unique_ptr<KlocalMachine> M(new KlocalMachine());
     M->impl_->H = H;
     M->impl_->opts = opts;
-    Status s = M->impl_->init(periodic_cmax);
+    M->impl_->keep_host_levels = periodic_cmax >= 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    Status s = M->impl_->init();
     if (!s.ok()) return s;
     if (periodic_cmax < 0) {
+        const auto t1 = std::chrono::steady_clock::now();
         s = M->impl_->gen_sright_all();
         if (!s.ok()) return s;
+        if (getenv("SGS_DP_TRACE"))
+            fprintf(stderr, "klocal create: init %.3f ms, right environments %.3f ms\n", std::chrono::duration<double>(t1 - t0).count() * 1e3,
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count() * 1e3);
         s = M->impl_->init_states();
         if (!s.ok()) return s;
     }
@@ -495,11 +550,16 @@ Status KlocalMachine::create(const Hamiltonian &H, const sgs_opts &opts, int per
 }
 
 int KlocalMachine::m() const { return impl_->m_; }
-int KlocalMachine::nstates() const { return impl_->nstates_; }
+int KlocalMachine::nstates() const
+{
+    Status s = impl_->sync_ctl();          // reads the device control block (one stream sync)
+    if (!s.ok()) { impl_->pending = s; return -1; }
+    return impl_->hctl.nin;
+}
 int KlocalMachine::sright_count(int m) const
 {
     auto it = impl_->lv.find(m);
-    return it == impl_->lv.end() ? 0 : (int)it->second.groups.size();
+    return it == impl_->lv.end() ? 0 : it->second.count;
 }
 Status KlocalMachine::evolve() { return impl_->evolve(); }
 Status KlocalMachine::ground_state(sgs_result *out) { return impl_->ground_state(out); }
@@ -513,12 +573,23 @@ Status klocal_search(const Hamiltonian &H, const sgs_opts &opts, sgs_result *out
     const auto t1 = std::chrono::steady_clock::now();
     std::vector<int> sr(H.n + 1), sp(H.n + 1);
     for (int m = 0; m <= H.n; m++) sr[m] = M->sright_count(m);
-    sp[0] = M->nstates();
-    while (M->m() < H.n) {
-        s = M->evolve();
+    KlocalMachine::Impl &K = *M->impl();
+    std::vector<DpStepLog> dlog;
+    for (int scale = 1;; scale *= 4) {
+        sp[0] = M->nstates();
+        while (M->m() < H.n) {             // n sites enqueued back to back, no host round trip in between
+            s = M->evolve();
+            if (!s.ok()) return s;
+        }
+        s = K.fetch_log(dlog);
+        if (s.ok()) break;
+        if (s.code != SGS_ERR_OVERFLOW || scale >= 4096) return s;
+        s = K.ensure_caps(scale * 4);      // a batch outgrew its buffers: grow and redo the DP
         if (!s.ok()) return s;
-        sp[M->m()] = M->nstates();
+        s = K.init_states();
+        if (!s.ok()) return s;
     }
+    for (const DpStepLog &e : dlog) if (e.m + 1 <= H.n) sp[e.m + 1] = e.nuniq;
     const auto t2 = std::chrono::steady_clock::now();
     s = M->ground_state(out);
     if (!s.ok()) return s;
@@ -558,10 +629,7 @@ Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &op
     // ---- generate_Sright_periodic ----
     const int end = l * (1 + cmax) + k;
     Level cur;
-    DpGroup empty{};
-    cur.groups.push_back(empty);
-    cur.map_off = {0, 0};
-    s = K.upload_level(cur);
+    s = make_top_level(K, cur);
     if (!s.ok()) return s;
     std::vector<DpGroup> id;
     bool have_id = false;
@@ -570,9 +638,8 @@ Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &op
             Level nx;
             s = K.gen_level(m, cur, nx);
             if (!s.ok()) return s;
-            cur.free_dev();
             cur = nx;
-            log.push_back(m); log.push_back((int)cur.groups.size());
+            log.push_back(m); log.push_back(cur.count);
         }
         bool same = have_id && id.size() == cur.groups.size();
         for (size_t i = 0; same && i < id.size(); i++) same = group_equal(id[i], cur.groups[i]);
@@ -582,14 +649,12 @@ Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &op
         if (same) break;
     }
     K.lv[end] = cur;
-    cur.d_groups = nullptr; cur.d_map_off = cur.d_map_idx = nullptr;
     for (int m = end - 1; m >= 0; m--) {
         Level L;
         s = K.gen_level(m, K.lv[m + 1], L);
         if (!s.ok()) return s;
         K.lv[m] = L;
-        L.d_groups = nullptr; L.d_map_off = L.d_map_idx = nullptr;
-        log.push_back(m); log.push_back((int)K.lv[m].groups.size());
+        log.push_back(m); log.push_back(L.count);
     }
 
     // State.shift(add): relabel the level; the right environment is looked up by content
@@ -635,10 +700,8 @@ Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &op
     auto periodic_evolve = [&](std::vector<HostState> hs, bool clear_history, int cc, std::vector<HostState> &res) -> Status {
         dedupe_sort(hs);
         const int m0 = k + l - 1;
-        Status st = K.set_states(hs, m0);
+        Status st = K.set_states(hs, m0, true);
         if (!st.ok()) return st;
-        K.steps.clear();
-        K.hist_floor = 0;
         for (int i = 0; i < l * cc; i++) { st = K.evolve(); if (!st.ok()) return st; }
         st = K.get_states(res);
         if (!st.ok()) return st;
@@ -697,7 +760,8 @@ Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &op
                 // `all` is in the device order of the final states (get_states keeps it), so i indexes K's history
                 Orb ob;
                 ob.energy = all[i].E[index];
-                ob.gens = K.traceback((int)i, (int)index);
+                s = K.traceback((int)i, (int)index, ob.gens);
+                if (!s.ok()) return s;
                 ob.begin = n; ob.end = 0;
                 for (auto &g : ob.gens) { ob.begin = std::min(ob.begin, H.begin[g.first]); ob.end = std::max(ob.end, H.end[g.first]); }
                 if (ob.gens.empty()) { ob.begin = 0; ob.end = 0; }

@@ -17,6 +17,7 @@
 #include "hamiltonian.hpp"
 #include "nccl_glue.hpp"
 #include "sparse_kernels.cuh"
+#include "arena.hpp"
 #include "sparse_search.hpp"
 
 namespace sgs {
@@ -54,34 +55,6 @@ struct DevCtx {
     Status status;
 };
 
-// Process-wide cache of one scratch arena per device: repeated one-shot searches (sgs_sparse_search)
-// reuse the device allocation instead of paying cudaMalloc/cudaFree of the work queues every call.
-struct ArenaCache {
-    struct Slot { void *p; size_t bytes; bool busy; };
-    std::mutex mu;
-    std::map<int, std::vector<Slot>> slots;
-    cudaError_t acquire(int dev, size_t bytes, void **out)
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        auto &v = slots[dev];
-        for (auto &s : v)
-            if (!s.busy && s.bytes >= bytes) { s.busy = true; *out = s.p; return cudaSuccess; }
-        for (size_t i = 0; i < v.size();)          // drop idle arenas that are too small
-            if (!v[i].busy) { cudaFree(v[i].p); v.erase(v.begin() + i); } else i++;
-        void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) return e;
-        v.push_back({p, bytes, true});
-        *out = p;
-        return cudaSuccess;
-    }
-    void release(int dev, void *p)
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        for (auto &s : slots[dev]) if (s.p == p) s.busy = false;
-    }
-};
-ArenaCache g_arena;
 
 }  // namespace
 
@@ -122,7 +95,7 @@ SparsePlan::Impl::~Impl()
     nccl.reset();
     for (auto &c : devs) {
         cudaSetDevice(c.device);
-        if (c.arena) g_arena.release(c.device, c.arena);
+        if (c.arena) sparse_arena().release(c.device, c.arena);
         if (c.ev0) cudaEventDestroy(c.ev0);
         if (c.ev1) cudaEventDestroy(c.ev1);
         if (c.evh0) cudaEventDestroy(c.evh0);
@@ -240,7 +213,7 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
     want(&c.memCount, 1);
     size_t total = 0;
     for (auto &cv : carve) total += cv.bytes;
-    SGS_CUDA_TRY(g_arena.acquire(c.device, total, &c.arena));
+    SGS_CUDA_TRY(sparse_arena().acquire(c.device, total, &c.arena));
     {
         size_t off = 0;
         for (auto &cv : carve) { *cv.pp = (char *)c.arena + off; off += cv.bytes; }
