@@ -15,6 +15,8 @@
 // The reference's keyed merge (std::map on a boost hash + omp critical, cpp/state.cpp:494-517) becomes a
 // deterministic group-by-full-key with "later in (parent, child) order wins exact ties" = its strict '<'.
 #pragma once
+#include <cooperative_groups.h>
+
 #include <cstdint>
 
 #include "packed.cuh"
@@ -194,19 +196,30 @@ SGS_D void group_project_site0(uint64_t *g, int &r, double *E, DpBack *bk)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Device-resident control block of the DP: the host enqueues every site step back to back without
-// reading anything; the kernels take the batch sizes from here (grid-stride loops under fixed grids).
+// Device-resident control block of the DP.  The whole DP (all sites) is ONE persistent cooperative kernel:
+// batch sizes, history offsets and errors live here, the host reads it once at the end.
 struct DpCtl {
-    int nin;                 // states entering the current step
-    int total;               // children emitted by the current step
-    int nuniq;               // merged states = nin of the next step
+    int nin;                 // states entering the next step
+    int total;               // children emitted by the step in flight
+    int nuniq;               // merged states of the step in flight
     int err;                 // 0 ok, 1 rank/table limit, 2 valid-set width, 5 state capacity, 6 child capacity, 7 history capacity
+    int err_snap;            // err as published by block 0 between two grid barriers (uniform early exit)
     int hm_off, hb_off;      // bump offsets into the history pools
     int step;                // steps logged so far
+    int cur;                 // which of the two state buffers holds the current states
+    unsigned gen;            // generation of the dedup table (monotone over the machine's life)
     int caps, capc, hm_cap, hb_cap, log_cap;
+    unsigned long long prof[8];   // ns spent per phase (thread 0's view), for SGS_DP_TRACE
 };
 struct DpStepLog { int m, nin, total, nuniq, hm_off, hb_off; };
 struct DpHistAdd { int nadd; uint16_t added[kDpMaxAdd]; };      // what one parent state added at one site
+
+struct DpLevelDev {          // type_Sright (cpp/state.hpp:49-51) of one site: groups + compatible next groups
+    const DpGroup *groups;
+    const int *map_off;      // [count + 1]
+    const int *map_idx;      // [nlinks] indices into the level of site m+1
+    int count, nlinks;
+};
 
 struct DpMoved {
     uint64_t g[kDpRows];
@@ -271,21 +284,6 @@ SGS_D void dp_move_one(const DpTerms &H, int m, int s, const DpState &st, const 
     for (int i = 0; i < kDpVW; i++) mv.valid[i] = valid[i];
 }
 
-// k_dp_move: one thread per state (grid-stride over ctl->nin)
-__global__ void k_dp_move(DpTerms H, int m, const DpState *__restrict__ in, const double *__restrict__ inE, DpCtl *ctl,
-                          int tstride, const DpGroup *__restrict__ level, DpMoved *__restrict__ out, double *slabE,
-                          DpBack *slabB, int slab_stride, DpHistAdd *hm)
-{
-    const int nin = ctl->nin;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nin; s += gridDim.x * blockDim.x) {
-        double *E = slabE + (size_t)s * 2 * slab_stride;
-        DpBack *B = slabB + (size_t)s * 2 * slab_stride;
-        DpHistAdd *h = nullptr;
-        if (ctl->hm_off + s < ctl->hm_cap) h = hm + ctl->hm_off + s; else atomicMax(&ctl->err, 7);
-        dp_move_one(H, m, s, in[s], inE, tstride, level, out[s], E, E + slab_stride, B, B + slab_stride, h, &ctl->err);
-    }
-}
-
 // span of the valid terms with last site in [m+1, min(m+k+1, n)) truncated to [max(m-k+2,0), m+2):
 // State::check_Sright_validity (cpp/state.cpp:347-365)
 SGS_D void dp_valid_span(const DpTerms &H, int m, const DpMoved &mv, Ech &e)
@@ -305,77 +303,6 @@ SGS_D bool dp_accepts(const Ech &e, const DpGroup &G)
     return true;
 }
 
-// k_dp_fanout: evolve_single's loop over compatible next right environments (cpp/state.cpp:467-479):
-// nacc[s] = number of accepted candidates of state s
-__global__ void k_dp_fanout(DpTerms H, int m, const DpMoved *__restrict__ mv, const DpCtl *ctl, const int *__restrict__ map_off,
-                            const int *__restrict__ map_idx, const DpGroup *__restrict__ next_level, int *__restrict__ nacc)
-{
-    const int nin = ctl->nin;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nin; s += gridDim.x * blockDim.x) {
-        int cnt = 0;
-        if (!mv[s].dead) {
-            Ech e;
-            dp_valid_span(H, m, mv[s], e);
-            const int sr = mv[s].sright;
-            for (int j = map_off[sr]; j < map_off[sr + 1]; j++) cnt += dp_accepts(e, next_level[map_idx[j]]);
-        }
-        nacc[s] = cnt;
-    }
-}
-
-// exclusive scan of nacc → child offsets; one block
-__global__ void k_dp_scan(const int *__restrict__ nacc, DpCtl *ctl, int *__restrict__ off)
-{
-    __shared__ int part[1024];
-    const int nin = ctl->nin, tid = threadIdx.x, nt = blockDim.x;
-    const int per = (nin + nt - 1) / nt, lo = min(tid * per, nin), hi = min(lo + per, nin);
-    int acc = 0;
-    for (int i = lo; i < hi; i++) acc += nacc[i];
-    part[tid] = acc;
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int i = 0; i < nt; i++) { const int v = part[i]; part[i] = run; run += v; }
-        ctl->total = run;
-        if (run > ctl->capc) { ctl->err = max(ctl->err, 6); ctl->total = 0; }
-        off[nin] = run;
-    }
-    __syncthreads();
-    acc = part[tid];
-    for (int i = lo; i < hi; i++) { off[i] = acc; acc += nacc[i]; }
-}
-
-// children in deterministic (parent, map order): key + reference to the moved state
-__global__ void k_dp_emit(DpTerms H, int m, const DpMoved *__restrict__ mv, const DpCtl *ctl, const int *__restrict__ map_off,
-                          const int *__restrict__ map_idx, const DpGroup *__restrict__ next_level, const int *__restrict__ off,
-                          DpKey *__restrict__ keys, int *__restrict__ parent)
-{
-    const int nin = ctl->nin;
-    if (ctl->total == 0) return;
-    const int k = H.k, m1 = m + 1;
-    // key: valid bits for last site in [m1+1, min(m1+k-1, n)), positions relative to boff[m1]
-    const int lo = H.boff[min(m1 + 1, H.n + 1)] - H.boff[m1];
-    const int hi = H.boff[min(max(m1 + k - 1, m1 + 1), H.n)] - H.boff[m1];
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nin; s += gridDim.x * blockDim.x) {
-        if (mv[s].dead) continue;
-        Ech e;
-        dp_valid_span(H, m, mv[s], e);
-        int c = off[s];
-        const int sr = mv[s].sright;
-        for (int j = map_off[sr]; j < map_off[sr + 1]; j++) {
-            if (!dp_accepts(e, next_level[map_idx[j]])) continue;
-            DpKey &K = keys[c];
-            for (int i = 0; i < kDpRows; i++) K.g[i] = mv[s].g[i];
-            for (int i = 0; i < kDpVW; i++) K.v[i] = 0;
-            for (int b = lo; b < hi; b++) if (vget(mv[s].valid, b)) K.v[b >> 6] |= 1ULL << (b & 63);
-            K.r = mv[s].r;
-            K.sright = map_idx[j];
-            parent[c] = s;
-            c++;
-        }
-    }
-}
-
 SGS_D int key_cmp(const DpKey &a, const DpKey &b)
 {
     if (a.r != b.r) return a.r < b.r ? -1 : 1;
@@ -392,118 +319,6 @@ SGS_D int key_cmp(const DpGroup &a, const DpGroup &b)
     for (int i = 0; i < kDpRows; i++) if (a.neg[i] != b.neg[i]) return a.neg[i] < b.neg[i] ? -1 : 1;
     return 0;
 }
-
-// leader[c] = first entry with the same key (the lists are a few hundred to a few thousand entries:
-// all-pairs compare); the list length is read from the device
-template <typename K>
-__global__ void k_group_leader(const K *__restrict__ keys, const int *nc_dev, int *__restrict__ leader)
-{
-    const int nc = *nc_dev;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
-        int lead = c;
-        for (int j = 0; j < c; j++) if (key_cmp(keys[j], keys[c]) == 0) { lead = j; break; }
-        leader[c] = lead;
-    }
-}
-
-// rank[c] (leaders only, else -1) = number of distinct smaller keys: the deterministic total order that
-// replaces the reference's std::map-on-a-boost-hash iteration order
-template <typename K>
-__global__ void k_group_rank(const K *__restrict__ keys, const int *nc_dev, const int *__restrict__ leader, int *__restrict__ rank, int *nuniq)
-{
-    const int nc = *nc_dev;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
-        if (leader[c] != c) { rank[c] = -1; continue; }
-        int rk = 0;
-        for (int j = 0; j < nc; j++) if (leader[j] == j && key_cmp(keys[j], keys[c]) < 0) rk++;
-        rank[c] = rk;
-        atomicAdd(nuniq, 1);
-    }
-}
-
-// merged states of site m+1, in key order: element-wise minimum over the children of a key, exact ties
-// won by the later child (merge_gs keeps the newcomer unless the incumbent is strictly lower,
-// cpp/stab.cpp:832).  One block per leader (grid-stride), one thread per table entry.
-__global__ void k_dp_merge(const DpKey *__restrict__ keys, const int *__restrict__ parent, const int *__restrict__ leader,
-                           const int *__restrict__ rank, DpCtl *ctl, const double *__restrict__ slabE, const DpBack *__restrict__ slabB,
-                           int slab_stride, int tstride, DpState *__restrict__ outS, double *__restrict__ outE,
-                           DpBack *__restrict__ hb, const DpMoved *__restrict__ mv)
-{
-    const int nc = ctl->total;
-    if (ctl->nuniq > ctl->caps) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&ctl->err, 5); return; }
-    const bool hist_ok = (long long)ctl->hb_off + (long long)ctl->nuniq * tstride <= (long long)ctl->hb_cap;
-    if (!hist_ok && threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&ctl->err, 7);
-    for (int c = blockIdx.x; c < nc; c += gridDim.x) {
-        if (leader[c] != c) continue;
-        const int dst = rank[c];
-        const int r = keys[c].r;
-        for (int e = threadIdx.x; e < (1 << r); e += blockDim.x) {
-            double best = 0.0;
-            DpBack bb;
-            bb.state = -1; bb.entry = 0; bb.signs = 0;
-            bool have = false;
-            for (int j = c; j < nc; j++) {
-                if (leader[j] != c) continue;
-                const int p = parent[j];
-                const double v = slabE[(size_t)p * 2 * slab_stride + e];
-                if (!have || !(best < v)) { best = v; bb = slabB[(size_t)p * 2 * slab_stride + e]; have = true; }
-            }
-            outE[(size_t)dst * tstride + e] = best;
-            if (hist_ok) hb[(size_t)ctl->hb_off + (size_t)dst * tstride + e] = bb;
-        }
-        if (threadIdx.x == 0) {
-            DpState &S = outS[dst];
-            const int p = parent[c];
-            for (int i = 0; i < kDpRows; i++) S.g[i] = keys[c].g[i];
-            for (int i = 0; i < kDpVW; i++) S.valid[i] = mv[p].valid[i];
-            S.r = r;
-            S.sright = keys[c].sright;
-        }
-    }
-}
-
-// end of a site step: log it, advance the history offsets, the merged states become the next input
-__global__ void k_dp_advance(DpCtl *ctl, DpStepLog *log, int m, int tstride)
-{
-    if (threadIdx.x || blockIdx.x) return;
-    if (ctl->step < ctl->log_cap) {
-        DpStepLog &L = log[ctl->step];
-        L.m = m; L.nin = ctl->nin; L.total = ctl->total; L.nuniq = ctl->nuniq; L.hm_off = ctl->hm_off; L.hb_off = ctl->hb_off;
-    } else ctl->err = max(ctl->err, 7);
-    if (ctl->err) ctl->nuniq = 0;          // a failed step leaves no state: later steps become no-ops, the host sees err
-    ctl->step++;
-    ctl->hm_off += ctl->nin;
-    ctl->hb_off += ctl->nuniq * tstride;
-    ctl->nin = ctl->nuniq;
-    ctl->total = 0;
-    ctl->nuniq = 0;
-}
-
-// history of (state, entry) of the current site back to step `floor`: (term position, sign) pairs in the order
-// the reference appends them (Ps_indices / Ps_signs, cpp/stab.cpp:752-759).  One thread.
-__global__ void k_dp_trace(const DpCtl *ctl, const DpStepLog *log, const DpHistAdd *hm, const DpBack *hb, int tstride, int floor_step,
-                           int state, int entry, int *out_pos, int *out_sign, int *out_n, int cap)
-{
-    if (threadIdx.x || blockIdx.x) return;
-    int n = 0, s = state, e = entry;
-    for (int t = ctl->step - 1; t >= floor_step; t--) {
-        const DpStepLog &L = log[t];
-        const DpBack b = hb[(size_t)L.hb_off + (size_t)s * tstride + e];
-        if (b.state < 0) break;
-        const DpHistAdd &h = hm[L.hm_off + b.state];
-        for (int a = h.nadd - 1; a >= 0 && n < cap; a--) { out_pos[n] = h.added[a]; out_sign[n] = ((b.signs >> a) & 1) ? -1 : 1; n++; }
-        s = b.state; e = b.entry;
-    }
-    for (int i = 0; i < n / 2; i++) {       // collected newest-first: reverse to chronological order
-        int t = out_pos[i]; out_pos[i] = out_pos[n - 1 - i]; out_pos[n - 1 - i] = t;
-        t = out_sign[i]; out_sign[i] = out_sign[n - 1 - i]; out_sign[n - 1 - i] = t;
-    }
-    *out_n = n;
-}
-
-// valid bits outside the key range may differ between the children of one key (the reference keeps the
-// first-inserted state's: State::merge_gs copies state1, cpp/state.cpp:415-419); take the FIRST child's,
-// as the sequential merge does.
 
 // ------------------------------------------------------------------------------------------------
 // Right environments.  k_sr_evolve: evolve_stab (cpp/state.cpp:147-185) for one parent group per thread:
@@ -526,11 +341,9 @@ SGS_D void signed_add(uint64_t *g, int *q, int &r, uint64_t P, int qP)     // St
     r++;
 }
 
-__global__ void k_sr_evolve(DpTerms H, int m, const DpGroup *__restrict__ next, int nnext, int maxbranch,
-                            DpGroup *__restrict__ out, int *__restrict__ nout, SrBranch *scratch, int *err)
+SGS_D void sr_evolve_one(const DpTerms &H, int m, const DpGroup *next, int p, int maxbranch, DpGroup *out, int *nout,
+                         SrBranch *scratch, int *err)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nnext) return;
     const int k = H.k, o = m - k + 1;                       // everything is done at the child origin o_m = o_{m+1} - 1
     SrBranch *br = scratch + (size_t)p * 2 * maxbranch, *nb = br + maxbranch;
     int nbr = 1;
@@ -598,55 +411,470 @@ __global__ void k_sr_evolve(DpTerms H, int m, const DpGroup *__restrict__ next, 
     nout[p] = nbr;
 }
 
-// children of all parents, compacted in parent order: flat[], par[] and the per-parent offsets; one block
-__global__ void k_sr_flatten(const DpGroup *__restrict__ strided, const int *__restrict__ nout, int nnext, int maxbranch,
-                             DpGroup *__restrict__ flat, int *__restrict__ par, int *__restrict__ offp, int *total)
+
+// ------------------------------------------------------------------------------------------------
+// Keyed de-duplication shared by the DP merge (keys = DpKey) and the right-environment levels (keys =
+// DpGroup).  An open-addressing table of generation-tagged 64-bit words replaces the reference's std::map
+// on a boost hash (cpp/state.cpp:187-216, :494-517): no clearing between uses (a word whose tag is not the
+// current generation is empty), every entry finds the slot of its key, the slot's `lead` becomes the lowest
+// entry index with that key (deterministic) and `head` a linked list of all entries with the key.
+struct DdSlot { unsigned long long claim, lead, head; };
+
+struct DdView {
+    uint64_t *pre;               // per entry: order prefix
+    int *owner, *next, *leader;  // per entry: slot, next entry with the same key, lowest entry with the same key
+    int *rank;                   // per leader entry: number of distinct smaller keys
+    int *lidx;                   // compacted leader entries (arbitrary order)
+    uint64_t *lpre;              // their prefixes
+    DdSlot *tab;
+    unsigned mask;               // table size - 1
+};
+
+SGS_D unsigned long long gtime()
 {
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int p = 0; p < nnext; p++) { offp[p] = run; run += nout[p]; }
-        offp[nnext] = run;
-        *total = run;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define SGS_PROF(ctl, i) do { if (tid == 0) { const unsigned long long t__ = gtime(); (ctl)->prof[i] += t__ - tprof; tprof = t__; } } while (0)
+
+SGS_D uint64_t mix64(uint64_t h, uint64_t v)
+{
+    h ^= v + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
+    h *= 0xBF58476D1CE4E5B9ULL;
+    return h ^ (h >> 31);
+}
+SGS_D uint64_t key_hash(const DpKey &k)
+{
+    uint64_t h = mix64((uint64_t)k.r << 32 | (uint32_t)k.sright, 0x1234567ULL);
+    for (int i = 0; i < k.r; i++) h = mix64(h, k.g[i]);
+    for (int i = 0; i < kDpVW; i++) h = mix64(h, k.v[i]);
+    return h;
+}
+SGS_D uint64_t key_hash(const DpGroup &k)
+{
+    uint64_t h = mix64((uint64_t)k.r, 0x7654321ULL);
+    for (int i = 0; i < k.r; i++) h = mix64(h, k.g[i] ^ ((uint64_t)k.neg[i] << 63));
+    return h;
+}
+// order prefixes: pre(a) < pre(b) implies key_cmp(a, b) < 0; equal prefixes decide nothing.  Never all-ones.
+SGS_D uint64_t key_prefix(const DpKey &k)
+{
+    const uint64_t g0 = k.r > 0 ? (k.g[0] > 0xFFFFFFFFULL ? 0xFFFFFFFFULL : k.g[0]) : 0;
+    return ((uint64_t)k.r << 58) | ((uint64_t)(k.sright & 0x3FFFFFF) << 32) | g0;
+}
+SGS_D uint64_t key_prefix(const DpGroup &k)
+{
+    const uint64_t lim = (1ULL << 58) - 1;
+    const uint64_t g0 = k.r > 0 ? (k.g[0] > lim ? lim : k.g[0]) : 0;
+    return ((uint64_t)k.r << 58) | g0;
+}
+
+// entry c looks up / claims the slot of its key, then joins the slot's minimum and list
+template <typename K>
+SGS_D void dd_insert(const DdView &D, unsigned gen, const K *keys, int c)
+{
+    const uint64_t h = key_hash(keys[c]);
+    D.pre[c] = key_prefix(keys[c]);
+    const unsigned long long tw = 0xFFFFFFFFu - gen, tagv = tw << 32;
+    unsigned i = (unsigned)(h ^ (h >> 32)) & D.mask;
+    for (;;) {
+        unsigned long long cur = *(volatile unsigned long long *)&D.tab[i].claim;
+        bool mine = false;
+        while ((cur >> 32) != tw) {
+            const unsigned long long prev = atomicCAS(&D.tab[i].claim, cur, tagv | (unsigned)c);
+            if (prev == cur) { mine = true; break; }
+            cur = prev;
+        }
+        if (mine) break;
+        const int j = (int)(unsigned)cur;
+        if (key_cmp(keys[j], keys[c]) == 0) break;
+        i = (i + 1) & D.mask;
     }
-    __syncthreads();
-    for (int p = threadIdx.x; p < nnext; p += blockDim.x) {
-        const int o = offp[p], c = offp[p + 1] - o;
-        for (int j = 0; j < c; j++) { flat[o + j] = strided[(size_t)p * maxbranch + j]; par[o + j] = p; }
+    D.owner[c] = (int)i;
+    atomicMin(&D.tab[i].lead, tagv | (unsigned)c);
+    const unsigned long long old = atomicExch(&D.tab[i].head, tagv | (unsigned)c);
+    D.next[c] = ((old >> 32) == tw) ? (int)(unsigned)old : -1;
+}
+
+// leader of every entry; leaders are compacted (order irrelevant) for the all-pairs ranking
+SGS_D void dd_lead(const DdView &D, int c, int *nuniq)
+{
+    const int ld = (int)(unsigned)D.tab[D.owner[c]].lead;
+    D.leader[c] = ld;
+    if (ld == c) {
+        const int p = atomicAdd(nuniq, 1);
+        D.lidx[p] = c;
+        D.lpre[p] = D.pre[c];
     }
 }
 
-// get_map_from_stabs (cpp/state.cpp:187-216) on the device: distinct groups in rank order and, per group, the
-// ascending list of distinct parents (py/state.py:523 uses a set).  info = {nuniq, nlinks, maxfan}.  One block.
-__global__ void k_sr_build(const DpGroup *__restrict__ flat, const int *__restrict__ par, const int *__restrict__ offp,
-                           const int *__restrict__ leader, const int *__restrict__ rank, const int *total_dev, const int *nuniq_dev,
-                           DpGroup *__restrict__ groups, int *__restrict__ map_off, int *__restrict__ map_idx, int *__restrict__ cnt, int *info)
+// rank of compacted leader p = number of distinct smaller keys; the warp's lanes stride over the leaders.
+// This is the deterministic total order that replaces the reference's iteration order of a std::map on a
+// boost hash.
+template <typename K>
+SGS_D void dd_rank_warp(const DdView &D, const K *keys, int p, int nuniq, int lane)
 {
-    const int total = *total_dev, nuniq = *nuniq_dev;
-    for (int g = threadIdx.x; g <= nuniq; g += blockDim.x) cnt[g] = 0;
+    const int c = D.lidx[p];
+    const uint64_t pc = D.lpre[p];
+    int cnt = 0;
+    for (int q = lane; q < nuniq; q += 32) {
+        const uint64_t pq = D.lpre[q];
+        if (pq < pc) cnt++;
+        else if (pq == pc && q != p && key_cmp(keys[D.lidx[q]], keys[c]) < 0) cnt++;
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) D.rank[c] = cnt;
+}
+
+// exclusive scan of v[0..n) into off[0..n] by one block; returns the total to every thread of the block
+SGS_D int block_scan(const int *v, int *off, int n, int *part /* shared, blockDim.x ints */)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = (n + nt - 1) / nt, lo = min(tid * per, n), hi = min(lo + per, n);
+    int acc = 0;
+    for (int i = lo; i < hi; i++) acc += v[i];
+    part[tid] = acc;
     __syncthreads();
-    for (int c = threadIdx.x; c < total; c += blockDim.x) {
-        const int g = rank[leader[c]];
-        if (leader[c] == c) groups[g] = flat[c];
-        bool first = true;                       // first child of this parent in this group?
-        for (int j = offp[par[c]]; j < c; j++) if (leader[j] == leader[c]) { first = false; break; }
-        if (first) atomicAdd(&cnt[g], 1);
+    if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < nt; i++) { const int t = part[i]; part[i] = run; run += t; }
+        off[n] = run;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0, mf = 0;
-        for (int g = 0; g < nuniq; g++) { map_off[g] = run; run += cnt[g]; mf = max(mf, cnt[g]); }
-        map_off[nuniq] = run;
-        info[0] = nuniq; info[1] = run; info[2] = mf;
-    }
+    acc = part[tid];
+    for (int i = lo; i < hi; i++) { const int t = v[i]; off[i] = acc; acc += t; }
     __syncthreads();
-    for (int g = threadIdx.x; g < nuniq; g += blockDim.x) {
-        int k = map_off[g];
-        for (int c = 0; c < total; c++) {
-            if (rank[leader[c]] != g) continue;
-            bool first = true;
-            for (int j = offp[par[c]]; j < c; j++) if (leader[j] == leader[c]) { first = false; break; }
-            if (first) map_idx[k++] = par[c];
+    return off[n];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_dp_run: StateMachine::evolve (cpp/state.cpp:483-533) for `nsteps` consecutive sites in one persistent
+// cooperative launch.  Phases of one site, separated by grid barriers:
+//   P0 move every state to the next site (one thread per state) and count its accepted next environments
+//   P1 block 0: exclusive scan -> child offsets, capacity checks, error snapshot
+//   P2 emit the children (key + parent) in deterministic (parent, map) order
+//   P3 key de-duplication   P4 leaders   P5 key order of the leaders (warp per leader)
+//   P6 merge: element-wise table minimum over the children of a key (warp per key), back-pointers to the
+//      history pool, merged states in key order
+struct DpBufs {
+    DpState *S[2];
+    double *E[2];
+    double *slabE;
+    DpBack *slabB;
+    DpMoved *moved;
+    int *nacc, *off;
+    DpKey *keys;
+    int *parent;
+    DdView D;
+    DpHistAdd *hm;
+    DpBack *hb;
+    DpCtl *ctl;
+    DpStepLog *log;
+    const DpLevelDev *levels;
+    int tstride, slab_stride;
+};
+
+__global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int nsteps)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int part[256];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, wid = tid >> 5, nw = nth >> 5;
+    DpCtl *ctl = B.ctl;
+    // private running copies: every thread advances them identically, thread 0 publishes them at the end
+    int nin = ctl->nin, cur = ctl->cur, hm_off = ctl->hm_off, hb_off = ctl->hb_off, step = ctl->step, err = ctl->err;
+    unsigned gen = ctl->gen;
+    const int caps = ctl->caps, capc = ctl->capc, hm_cap = ctl->hm_cap, hb_cap = ctl->hb_cap, log_cap = ctl->log_cap;
+    const int tstride = B.tstride, slab_stride = B.slab_stride, k = H.k;
+    grid.sync();                                             // everyone has read ctl before anyone writes it
+    unsigned long long tprof = gtime();
+    for (int it = 0; it < nsteps && !err; it++) {
+        const int m = m0 + it, m1 = m + 1;
+        const DpLevelDev L = B.levels[m], Ln = B.levels[m1];
+        const DpState *inS = B.S[cur];
+        const double *inE = B.E[cur];
+        DpState *outS = B.S[cur ^ 1];
+        double *outE = B.E[cur ^ 1];
+        if ((long long)hm_off + nin > hm_cap || step >= log_cap) { err = 7; break; }
+        // ---- P0
+        if (tid == 0) ctl->nuniq = 0;
+        for (int s = tid; s < nin; s += nth) {
+            double *E = B.slabE + (size_t)s * 2 * slab_stride;
+            DpBack *Bk = B.slabB + (size_t)s * 2 * slab_stride;
+            dp_move_one(H, m, s, inS[s], inE, tstride, L.groups, B.moved[s], E, E + slab_stride, Bk, Bk + slab_stride, B.hm + hm_off + s,
+                        &ctl->err);
+            int cnt = 0;
+            if (!B.moved[s].dead) {
+                Ech e;
+                dp_valid_span(H, m, B.moved[s], e);
+                const int sr = B.moved[s].sright;
+                for (int j = L.map_off[sr]; j < L.map_off[sr + 1]; j++) cnt += dp_accepts(e, Ln.groups[L.map_idx[j]]);
+            }
+            B.nacc[s] = cnt;
         }
+        grid.sync();
+        SGS_PROF(ctl, 0);
+        // ---- P1
+        if (blockIdx.x == 0) {
+            const int tot = block_scan(B.nacc, B.off, nin, part);
+            if (threadIdx.x == 0) {
+                if (tot > capc) atomicMax(&ctl->err, 6);
+                ctl->total = tot;
+                ctl->err_snap = ctl->err;
+            }
+        }
+        grid.sync();
+        SGS_PROF(ctl, 1);
+        const int total = ctl->total;
+        err = ctl->err_snap;
+        if (err) break;
+        // ---- P2: key = valid bits for last site in [m1+1, min(m1+k-1, n)), positions relative to boff[m1]
+        {
+            const int lo = H.boff[min(m1 + 1, H.n + 1)] - H.boff[m1];
+            const int hi = H.boff[min(max(m1 + k - 1, m1 + 1), H.n)] - H.boff[m1];
+            for (int s = tid; s < nin; s += nth) {
+                const DpMoved &mv = B.moved[s];
+                if (mv.dead) continue;
+                Ech e;
+                dp_valid_span(H, m, mv, e);
+                int c = B.off[s];
+                for (int j = L.map_off[mv.sright]; j < L.map_off[mv.sright + 1]; j++) {
+                    if (!dp_accepts(e, Ln.groups[L.map_idx[j]])) continue;
+                    DpKey &K = B.keys[c];
+                    for (int i = 0; i < kDpRows; i++) K.g[i] = mv.g[i];
+                    for (int i = 0; i < kDpVW; i++) K.v[i] = 0;
+                    for (int b = lo; b < hi; b++) if (vget(mv.valid, b)) K.v[b >> 6] |= 1ULL << (b & 63);
+                    K.r = mv.r;
+                    K.sright = L.map_idx[j];
+                    B.parent[c] = s;
+                    c++;
+                }
+            }
+        }
+        grid.sync();
+        SGS_PROF(ctl, 2);
+        // ---- P3
+        for (int c = tid; c < total; c += nth) dd_insert(B.D, gen, B.keys, c);
+        grid.sync();
+        SGS_PROF(ctl, 3);
+        // ---- P4
+        for (int c = tid; c < total; c += nth) dd_lead(B.D, c, &ctl->nuniq);
+        grid.sync();
+        SGS_PROF(ctl, 4);
+        const int nuniq = ctl->nuniq;
+        if (nuniq > caps) { err = 5; break; }
+        if ((long long)hb_off + (long long)nuniq * tstride > hb_cap) { err = 7; break; }
+        // ---- P5
+        for (int p = wid; p < nuniq; p += nw) dd_rank_warp(B.D, B.keys, p, nuniq, lane);
+        grid.sync();
+        SGS_PROF(ctl, 5);
+        // ---- P6: exact ties are won by the later child (merge_gs keeps the newcomer unless the incumbent is
+        //      strictly lower, cpp/stab.cpp:832); valid bits outside the key come from the first child
+        //      (State::merge_gs copies state1, cpp/state.cpp:415-419)
+        for (int p = wid; p < nuniq; p += nw) {
+            const int c = B.D.lidx[p], dst = B.D.rank[c], r = B.keys[c].r;
+            const int head = (int)(unsigned)B.D.tab[B.D.owner[c]].head;
+            for (int e = lane; e < (1 << r); e += 32) {
+                double best = 0.0;
+                int bj = -1, bp = 0;
+                for (int j = head; j >= 0; j = B.D.next[j]) {
+                    const int pj = B.parent[j];
+                    const double v = B.slabE[(size_t)pj * 2 * slab_stride + e];
+                    if (bj < 0 || v < best || (v == best && j > bj)) { best = v; bj = j; bp = pj; }
+                }
+                outE[(size_t)dst * tstride + e] = best;
+                B.hb[(size_t)hb_off + (size_t)dst * tstride + e] = B.slabB[(size_t)bp * 2 * slab_stride + e];
+            }
+            if (lane == 0) {
+                DpState &S = outS[dst];
+                const int pp = B.parent[c];
+                for (int i = 0; i < kDpRows; i++) S.g[i] = B.keys[c].g[i];
+                for (int i = 0; i < kDpVW; i++) S.valid[i] = B.moved[pp].valid[i];
+                S.r = r;
+                S.sright = B.keys[c].sright;
+            }
+        }
+        if (tid == 0) {
+            DpStepLog &Lg = B.log[step];
+            Lg.m = m; Lg.nin = nin; Lg.total = total; Lg.nuniq = nuniq; Lg.hm_off = hm_off; Lg.hb_off = hb_off;
+        }
+        grid.sync();
+        SGS_PROF(ctl, 6);
+        hm_off += nin; hb_off += nuniq * tstride; step++; nin = nuniq; cur ^= 1; gen++;
+    }
+    grid.sync();                                             // every exit above is uniform; nobody reads ctl any more
+    if (tid == 0) {
+        if (err) { atomicMax(&ctl->err, err); nin = 0; }
+        ctl->nin = nin; ctl->cur = cur; ctl->hm_off = hm_off; ctl->hb_off = hb_off; ctl->step = step; ctl->gen = gen;
+        ctl->total = 0; ctl->nuniq = nin;
+    }
+}
+
+// history of (state, entry) of the current site back to step `floor`: (term position, sign) pairs in the order
+// the reference appends them (Ps_indices / Ps_signs, cpp/stab.cpp:752-759).  One thread.
+__global__ void k_dp_trace(const DpCtl *ctl, const DpStepLog *log, const DpHistAdd *hm, const DpBack *hb, int tstride, int floor_step,
+                           int state, int entry, int *out_pos, int *out_sign, int *out_n, int cap)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    int n = 0, s = state, e = entry;
+    for (int t = ctl->step - 1; t >= floor_step; t--) {
+        const DpStepLog &L = log[t];
+        const DpBack b = hb[(size_t)L.hb_off + (size_t)s * tstride + e];
+        if (b.state < 0) break;
+        const DpHistAdd &h = hm[L.hm_off + b.state];
+        for (int a = h.nadd - 1; a >= 0 && n < cap; a--) { out_pos[n] = h.added[a]; out_sign[n] = ((b.signs >> a) & 1) ? -1 : 1; n++; }
+        s = b.state; e = b.entry;
+    }
+    for (int i = 0; i < n / 2; i++) {       // collected newest-first: reverse to chronological order
+        int t = out_pos[i]; out_pos[i] = out_pos[n - 1 - i]; out_pos[n - 1 - i] = t;
+        t = out_sign[i]; out_sign[i] = out_sign[n - 1 - i]; out_sign[n - 1 - i] = t;
+    }
+    *out_n = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_sr_run: generate_Sright_all (cpp/state.cpp:218-238) for the levels m_hi-1 ... m_lo in one persistent
+// cooperative launch: evolve_stab for every group of level m+1 (one thread each), get_map_from_stabs
+// (cpp/state.cpp:187-216) as keyed de-duplication + key order, level tables bump-allocated on the device.
+// The list of compatible next groups of a group is a set (py/state.py:523); its order is not significant.
+struct SrCtl {
+    int err, err_snap, total, nuniq, nlinks, done_m;
+    unsigned gen;
+    unsigned long long pool_used, pool_cap;
+    unsigned long long prof[10];  // ns spent per phase (thread 0's view), for SGS_DP_TRACE
+};
+struct SrBufs {
+    SrBranch *scratch;           // [2 * cap]
+    DpGroup *strided, *flat;     // [cap]
+    int *nout, *offp;            // per parent
+    int *par, *cnt, *moff;       // per child / per group
+    uint8_t *first;
+    DdView D;
+    SrCtl *ctl;
+    DpLevelDev *levels;
+    char *pool;
+    int cap;
+};
+
+SGS_D void *sr_take(SrCtl *ctl, char *pool, size_t bytes)       // one thread
+{
+    const unsigned long long at = (ctl->pool_used + 255ULL) & ~255ULL;
+    if (at + bytes > ctl->pool_cap) { atomicMax(&ctl->err, 8); return nullptr; }
+    ctl->pool_used = at + bytes;
+    return pool + at;
+}
+
+__global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, int m_lo)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int part[256];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, wid = tid >> 5, nw = nth >> 5;
+    SrCtl *ctl = B.ctl;
+    unsigned gen = ctl->gen;
+    int err = ctl->err;
+    grid.sync();
+    unsigned long long tprof = gtime();
+    int m = m_hi - 1;
+    for (; m >= m_lo && !err; m--) {
+        const DpLevelDev Ln = B.levels[m + 1];
+        const int nnext = Ln.count;
+        const int nterm = H.boff[m + 1] - H.boff[m];
+        if (nterm > 16) { err = 3; break; }
+        const int maxbranch = 1 << nterm;
+        if ((long long)nnext * maxbranch > B.cap) { err = 4; break; }
+        // ---- S0: children of every parent group
+        if (tid == 0) ctl->nuniq = 0;
+        for (int p = tid; p < nnext; p += nth) sr_evolve_one(H, m, Ln.groups, p, maxbranch, B.strided, B.nout, B.scratch, &ctl->err);
+        grid.sync();
+        SGS_PROF(ctl, 0);
+        // ---- S1: offsets of the children in parent order
+        if (blockIdx.x == 0) {
+            const int tot = block_scan(B.nout, B.offp, nnext, part);
+            if (threadIdx.x == 0) { ctl->total = tot; ctl->err_snap = ctl->err; }
+        }
+        grid.sync();
+        SGS_PROF(ctl, 1);
+        const int total = ctl->total;
+        err = ctl->err_snap;
+        if (err) break;
+        // ---- S2: compact
+        for (int p = tid; p < nnext; p += nth) {
+            const int o = B.offp[p], c = B.offp[p + 1] - o;
+            for (int j = 0; j < c; j++) { B.flat[o + j] = B.strided[(size_t)p * maxbranch + j]; B.par[o + j] = p; }
+        }
+        grid.sync();
+        SGS_PROF(ctl, 2);
+        // ---- S3 / S4: distinct groups
+        for (int c = tid; c < total; c += nth) dd_insert(B.D, gen, B.flat, c);
+        grid.sync();
+        SGS_PROF(ctl, 3);
+        for (int c = tid; c < total; c += nth) dd_lead(B.D, c, &ctl->nuniq);
+        grid.sync();
+        SGS_PROF(ctl, 4);
+        const int nuniq = ctl->nuniq;
+        // ---- S5: key order; level storage; clear the per-group counters
+        for (int p = wid; p < nuniq; p += nw) dd_rank_warp(B.D, B.flat, p, nuniq, lane);
+        for (int g = tid; g <= nuniq; g += nth) B.cnt[g] = 0;
+        if (tid == 0) {
+            DpLevelDev &Lv = B.levels[m];
+            Lv.groups = (const DpGroup *)sr_take(ctl, B.pool, sizeof(DpGroup) * (size_t)max(nuniq, 1));
+            Lv.map_off = (const int *)sr_take(ctl, B.pool, sizeof(int) * (size_t)(nuniq + 1));
+            Lv.count = nuniq;
+            ctl->err_snap = ctl->err;
+        }
+        grid.sync();
+        SGS_PROF(ctl, 5);
+        err = ctl->err_snap;
+        if (err) break;
+        // ---- S6: groups in key order; a (group, parent) link is counted once (first child of that parent in the group)
+        {
+            DpGroup *groups = const_cast<DpGroup *>(B.levels[m].groups);
+            for (int c = tid; c < total; c += nth) {
+                const int ld = B.D.leader[c], g = B.D.rank[ld];
+                if (ld == c) groups[g] = B.flat[c];
+                bool first = true;
+                for (int j = B.offp[B.par[c]]; j < c; j++) if (B.D.leader[j] == ld) { first = false; break; }
+                B.first[c] = first;
+                if (first) atomicAdd(&B.cnt[g], 1);
+            }
+        }
+        grid.sync();
+        SGS_PROF(ctl, 6);
+        // ---- S7: link offsets
+        if (blockIdx.x == 0) {
+            const int nl = block_scan(B.cnt, B.moff, nuniq, part);
+            int *map_off = const_cast<int *>(B.levels[m].map_off);
+            for (int g = threadIdx.x; g <= nuniq; g += blockDim.x) { map_off[g] = B.moff[g]; if (g < nuniq) B.cnt[g] = B.moff[g]; }
+            if (threadIdx.x == 0) {
+                DpLevelDev &Lv = B.levels[m];
+                Lv.map_idx = (const int *)sr_take(ctl, B.pool, sizeof(int) * (size_t)max(nl, 1));
+                Lv.nlinks = nl;
+                ctl->err_snap = ctl->err;
+            }
+        }
+        grid.sync();
+        SGS_PROF(ctl, 7);
+        err = ctl->err_snap;
+        if (err) break;
+        // ---- S8: fill the links (cnt[g] is now the group's write cursor)
+        {
+            int *map_idx = const_cast<int *>(B.levels[m].map_idx);
+            for (int c = tid; c < total; c += nth)
+                if (B.first[c]) map_idx[atomicAdd(&B.cnt[B.D.rank[B.D.leader[c]]], 1)] = B.par[c];
+        }
+        SGS_PROF(ctl, 8);
+        gen++;
+        // no barrier: the next level's S0/S1 touch none of S8's inputs and two barriers precede the first overwrite
+    }
+    grid.sync();
+    if (tid == 0) {
+        if (err) atomicMax(&ctl->err, err);
+        ctl->gen = gen;
+        ctl->done_m = m + 1;
     }
 }
 

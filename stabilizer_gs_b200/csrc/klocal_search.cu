@@ -77,18 +77,18 @@ struct DBuf {                       // growable device buffer carved from the po
     }
 };
 
-struct Level {                      // type_Sright (cpp/state.hpp:49-51) of one site, device resident
-    int count = 0, nlinks = 0, maxfan = 0;
-    DpGroup *d_groups = nullptr;
-    int *d_map_off = nullptr, *d_map_idx = nullptr;
-    std::vector<DpGroup> groups;    // host copy (periodic driver only)
-};
-
 bool group_equal(const DpGroup &a, const DpGroup &b)
 {
     if (a.r != b.r) return false;
     for (int i = 0; i < a.r; i++) if (a.g[i] != b.g[i] || a.neg[i] != b.neg[i]) return false;
     return true;
+}
+
+unsigned pow2_at_least(size_t v)
+{
+    unsigned p = 1024;
+    while (p < v) p <<= 1;
+    return p;
 }
 
 }  // namespace
@@ -98,68 +98,59 @@ struct HostState { DpState s; std::vector<double> E; };
 struct KlocalMachine::Impl {
     Hamiltonian H;
     sgs_opts opts{};
-    int device = 0;
+    int device = 0, nsm = 0;
     int n = 0, k = 0, T = 0, W = 1;
-    bool keep_host_levels = false;
+    int scale = 1;                 // capacity multiplier (x4 per retry after an overflow)
+    int max_m = 0;                 // highest level index (n, or l(1+cmax)+k for the periodic driver)
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     bool seg_open = false;
-    uint64_t *d_rows = nullptr;
-    double *d_w = nullptr;
-    int *d_boff = nullptr, *d_fidx = nullptr, *d_info = nullptr;
-    DpCtl *d_ctl = nullptr;
-    DpStepLog *d_log = nullptr;
-    int log_cap = 1 << 14;
-    std::vector<int> boff;
-    DpTerms terms{};
     DevPool pool;
-    std::map<int, Level> lv;
-    int m_ = 0, tstride = 1, slab_stride = 1;
-    // capacities of the DP batch buffers (grown x4 and the run restarted on overflow)
-    int caps = 0, capc = 0, hm_cap = 0, hb_cap = 0;
-    DBuf<DpState> statesA, statesB;
-    DBuf<double> tabEA, tabEB, slabE;
-    DBuf<DpBack> slabB, hb;
-    DBuf<DpHistAdd> hm;
-    DBuf<DpMoved> moved;
-    DBuf<int> nacc, off, parent, leader, rank, trace;
-    DBuf<DpKey> keys;
-    // right-environment scratch
-    DBuf<SrBranch> srscratch;
-    DBuf<DpGroup> srout, srflat, srgroups;
-    DBuf<int> srcnt, srpar, sroffp, srleader, srrank, srmapoff, srmapidx, srgcnt;
-    bool cur_is_A = true;
-    int hist_floor = 0;
-    DpCtl hctl{};                  // last host copy of the control block
+    DpTerms terms{};
+    std::vector<int> boff;
+    // right environments
+    SrBufs sr{};
+    SrCtl hsr{};
+    DpLevelDev *d_levels = nullptr;
+    std::vector<DpLevelDev> hlev;                  // host mirror of the level directory
+    std::map<int, std::vector<DpGroup>> hgroups;   // host copies of level group lists (periodic driver)
+    // DP
+    DpBufs dp{};
+    DpCtl hctl{};
     bool hctl_valid = false;
+    int m_ = 0, tstride = 1, slab_stride = 1;
+    int caps = 0, capc = 0, hm_cap = 0, hb_cap = 0, log_cap = 1 << 14;
+    int *d_trace = nullptr;
+    int trace_cap = 0;
     unsigned launches = 0;
     double dev_seconds = 0.0;
     Status pending;                // error met inside a const accessor, returned by the next call
 
     ~Impl();
     Status init();
-    Status ensure_caps(int scale);
-    Status gen_level(int m, const Level &next, Level &out);
+    Status alloc_sr(int cap, size_t pool_bytes);
+    Status alloc_dp();
+    Status set_level(int m, const DpLevelDev &L);
+    Status make_top_level(int m);
+    Status run_sright(int m_hi, int m_lo);
+    Status host_groups(int m, const std::vector<DpGroup> **out);
     Status gen_sright_all();
     Status write_ctl(int nin, bool reset_history);
     Status sync_ctl();
     Status init_states();
-    Status evolve();
+    Status advance(int nsteps);
     Status set_states(const std::vector<HostState> &hs, int m, bool reset_history);
     Status get_states(std::vector<HostState> &hs);
     Status ground_state(sgs_result *out);
     Status traceback(int state, int entry, std::vector<std::pair<int, int>> &out);   // (file index, sign) in history order
     Status fetch_log(std::vector<DpStepLog> &log);
-    DpState *cur_states() { return cur_is_A ? statesA.p : statesB.p; }
-    DpState *nxt_states() { return cur_is_A ? statesB.p : statesA.p; }
-    double *cur_E() { return cur_is_A ? tabEA.p : tabEB.p; }
-    double *nxt_E() { return cur_is_A ? tabEB.p : tabEA.p; }
+    template <typename T> Status take(T **p, size_t count) { void *q = nullptr; SGS_CUDA_TRY(pool.take(&q, std::max<size_t>(count, 1) * sizeof(T))); *p = (T *)q; return Status(); }
 };
 
 KlocalMachine::Impl::~Impl()
 {
     cudaSetDevice(device);
-    cudaFree(d_rows); cudaFree(d_w); cudaFree(d_boff); cudaFree(d_fidx); cudaFree(d_info); cudaFree(d_ctl); cudaFree(d_log);
+    if (st) cudaStreamSynchronize(st);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
@@ -169,11 +160,13 @@ static Status ctl_error(int err, const char *what)
 {
     const char *why = err == 1 ? "window group rank exceeds the table limit (k too large)"
                       : err == 2 ? "more than 256 terms in k+2 consecutive last-site buckets"
-                      : err == 3 ? "more than 30 terms share one last site"
+                      : err == 3 ? "more than 16 terms share one last site (2^t right-environment branches)"
                       : err == 4 ? "right-environment branch capacity exceeded"
                                  : "batch capacity exceeded";
-    return Status::fail(err >= 5 ? SGS_ERR_OVERFLOW : SGS_ERR_LIMIT, std::string(what) + ": " + why);
+    return Status::fail(err >= 4 ? SGS_ERR_OVERFLOW : SGS_ERR_LIMIT, std::string(what) + ": " + why);
 }
+
+#define SGS_TRY(expr) do { Status s__ = (expr); if (!s__.ok()) return s__; } while (0)
 
 Status KlocalMachine::Impl::init()
 {
@@ -189,10 +182,33 @@ Status KlocalMachine::Impl::init()
     device = opts.device;
     if (device < 0 || device >= ndev) return Status::fail(SGS_ERR_ARG, "device ordinal out of range");
     SGS_CUDA_TRY(cudaSetDevice(device));
+    SGS_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    int coop = 0, occ_dp = 0, occ_sr = 0;
+    SGS_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dp, k_dp_run, 256, 0));
+    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_sr_run, 256, 0));
+    if (!coop || occ_dp < 1 || occ_sr < 1) return Status::fail(SGS_ERR_CUDA, "device cannot co-schedule the persistent DP kernels");
     SGS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     SGS_CUDA_TRY(cudaEventCreate(&e0));
     SGS_CUDA_TRY(cudaEventCreate(&e1));
     W = (2 * (n + 1) + 63) / 64;
+    tstride = 1 << std::min(k, kDpTab);
+    slab_stride = tstride;
+    max_m = std::max(max_m, n);
+    const long long base = std::max<long long>(2048, (1ll << 22) / ((long long)slab_stride * 16));   // k=4: 16384 states
+    caps = (int)std::min<long long>(base * scale, 1ll << 22);
+    capc = (int)std::min<long long>((long long)caps * 8, 1ll << 25);
+    hm_cap = (int)std::min<long long>((long long)caps * 64, 1ll << 27);
+    hb_cap = (int)std::min<long long>((long long)caps * 64 * std::min(tstride, 64), 1ll << 29);
+    const int srcap = (int)std::min<long long>(65536ll * scale, 1ll << 24);
+    const size_t srpool = ((size_t)64 << 20) * (size_t)std::min(scale, 64);
+    {   // one cached arena for the tables, the DP batch buffers, the right-environment scratch and the level tables
+        const size_t dpb = (size_t)caps * (2 * sizeof(DpState) + sizeof(DpMoved) + 16) + (size_t)caps * tstride * 16 +
+                           (size_t)caps * 2 * slab_stride * 16 + (size_t)capc * (sizeof(DpKey) + 48 + 2 * sizeof(DdSlot)) +
+                           (size_t)hm_cap * sizeof(DpHistAdd) + (size_t)hb_cap * sizeof(DpBack);
+        const size_t srb = (size_t)srcap * (2 * sizeof(SrBranch) + 2 * sizeof(DpGroup) + 64 + 2 * sizeof(DdSlot)) + srpool;
+        SGS_CUDA_TRY(pool.open(device, dpb + srb + ((size_t)16 << 20)));
+    }
     const int Tn = std::max(T, 1);
     std::vector<uint64_t> rows((size_t)Tn * W, 0);
     std::vector<double> w(Tn, 0.0);
@@ -205,136 +221,150 @@ Status KlocalMachine::Impl::init()
     }
     boff = H.bucket_off;            // n + 1 entries, boff[n] = T
     boff.push_back(T);              // boff[n + 1]
-    SGS_CUDA_TRY(cudaMalloc((void **)&d_rows, rows.size() * 8));
-    SGS_CUDA_TRY(cudaMalloc((void **)&d_w, w.size() * 8));
-    SGS_CUDA_TRY(cudaMalloc((void **)&d_boff, boff.size() * 4));
-    SGS_CUDA_TRY(cudaMalloc((void **)&d_fidx, fidx.size() * 4));
-    SGS_CUDA_TRY(cudaMalloc((void **)&d_info, 64));
-    SGS_CUDA_TRY(cudaMalloc((void **)&d_ctl, sizeof(DpCtl)));
-    SGS_CUDA_TRY(cudaMalloc((void **)&d_log, sizeof(DpStepLog) * log_cap));
+    uint64_t *d_rows; double *d_w; int *d_boff, *d_fidx;
+    SGS_TRY(take(&d_rows, rows.size())); SGS_TRY(take(&d_w, w.size())); SGS_TRY(take(&d_boff, boff.size())); SGS_TRY(take(&d_fidx, fidx.size()));
     SGS_CUDA_TRY(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaMemcpyAsync(d_w, w.data(), w.size() * 8, cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaMemcpyAsync(d_boff, boff.data(), boff.size() * 4, cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaMemcpyAsync(d_fidx, fidx.data(), fidx.size() * 4, cudaMemcpyHostToDevice, st));
-    SGS_CUDA_TRY(cudaMemsetAsync(d_info, 0, 64, st));
-    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));                // the host vectors go out of scope
     terms.n = n; terms.k = k; terms.T = T; terms.W = W;
     terms.rows = d_rows; terms.w = d_w; terms.boff = d_boff; terms.file_index = d_fidx;
-    tstride = 1 << std::min(k, kDpTab);
-    slab_stride = 1 << std::min(k, kDpTab);
-    {   // one cached arena for the DP batch buffers, the right-environment scratch and the level tables
-        const size_t c0 = (size_t)std::max<long long>(2048, (1ll << 22) / ((long long)slab_stride * 16));
-        const size_t est = c0 * (2 * sizeof(DpState) + sizeof(DpMoved) + 8 * sizeof(DpKey) + 64 * sizeof(DpHistAdd) + 64) +
-                           c0 * (size_t)tstride * 16 + c0 * 2 * (size_t)slab_stride * 16 +
-                           c0 * 64 * (size_t)std::min(tstride, 64) * sizeof(DpBack) + ((size_t)96 << 20);
-        SGS_CUDA_TRY(pool.open(device, est));
-    }
-    return ensure_caps(1);
-}
-
-// batch buffers of the DP; scale = 1 on creation, x4 per retry after an overflow
-Status KlocalMachine::Impl::ensure_caps(int scale)
-{
-    const long long base = std::max<long long>(2048, (1ll << 22) / ((long long)slab_stride * 16));   // k=4: 16384 states
-    caps = (int)std::min<long long>(base * scale, 1ll << 22);
-    capc = (int)std::min<long long>((long long)caps * 8, 1ll << 24);
-    hm_cap = (int)std::min<long long>((long long)caps * 64, 1ll << 26);
-    hb_cap = (int)std::min<long long>((long long)caps * 64 * std::min(tstride, 64), 1ll << 28);
-    SGS_CUDA_TRY(statesA.need(pool, caps)); SGS_CUDA_TRY(statesB.need(pool, caps));
-    SGS_CUDA_TRY(tabEA.need(pool, (size_t)caps * tstride)); SGS_CUDA_TRY(tabEB.need(pool, (size_t)caps * tstride));
-    SGS_CUDA_TRY(slabE.need(pool, (size_t)caps * 2 * slab_stride)); SGS_CUDA_TRY(slabB.need(pool, (size_t)caps * 2 * slab_stride));
-    SGS_CUDA_TRY(moved.need(pool, caps)); SGS_CUDA_TRY(nacc.need(pool, caps + 1)); SGS_CUDA_TRY(off.need(pool, caps + 1));
-    SGS_CUDA_TRY(keys.need(pool, capc)); SGS_CUDA_TRY(parent.need(pool, capc)); SGS_CUDA_TRY(leader.need(pool, capc)); SGS_CUDA_TRY(rank.need(pool, capc));
-    SGS_CUDA_TRY(hm.need(pool, hm_cap)); SGS_CUDA_TRY(hb.need(pool, hb_cap));
-    SGS_CUDA_TRY(trace.need(pool, 2 * (size_t)(T + 16) + 32));
+    hlev.assign(max_m + 2, DpLevelDev{});
+    SGS_TRY(take(&d_levels, hlev.size()));
+    SGS_CUDA_TRY(cudaMemsetAsync(d_levels, 0, hlev.size() * sizeof(DpLevelDev), st));
+    SGS_TRY(alloc_sr(srcap, srpool));
+    SGS_TRY(alloc_dp());
     return Status();
 }
 
-// one backward step of generate_Sright_all (cpp/state.cpp:222-236): level m from level m+1, all on the device;
-// the host only reads three integers (distinct groups, links, widest fan-out)
-Status KlocalMachine::Impl::gen_level(int m, const Level &next, Level &out)
+static Status alloc_view(KlocalMachine::Impl &K, DdView &D, size_t entries, cudaStream_t st)
 {
-    const int nnext = next.count;
-    const int nterm = boff[m + 1] - boff[m];
-    if (nterm > 16) return Status::fail(SGS_ERR_LIMIT, "more than 16 terms share one last site (2^t right-environment branches)");
-    const int maxbranch = 1 << nterm;
-    const size_t bound = (size_t)nnext * maxbranch;
-    SGS_CUDA_TRY(srscratch.need(pool, 2 * bound));
-    SGS_CUDA_TRY(srout.need(pool, bound)); SGS_CUDA_TRY(srflat.need(pool, bound)); SGS_CUDA_TRY(srgroups.need(pool, bound));
-    SGS_CUDA_TRY(srcnt.need(pool, nnext + 1)); SGS_CUDA_TRY(sroffp.need(pool, nnext + 1));
-    SGS_CUDA_TRY(srpar.need(pool, bound)); SGS_CUDA_TRY(srleader.need(pool, bound)); SGS_CUDA_TRY(srrank.need(pool, bound));
-    SGS_CUDA_TRY(srmapoff.need(pool, bound + 1)); SGS_CUDA_TRY(srmapidx.need(pool, bound)); SGS_CUDA_TRY(srgcnt.need(pool, bound + 1));
-    int *d_total = d_info + 4, *d_nuniq = d_info + 5, *d_err = d_info + 6;
-    SGS_CUDA_TRY(cudaMemsetAsync(d_info, 0, 32, st));
-    k_sr_evolve<<<(nnext + 63) / 64, 64, 0, st>>>(terms, m, next.d_groups, nnext, maxbranch, srout.p, srcnt.p, srscratch.p, d_err);
-    k_sr_flatten<<<1, 256, 0, st>>>(srout.p, srcnt.p, nnext, maxbranch, srflat.p, srpar.p, sroffp.p, d_total);
-    const int gb = (int)std::min<size_t>((bound + 63) / 64, 512);
-    k_group_leader<DpGroup><<<gb, 64, 0, st>>>(srflat.p, d_total, srleader.p);
-    k_group_rank<DpGroup><<<gb, 64, 0, st>>>(srflat.p, d_total, srleader.p, srrank.p, d_nuniq);
-    k_sr_build<<<1, 256, 0, st>>>(srflat.p, srpar.p, sroffp.p, srleader.p, srrank.p, d_total, d_nuniq, srgroups.p, srmapoff.p,
-                                  srmapidx.p, srgcnt.p, d_info);
-    launches += 5;
-    SGS_CUDA_TRY(cudaGetLastError());
-    int info[8];
-    SGS_CUDA_TRY(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, st));
+    SGS_TRY(K.take(&D.pre, entries)); SGS_TRY(K.take(&D.owner, entries)); SGS_TRY(K.take(&D.next, entries));
+    SGS_TRY(K.take(&D.leader, entries)); SGS_TRY(K.take(&D.rank, entries)); SGS_TRY(K.take(&D.lidx, entries));
+    SGS_TRY(K.take(&D.lpre, entries));
+    const unsigned tsz = pow2_at_least(2 * entries);
+    SGS_TRY(K.take(&D.tab, tsz));
+    D.mask = tsz - 1;
+    SGS_CUDA_TRY(cudaMemsetAsync(D.tab, 0xFF, (size_t)tsz * sizeof(DdSlot), st));   // every word carries the tag of generation 0 = empty
+    return Status();
+}
+
+Status KlocalMachine::Impl::alloc_sr(int cap, size_t pool_bytes)
+{
+    sr.cap = cap;
+    SGS_TRY(take(&sr.scratch, 2 * (size_t)cap)); SGS_TRY(take(&sr.strided, cap)); SGS_TRY(take(&sr.flat, cap));
+    SGS_TRY(take(&sr.nout, (size_t)cap + 1)); SGS_TRY(take(&sr.offp, (size_t)cap + 1)); SGS_TRY(take(&sr.par, cap));
+    SGS_TRY(take(&sr.cnt, (size_t)cap + 1)); SGS_TRY(take(&sr.moff, (size_t)cap + 1)); SGS_TRY(take(&sr.first, cap));
+    SGS_TRY(alloc_view(*this, sr.D, cap, st));
+    SGS_TRY(take(&sr.ctl, 1));
+    SGS_TRY(take(&sr.pool, pool_bytes));
+    sr.levels = d_levels;
+    hsr = SrCtl{};
+    hsr.gen = 1;
+    hsr.pool_cap = pool_bytes;
+    SGS_CUDA_TRY(cudaMemcpyAsync(sr.ctl, &hsr, sizeof(SrCtl), cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
-    if (info[6]) return ctl_error(info[6], "right environments");
-    out.count = info[0]; out.nlinks = info[1]; out.maxfan = info[2];
-    SGS_CUDA_TRY(pool.take((void **)&out.d_groups, sizeof(DpGroup) * std::max(out.count, 1)));
-    SGS_CUDA_TRY(pool.take((void **)&out.d_map_off, sizeof(int) * (out.count + 1)));
-    SGS_CUDA_TRY(pool.take((void **)&out.d_map_idx, sizeof(int) * std::max(out.nlinks, 1)));
-    SGS_CUDA_TRY(cudaMemcpyAsync(out.d_groups, srgroups.p, sizeof(DpGroup) * out.count, cudaMemcpyDeviceToDevice, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(out.d_map_off, srmapoff.p, sizeof(int) * (out.count + 1), cudaMemcpyDeviceToDevice, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(out.d_map_idx, srmapidx.p, sizeof(int) * out.nlinks, cudaMemcpyDeviceToDevice, st));
-    if (keep_host_levels) {
-        out.groups.resize(out.count);
-        SGS_CUDA_TRY(cudaMemcpyAsync(out.groups.data(), srgroups.p, sizeof(DpGroup) * out.count, cudaMemcpyDeviceToHost, st));
-        SGS_CUDA_TRY(cudaStreamSynchronize(st));
-    }
     return Status();
 }
 
-static Status make_top_level(KlocalMachine::Impl &K, Level &top);
-
-Status KlocalMachine::Impl::gen_sright_all()
+Status KlocalMachine::Impl::alloc_dp()
 {
-    Level top;
-    Status s = make_top_level(*this, top);     // Stab::empty(H.k, H.n - H.k + 1), cpp/state.cpp:219
-    if (!s.ok()) return s;
-    lv[n] = top;
-    for (int m = n - 1; m >= 0; m--) {
-        Level L;
-        s = gen_level(m, lv[m + 1], L);
-        if (!s.ok()) return s;
-        lv[m] = L;
-    }
+    for (int i = 0; i < 2; i++) { SGS_TRY(take(&dp.S[i], caps)); SGS_TRY(take(&dp.E[i], (size_t)caps * tstride)); }
+    SGS_TRY(take(&dp.slabE, (size_t)caps * 2 * slab_stride)); SGS_TRY(take(&dp.slabB, (size_t)caps * 2 * slab_stride));
+    SGS_TRY(take(&dp.moved, caps)); SGS_TRY(take(&dp.nacc, (size_t)caps + 1)); SGS_TRY(take(&dp.off, (size_t)caps + 1));
+    SGS_TRY(take(&dp.keys, capc)); SGS_TRY(take(&dp.parent, capc));
+    SGS_TRY(alloc_view(*this, dp.D, capc, st));
+    SGS_TRY(take(&dp.hm, hm_cap)); SGS_TRY(take(&dp.hb, hb_cap));
+    SGS_TRY(take(&dp.ctl, 1)); SGS_TRY(take(&dp.log, log_cap));
+    trace_cap = T + 16;
+    SGS_TRY(take(&d_trace, 2 * (size_t)trace_cap + 8));
+    dp.levels = d_levels;
+    dp.tstride = tstride; dp.slab_stride = slab_stride;
+    hctl = DpCtl{};
+    hctl.gen = 1;
+    hctl.caps = caps; hctl.capc = capc; hctl.hm_cap = hm_cap; hctl.hb_cap = hb_cap; hctl.log_cap = log_cap;
+    SGS_CUDA_TRY(cudaMemcpyAsync(dp.ctl, &hctl, sizeof(DpCtl), cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    hctl_valid = true;
     return Status();
 }
 
-static Status make_top_level(KlocalMachine::Impl &K, Level &top)
+Status KlocalMachine::Impl::set_level(int m, const DpLevelDev &L)
+{
+    hlev[m] = L;
+    hgroups.erase(m);
+    SGS_CUDA_TRY(cudaMemcpyAsync(d_levels + m, &hlev[m], sizeof(DpLevelDev), cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    return Status();
+}
+
+// Stab::empty(H.k, H.n - H.k + 1) as the only group of level m (cpp/state.cpp:219)
+Status KlocalMachine::Impl::make_top_level(int m)
 {
     DpGroup empty{};
     const int zero2[2] = {0, 0};
-    top.count = 1; top.nlinks = 0; top.maxfan = 0;
-    SGS_CUDA_TRY(K.pool.take((void **)&top.d_groups, sizeof(DpGroup)));
-    SGS_CUDA_TRY(K.pool.take((void **)&top.d_map_off, sizeof(int) * 2));
-    SGS_CUDA_TRY(K.pool.take((void **)&top.d_map_idx, sizeof(int)));
-    SGS_CUDA_TRY(cudaMemcpy(top.d_groups, &empty, sizeof(DpGroup), cudaMemcpyHostToDevice));
-    SGS_CUDA_TRY(cudaMemcpy(top.d_map_off, zero2, sizeof(zero2), cudaMemcpyHostToDevice));
-    top.groups.assign(1, empty);
+    DpGroup *g; int *mo, *mi;
+    SGS_TRY(take(&g, 1)); SGS_TRY(take(&mo, 2)); SGS_TRY(take(&mi, 1));
+    SGS_CUDA_TRY(cudaMemcpyAsync(g, &empty, sizeof(DpGroup), cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(mo, zero2, sizeof(zero2), cudaMemcpyHostToDevice, st));
+    DpLevelDev L{g, mo, mi, 1, 0};
+    return set_level(m, L);
+}
+
+// levels m_hi-1 ... m_lo from level m_hi: one cooperative launch, one synchronisation
+Status KlocalMachine::Impl::run_sright(int m_hi, int m_lo)
+{
+    for (int attempt = 0;; attempt++) {
+        void *args[] = {&terms, &sr, &m_hi, &m_lo};
+        SGS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_sr_run, dim3(nsm), dim3(256), args, 0, st));
+        launches++;
+        SGS_CUDA_TRY(cudaMemcpyAsync(&hsr, sr.ctl, sizeof(SrCtl), cudaMemcpyDeviceToHost, st));
+        SGS_CUDA_TRY(cudaStreamSynchronize(st));
+        if (!hsr.err) break;
+        if ((hsr.err != 4 && hsr.err != 8) || attempt >= 6) return ctl_error(hsr.err, "right environments");
+        // scratch (4) or level pool (8) too small: take bigger ones and redo this run
+        const int ncap = hsr.err == 4 ? (int)std::min<long long>((long long)sr.cap * 8, 1ll << 26) : sr.cap;
+        const size_t npool = hsr.err == 8 ? (size_t)hsr.pool_cap * 4 : (size_t)hsr.pool_cap;
+        if (hsr.err == 4) {
+            SGS_TRY(alloc_sr(ncap, npool));                 // fresh scratch, table and control block
+        } else {
+            SGS_TRY(take(&sr.pool, npool));                 // levels already written stay where they are
+            hsr.pool_used = 0; hsr.pool_cap = npool;
+            hsr.err = hsr.err_snap = 0;
+            SGS_CUDA_TRY(cudaMemcpyAsync(sr.ctl, &hsr, sizeof(SrCtl), cudaMemcpyHostToDevice, st));
+        }
+    }
+    SGS_CUDA_TRY(cudaMemcpyAsync(&hlev[m_lo], d_levels + m_lo, sizeof(DpLevelDev) * (m_hi - m_lo), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int m = m_lo; m < m_hi; m++) hgroups.erase(m);
     return Status();
+}
+
+Status KlocalMachine::Impl::host_groups(int m, const std::vector<DpGroup> **out)
+{
+    auto it = hgroups.find(m);
+    if (it == hgroups.end()) {
+        std::vector<DpGroup> g(hlev[m].count);
+        if (!g.empty()) SGS_CUDA_TRY(cudaMemcpy(g.data(), hlev[m].groups, sizeof(DpGroup) * g.size(), cudaMemcpyDeviceToHost));
+        it = hgroups.emplace(m, std::move(g)).first;
+    }
+    *out = &it->second;
+    return Status();
+}
+
+Status KlocalMachine::Impl::gen_sright_all()
+{
+    SGS_TRY(make_top_level(n));
+    return run_sright(n, 0);
 }
 
 Status KlocalMachine::Impl::write_ctl(int nin, bool reset_history)
 {
-    Status s = sync_ctl();
-    if (!s.ok()) return s;
-    DpCtl c = hctl;
-    c.nin = nin; c.total = 0; c.nuniq = 0; c.err = 0;
-    if (reset_history) { c.hm_off = 0; c.hb_off = 0; c.step = 0; hist_floor = 0; }
-    c.caps = caps; c.capc = capc; c.hm_cap = hm_cap; c.hb_cap = hb_cap; c.log_cap = log_cap;
-    hctl = c;
-    SGS_CUDA_TRY(cudaMemcpyAsync(d_ctl, &hctl, sizeof(DpCtl), cudaMemcpyHostToDevice, st));
+    SGS_TRY(sync_ctl());
+    hctl.nin = nin; hctl.total = 0; hctl.nuniq = nin; hctl.err = 0; hctl.err_snap = 0; hctl.cur = 0;
+    if (reset_history) { hctl.hm_off = 0; hctl.hb_off = 0; hctl.step = 0; }
+    SGS_CUDA_TRY(cudaMemcpyAsync(dp.ctl, &hctl, sizeof(DpCtl), cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
     hctl_valid = true;
     return Status();
@@ -345,7 +375,7 @@ Status KlocalMachine::Impl::sync_ctl()
 {
     if (hctl_valid && !seg_open) return Status();
     if (seg_open) SGS_CUDA_TRY(cudaEventRecord(e1, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(&hctl, d_ctl, sizeof(DpCtl), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(&hctl, dp.ctl, sizeof(DpCtl), cudaMemcpyDeviceToHost, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
     if (seg_open) {
         float ms = 0.f;
@@ -369,25 +399,23 @@ Status KlocalMachine::Impl::set_states(const std::vector<HostState> &hs, int m, 
         ss[i] = hs[i].s;
         for (size_t e = 0; e < hs[i].E.size() && e < (size_t)tstride; e++) ee[i * tstride + e] = hs[i].E[e];
     }
-    Status s = write_ctl((int)hs.size(), reset_history);
-    if (!s.ok()) return s;
-    SGS_CUDA_TRY(cudaMemcpyAsync(cur_states(), ss.data(), ns * sizeof(DpState), cudaMemcpyHostToDevice, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(cur_E(), ee.data(), ns * tstride * sizeof(double), cudaMemcpyHostToDevice, st));
+    SGS_TRY(write_ctl((int)hs.size(), reset_history));      // states go to buffer 0
+    SGS_CUDA_TRY(cudaMemcpyAsync(dp.S[0], ss.data(), ns * sizeof(DpState), cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(dp.E[0], ee.data(), ns * tstride * sizeof(double), cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
     return Status();
 }
 
 Status KlocalMachine::Impl::get_states(std::vector<HostState> &hs)
 {
-    Status s = sync_ctl();
-    if (!s.ok()) return s;
+    SGS_TRY(sync_ctl());
     const int ns = hctl.nin;
     hs.assign(ns, HostState());
     if (!ns) return Status();
     std::vector<DpState> ss(ns);
     std::vector<double> ee((size_t)ns * tstride);
-    SGS_CUDA_TRY(cudaMemcpyAsync(ss.data(), cur_states(), ns * sizeof(DpState), cudaMemcpyDeviceToHost, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(ee.data(), cur_E(), ee.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(ss.data(), dp.S[hctl.cur], ns * sizeof(DpState), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(ee.data(), dp.E[hctl.cur], ee.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
     for (int i = 0; i < ns; i++) {
         hs[i].s = ss[i];
@@ -399,7 +427,7 @@ Status KlocalMachine::Impl::get_states(std::vector<HostState> &hs)
 // StateMachine ctor (cpp/state.cpp:445-458): one state per right environment at site 0
 Status KlocalMachine::Impl::init_states()
 {
-    std::vector<HostState> hs(lv[0].count);
+    std::vector<HostState> hs(hlev[0].count);
     for (size_t i = 0; i < hs.size(); i++) {
         memset(&hs[i].s, 0, sizeof(DpState));
         for (int w = 0; w < kDpVW; w++) hs[i].s.valid[w] = ~0ULL;
@@ -407,53 +435,41 @@ Status KlocalMachine::Impl::init_states()
         hs[i].s.sright = (int)i;
         hs[i].E = {0.0};
     }
-    cur_is_A = true;
     return set_states(hs, 0, true);
 }
 
-// StateMachine::evolve (cpp/state.cpp:483-533): every state of site m → merged states of site m+1.
-// Enqueue only: batch sizes live in the device control block, nothing is read back here.
-Status KlocalMachine::Impl::evolve()
+// StateMachine::evolve (cpp/state.cpp:483-533) for nsteps consecutive sites: one cooperative launch, enqueued
+// only — batch sizes live in the device control block, nothing is read back here.
+Status KlocalMachine::Impl::advance(int nsteps)
 {
-    if (lv.find(m_) == lv.end() || lv.find(m_ + 1) == lv.end()) return Status::fail(SGS_ERR_ARG, "no right-environment level for this site");
     if (!pending.ok()) return pending;
-    const Level &L = lv[m_], &Ln = lv[m_ + 1];
+    if (nsteps <= 0) return Status();
+    if (m_ + nsteps > max_m || !hlev[m_].groups || !hlev[m_ + nsteps].groups)
+        return Status::fail(SGS_ERR_ARG, "no right-environment level for this site");
     if (!seg_open) { SGS_CUDA_TRY(cudaEventRecord(e0, st)); seg_open = true; }
     hctl_valid = false;
-    const int tb = 64, gs = std::min((caps + tb - 1) / tb, 256), gc = std::min((capc + tb - 1) / tb, 512);
-    k_dp_move<<<gs, tb, 0, st>>>(terms, m_, cur_states(), cur_E(), d_ctl, tstride, L.d_groups, moved.p, slabE.p, slabB.p, slab_stride, hm.p);
-    k_dp_fanout<<<gs, tb, 0, st>>>(terms, m_, moved.p, d_ctl, L.d_map_off, L.d_map_idx, Ln.d_groups, nacc.p);
-    k_dp_scan<<<1, 1024, 0, st>>>(nacc.p, d_ctl, off.p);
-    k_dp_emit<<<gs, tb, 0, st>>>(terms, m_, moved.p, d_ctl, L.d_map_off, L.d_map_idx, Ln.d_groups, off.p, keys.p, parent.p);
-    k_group_leader<DpKey><<<gc, tb, 0, st>>>(keys.p, &d_ctl->total, leader.p);
-    k_group_rank<DpKey><<<gc, tb, 0, st>>>(keys.p, &d_ctl->total, leader.p, rank.p, &d_ctl->nuniq);
-    k_dp_merge<<<1024, 64, 0, st>>>(keys.p, parent.p, leader.p, rank.p, d_ctl, slabE.p, slabB.p, slab_stride, tstride, nxt_states(), nxt_E(),
-                                    hb.p, moved.p);
-    k_dp_advance<<<1, 1, 0, st>>>(d_ctl, d_log, m_, tstride);
-    launches += 8;
-    SGS_CUDA_TRY(cudaGetLastError());
-    cur_is_A = !cur_is_A;
-    m_++;
+    int m0 = m_;
+    void *args[] = {&terms, &dp, &m0, &nsteps};
+    SGS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_dp_run, dim3(nsm), dim3(256), args, 0, st));
+    launches++;
+    m_ += nsteps;
     return Status();
 }
 
 Status KlocalMachine::Impl::fetch_log(std::vector<DpStepLog> &log)
 {
-    Status s = sync_ctl();
-    if (!s.ok()) return s;
+    SGS_TRY(sync_ctl());
     log.resize(std::min(hctl.step, log_cap));
-    if (!log.empty()) SGS_CUDA_TRY(cudaMemcpy(log.data(), d_log, sizeof(DpStepLog) * log.size(), cudaMemcpyDeviceToHost));
+    if (!log.empty()) SGS_CUDA_TRY(cudaMemcpy(log.data(), dp.log, sizeof(DpStepLog) * log.size(), cudaMemcpyDeviceToHost));
     return Status();
 }
 
 // history of (state, entry) of the current site back to the last cleared point, walked on the device
 Status KlocalMachine::Impl::traceback(int state, int entry, std::vector<std::pair<int, int>> &out)
 {
-    Status s = sync_ctl();
-    if (!s.ok()) return s;
-    const int cap = (int)(trace.cap / 2) - 8;
-    int *d_pos = trace.p, *d_sign = trace.p + cap, *d_n = trace.p + 2 * cap;
-    k_dp_trace<<<1, 1, 0, st>>>(d_ctl, d_log, hm.p, hb.p, tstride, hist_floor, state, entry, d_pos, d_sign, d_n, cap);
+    SGS_TRY(sync_ctl());
+    int *d_pos = d_trace, *d_sign = d_trace + trace_cap, *d_n = d_trace + 2 * trace_cap;
+    k_dp_trace<<<1, 1, 0, st>>>(dp.ctl, dp.log, dp.hm, dp.hb, tstride, 0, state, entry, d_pos, d_sign, d_n, trace_cap);
     launches++;
     int nn = 0;
     SGS_CUDA_TRY(cudaMemcpyAsync(&nn, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -489,8 +505,10 @@ Status KlocalMachine::Impl::ground_state(sgs_result *out)
     uint64_t transitions = 0;                   // evolve_single calls = states entering each site step
     for (const DpStepLog &e : lg) transitions += (uint64_t)e.nin;
     std::vector<std::pair<int, int>> hist;
+    const auto tg0 = std::chrono::steady_clock::now();
     s = traceback(bs, be, hist);
     if (!s.ok()) return s;
+    const auto tg1 = std::chrono::steady_clock::now();
     const int Wout = (2 * n + 63) / 64;
     const int mg = (int)hist.size();
     std::vector<uint64_t> rows((size_t)std::max(mg, 1) * Wout, 0);
@@ -507,6 +525,9 @@ Status KlocalMachine::Impl::ground_state(sgs_result *out)
     std::vector<int8_t> ts(std::max(T, 1), 0);
     s = group_energy(device, n, rankc, rows.data(), signs.data(), T, P.data(), nullptr, ts.data());   // K2
     if (!s.ok()) return s;
+    if (getenv("SGS_DP_TRACE"))
+        fprintf(stderr, "  ground state: traceback %.3f ms, canonicalise + term signs %.3f ms\n", std::chrono::duration<double>(tg1 - tg0).count() * 1e3,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - tg1).count() * 1e3);
     out->energy = bestE;
     out->n = n; out->m = rankc; out->W = Wout; out->T = T;
     out->gens = (uint64_t *)calloc((size_t)std::max(rankc, 1) * Wout, 8);
@@ -526,12 +547,13 @@ Status KlocalMachine::Impl::ground_state(sgs_result *out)
 KlocalMachine::KlocalMachine() : impl_(new Impl()) {}
 KlocalMachine::~KlocalMachine() { delete impl_; }
 
-Status KlocalMachine::create(const Hamiltonian &H, const sgs_opts &opts, int periodic_cmax, std::unique_ptr<KlocalMachine> &out)
+Status KlocalMachine::create(const Hamiltonian &H, const sgs_opts &opts, int periodic_cmax, std::unique_ptr<KlocalMachine> &out, int scale)
 {
     std::unique_ptr<KlocalMachine> M(new KlocalMachine());
     M->impl_->H = H;
     M->impl_->opts = opts;
-    M->impl_->keep_host_levels = periodic_cmax >= 0;
+    M->impl_->scale = std::max(scale, 1);
+    M->impl_->max_m = periodic_cmax >= 0 ? std::max(H.n, H.l * (1 + periodic_cmax) + H.k) : H.n;
     const auto t0 = std::chrono::steady_clock::now();
     Status s = M->impl_->init();
     if (!s.ok()) return s;
@@ -539,11 +561,13 @@ Status KlocalMachine::create(const Hamiltonian &H, const sgs_opts &opts, int per
         const auto t1 = std::chrono::steady_clock::now();
         s = M->impl_->gen_sright_all();
         if (!s.ok()) return s;
-        if (getenv("SGS_DP_TRACE"))
-            fprintf(stderr, "klocal create: init %.3f ms, right environments %.3f ms\n", std::chrono::duration<double>(t1 - t0).count() * 1e3,
-                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count() * 1e3);
+        const auto t2 = std::chrono::steady_clock::now();
         s = M->impl_->init_states();
         if (!s.ok()) return s;
+        if (getenv("SGS_DP_TRACE"))
+            fprintf(stderr, "klocal create: init %.3f ms, right environments %.3f ms, initial states %.3f ms\n",
+                    std::chrono::duration<double>(t1 - t0).count() * 1e3, std::chrono::duration<double>(t2 - t1).count() * 1e3,
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count() * 1e3);
     }
     out = std::move(M);
     return Status();
@@ -556,48 +580,48 @@ int KlocalMachine::nstates() const
     if (!s.ok()) { impl_->pending = s; return -1; }
     return impl_->hctl.nin;
 }
-int KlocalMachine::sright_count(int m) const
-{
-    auto it = impl_->lv.find(m);
-    return it == impl_->lv.end() ? 0 : it->second.count;
-}
-Status KlocalMachine::evolve() { return impl_->evolve(); }
+int KlocalMachine::sright_count(int m) const { return m < 0 || m >= (int)impl_->hlev.size() ? 0 : impl_->hlev[m].count; }
+Status KlocalMachine::evolve() { return impl_->advance(1); }
 Status KlocalMachine::ground_state(sgs_result *out) { return impl_->ground_state(out); }
 
 Status klocal_search(const Hamiltonian &H, const sgs_opts &opts, sgs_result *out)
 {
     const auto t0 = std::chrono::steady_clock::now();
     std::unique_ptr<KlocalMachine> M;
-    Status s = KlocalMachine::create(H, opts, -1, M);
-    if (!s.ok()) return s;
-    const auto t1 = std::chrono::steady_clock::now();
-    std::vector<int> sr(H.n + 1), sp(H.n + 1);
-    for (int m = 0; m <= H.n; m++) sr[m] = M->sright_count(m);
-    KlocalMachine::Impl &K = *M->impl();
+    std::vector<int> sr(H.n + 1), sp(H.n + 1, 0);
     std::vector<DpStepLog> dlog;
+    double ms_create = 0, ms_dp = 0;
     for (int scale = 1;; scale *= 4) {
-        sp[0] = M->nstates();
-        while (M->m() < H.n) {             // n sites enqueued back to back, no host round trip in between
-            s = M->evolve();
-            if (!s.ok()) return s;
+        const auto ta = std::chrono::steady_clock::now();
+        M.reset();                         // hand the arena back before asking for a bigger one
+        Status s = KlocalMachine::create(H, opts, -1, M, scale);
+        if (s.ok()) {
+            const auto tb = std::chrono::steady_clock::now();
+            ms_create = std::chrono::duration<double>(tb - ta).count() * 1e3;
+            sp[0] = M->nstates();
+            s = M->impl()->advance(H.n);   // all n sites in one persistent launch
+            if (s.ok()) s = M->impl()->fetch_log(dlog);
+            ms_dp = std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count() * 1e3;
         }
-        s = K.fetch_log(dlog);
         if (s.ok()) break;
-        if (s.code != SGS_ERR_OVERFLOW || scale >= 4096) return s;
-        s = K.ensure_caps(scale * 4);      // a batch outgrew its buffers: grow and redo the DP
-        if (!s.ok()) return s;
-        s = K.init_states();
-        if (!s.ok()) return s;
+        if (s.code != SGS_ERR_OVERFLOW || scale >= 1024) return s;     // a batch outgrew its buffers: redo with 4x the capacity
     }
+    for (int m = 0; m <= H.n; m++) sr[m] = M->sright_count(m);
     for (const DpStepLog &e : dlog) if (e.m + 1 <= H.n) sp[e.m + 1] = e.nuniq;
     const auto t2 = std::chrono::steady_clock::now();
-    s = M->ground_state(out);
+    Status s = M->ground_state(out);
     if (!s.ok()) return s;
     if (getenv("SGS_DP_TRACE")) {
-        const auto t3 = std::chrono::steady_clock::now();
-        fprintf(stderr, "klocal_search: right environments %.3f ms, DP %.3f ms, ground state %.3f ms\n",
-                std::chrono::duration<double>(t1 - t0).count() * 1e3, std::chrono::duration<double>(t2 - t1).count() * 1e3,
-                std::chrono::duration<double>(t3 - t2).count() * 1e3);
+        fprintf(stderr, "klocal_search: create %.3f ms, DP %.3f ms, ground state %.3f ms\n", ms_create, ms_dp,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count() * 1e3);
+        const KlocalMachine::Impl &K = *M->impl();
+        fprintf(stderr, "  DP phases (us): move+fanout %.0f, scan %.0f, emit %.0f, dedup %.0f, leaders %.0f, order %.0f, merge %.0f\n",
+                K.hctl.prof[0] * 1e-3, K.hctl.prof[1] * 1e-3, K.hctl.prof[2] * 1e-3, K.hctl.prof[3] * 1e-3, K.hctl.prof[4] * 1e-3,
+                K.hctl.prof[5] * 1e-3, K.hctl.prof[6] * 1e-3);
+        fprintf(stderr, "  right-environment phases (us): evolve %.0f, scan %.0f, compact %.0f, dedup %.0f, leaders %.0f, order %.0f, "
+                        "groups+links %.0f, offsets %.0f, fill %.0f\n",
+                K.hsr.prof[0] * 1e-3, K.hsr.prof[1] * 1e-3, K.hsr.prof[2] * 1e-3, K.hsr.prof[3] * 1e-3, K.hsr.prof[4] * 1e-3,
+                K.hsr.prof[5] * 1e-3, K.hsr.prof[6] * 1e-3, K.hsr.prof[7] * 1e-3, K.hsr.prof[8] * 1e-3);
     }
     out->nsites = H.n;
     out->sright_counts = (int *)malloc(sizeof(int) * (H.n + 1));
@@ -614,12 +638,12 @@ Status klocal_search(const Hamiltonian &H, const sgs_opts &opts, sgs_result *out
 // py/state.py:309-322) is a relabelling of the level; only the right-environment index has to be looked up
 // in the destination level.
 
-Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &opts, sgs_periodic_result *out)
+static Status periodic_once(const Hamiltonian &H, int cmax, int c, const sgs_opts &opts, int scale, sgs_periodic_result *out)
 {
     const auto t0 = std::chrono::steady_clock::now();
     const double max_float = 1e100;                        // py/klocal_periodic.py:4
     std::unique_ptr<KlocalMachine> M;
-    Status s = KlocalMachine::create(H, opts, cmax, M);
+    Status s = KlocalMachine::create(H, opts, cmax, M, scale);
     if (!s.ok()) return s;
     KlocalMachine::Impl &K = *M->impl();
     const int l = H.l, k = H.k, n = H.n;
@@ -628,42 +652,40 @@ Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &op
 
     // ---- generate_Sright_periodic ----
     const int end = l * (1 + cmax) + k;
-    Level cur;
-    s = make_top_level(K, cur);
+    s = K.make_top_level(end);
     if (!s.ok()) return s;
     std::vector<DpGroup> id;
     bool have_id = false;
     for (;;) {
-        for (int m = end - 1; m >= end - l; m--) {
-            Level nx;
-            s = K.gen_level(m, cur, nx);
-            if (!s.ok()) return s;
-            cur = nx;
-            log.push_back(m); log.push_back(cur.count);
-        }
-        bool same = have_id && id.size() == cur.groups.size();
-        for (size_t i = 0; same && i < id.size(); i++) same = group_equal(id[i], cur.groups[i]);
-        id = cur.groups;
+        s = K.run_sright(end, end - l);
+        if (!s.ok()) return s;
+        for (int m = end - 1; m >= end - l; m--) { log.push_back(m); log.push_back(K.hlev[m].count); }
+        const std::vector<DpGroup> *cur = nullptr;
+        s = K.host_groups(end - l, &cur);
+        if (!s.ok()) return s;
+        bool same = have_id && id.size() == cur->size();
+        for (size_t i = 0; same && i < id.size(); i++) same = group_equal(id[i], (*cur)[i]);
+        id = *cur;
         have_id = true;
         // stabs shifted by +l: same relative rows, now the level-`end` list
+        s = K.set_level(end, K.hlev[end - l]);
+        if (!s.ok()) return s;
         if (same) break;
     }
-    K.lv[end] = cur;
-    for (int m = end - 1; m >= 0; m--) {
-        Level L;
-        s = K.gen_level(m, K.lv[m + 1], L);
-        if (!s.ok()) return s;
-        K.lv[m] = L;
-        log.push_back(m); log.push_back(L.count);
-    }
+    s = K.run_sright(end, 0);
+    if (!s.ok()) return s;
+    for (int m = end - 1; m >= 0; m--) { log.push_back(m); log.push_back(K.hlev[m].count); }
 
     // State.shift(add): relabel the level; the right environment is looked up by content
     auto shift_states = [&](std::vector<HostState> &hs, int from_m, int add) -> Status {
-        const Level &A = K.lv[from_m], &B = K.lv[from_m + add];
+        const std::vector<DpGroup> *A = nullptr, *B = nullptr;
+        Status sg = K.host_groups(from_m, &A);
+        if (sg.ok()) sg = K.host_groups(from_m + add, &B);
+        if (!sg.ok()) return sg;
         for (auto &h : hs) {
-            const DpGroup &G = A.groups[h.s.sright];
+            const DpGroup &G = (*A)[h.s.sright];
             int found = -1;
-            for (size_t i = 0; i < B.groups.size(); i++) if (group_equal(B.groups[i], G)) { found = (int)i; break; }
+            for (size_t i = 0; i < B->size(); i++) if (group_equal((*B)[i], G)) { found = (int)i; break; }
             if (found < 0) return Status::fail(SGS_ERR_ARG, "periodic shift: right environment not found at the shifted site (increase cmax)");
             h.s.sright = found;
         }
@@ -702,7 +724,8 @@ Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &op
         const int m0 = k + l - 1;
         Status st = K.set_states(hs, m0, true);
         if (!st.ok()) return st;
-        for (int i = 0; i < l * cc; i++) { st = K.evolve(); if (!st.ok()) return st; }
+        st = K.advance(l * cc);
+        if (!st.ok()) return st;
         st = K.get_states(res);
         if (!st.ok()) return st;
         st = shift_states(res, m0 + l * cc, -l * cc);
@@ -713,7 +736,8 @@ Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &op
     // ---- driver: py/klocal_periodic.py:21-34 ----
     s = K.init_states();
     if (!s.ok()) return s;
-    for (int i = 0; i < k + 2 * l - 1; i++) { s = K.evolve(); if (!s.ok()) return s; }
+    s = K.advance(k + 2 * l - 1);
+    if (!s.ok()) return s;
     std::vector<HostState> states;
     s = K.get_states(states);
     if (!s.ok()) return s;
@@ -806,6 +830,14 @@ Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &op
     }
     out->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return Status();
+}
+
+Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &opts, sgs_periodic_result *out)
+{
+    for (int scale = 1;; scale *= 4) {
+        Status s = periodic_once(H, cmax, c, opts, scale, out);
+        if (s.code != SGS_ERR_OVERFLOW || scale >= 1024) return s;     // a batch outgrew its buffers: redo with 4x the capacity
+    }
 }
 
 }  // namespace sgs

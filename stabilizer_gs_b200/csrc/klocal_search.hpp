@@ -12,7 +12,8 @@ class KlocalMachine {
   public:
     ~KlocalMachine();
     // periodic_cmax < 0: finite chain (generate_Sright_all); >= 0: generate_Sright_periodic(H, cmax)
-    static Status create(const Hamiltonian &H, const sgs_opts &opts, int periodic_cmax, std::unique_ptr<KlocalMachine> &out);
+    static Status create(const Hamiltonian &H, const sgs_opts &opts, int periodic_cmax, std::unique_ptr<KlocalMachine> &out,
+                         int scale = 1);   // scale: capacity multiplier of the device batch buffers
     int m() const;
     int nstates() const;
     int sright_count(int m) const;
