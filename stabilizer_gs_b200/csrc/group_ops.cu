@@ -1,6 +1,7 @@
 // group_ops.cu — device utilities behind sgs_group_* / sgs_pauli_commute / sgs_measure_int_peaks.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "group_ops.hpp"
@@ -65,8 +66,10 @@ __global__ void k_canonicalize(int m, uint64_t *rows, int8_t *signs, int *rank)
 // K2: Stab::energy / decompose (cpp/stab.cpp:493-505,579-587) for a batch; the group is canonical.
 template <int W>
 __global__ void k_group_energy(int m, const uint64_t *__restrict__ rows, const int8_t *__restrict__ signs, int B,
-                               const uint64_t *__restrict__ P, const int8_t *__restrict__ Psigns, int8_t *__restrict__ out)
+                               const uint64_t *__restrict__ P, const int8_t *__restrict__ Psigns, int8_t *__restrict__ out,
+                               const int *m_dev = nullptr)
 {
+    if (m_dev) m = *m_dev;               // rank left on the device by k_canonicalize
     __shared__ uint64_t C[kMaxRows * W];
     __shared__ int q[kMaxRows], piv[kMaxRows];
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
@@ -184,6 +187,40 @@ Status group_canonicalize(int device, int n, int m, uint64_t *rows, int8_t *sign
     SGS_CUDA_TRY(cudaMemcpy(rank, dk.p, sizeof(int), cudaMemcpyDeviceToHost));
     for (int i = 0; i < m; i++)
         for (int k = 0; k < Win; k++) rows[(size_t)i * Win + k] = i < *rank ? h[(size_t)i * W + k] : 0;
+    return Status();
+}
+
+// K1 + K2 back to back on the caller's stream and workspace (no allocation, one synchronisation): canonicalise
+// the m generator rows, then the sign of every one of the T terms under the canonical group.
+size_t group_finish_ws_bytes(int T) { return (size_t)kMaxRows * 4 * 8 + (size_t)std::max(T, 1) * 4 * 8 + kMaxRows + std::max(T, 1) + 64 + 1024; }
+
+Status group_finish(cudaStream_t st, void *ws, int n, int m, uint64_t *rows, int8_t *signs, int *rank, int T, const uint64_t *P,
+                    int8_t *term_signs)
+{
+    if (m > kMaxRows) return Status::fail(SGS_ERR_LIMIT, "at most 128 generator rows");
+    const int Win = (2 * n + 63) / 64, W = words_for(n), Tn = std::max(T, 1);
+    char *base = (char *)ws;
+    uint64_t *d_rows = (uint64_t *)base; base += (size_t)kMaxRows * 4 * 8;
+    uint64_t *d_P = (uint64_t *)base; base += (size_t)Tn * 4 * 8;
+    int *d_rank = (int *)base; base += 64;
+    int8_t *d_signs = (int8_t *)base; base += (kMaxRows + 255) & ~255;
+    int8_t *d_out = (int8_t *)base;
+    std::vector<uint64_t> hr = widen(rows, m, Win, W), hp = widen(P, T, Win, W);
+    SGS_CUDA_TRY(cudaMemcpyAsync(d_rows, hr.data(), hr.size() * 8, cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(d_P, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, st));
+    if (m) SGS_CUDA_TRY(cudaMemcpyAsync(d_signs, signs, m, cudaMemcpyHostToDevice, st));
+    const int grid = (Tn + 127) / 128;
+    if (W == 1) { k_canonicalize<1><<<1, 32, 0, st>>>(m, d_rows, d_signs, d_rank); k_group_energy<1><<<grid, 128, 0, st>>>(0, d_rows, d_signs, T, d_P, nullptr, d_out, d_rank); }
+    else if (W == 2) { k_canonicalize<2><<<1, 32, 0, st>>>(m, d_rows, d_signs, d_rank); k_group_energy<2><<<grid, 128, 0, st>>>(0, d_rows, d_signs, T, d_P, nullptr, d_out, d_rank); }
+    else { k_canonicalize<4><<<1, 32, 0, st>>>(m, d_rows, d_signs, d_rank); k_group_energy<4><<<grid, 128, 0, st>>>(0, d_rows, d_signs, T, d_P, nullptr, d_out, d_rank); }
+    SGS_CUDA_TRY(cudaGetLastError());
+    SGS_CUDA_TRY(cudaMemcpyAsync(hr.data(), d_rows, hr.size() * 8, cudaMemcpyDeviceToHost, st));
+    if (m) SGS_CUDA_TRY(cudaMemcpyAsync(signs, d_signs, m, cudaMemcpyDeviceToHost, st));
+    if (T) SGS_CUDA_TRY(cudaMemcpyAsync(term_signs, d_out, T, cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(rank, d_rank, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < m; i++)
+        for (int k = 0; k < Win; k++) rows[(size_t)i * Win + k] = i < *rank ? hr[(size_t)i * W + k] : 0;
     return Status();
 }
 

@@ -119,15 +119,19 @@ SGS_D void vclr(uint64_t *v, int i) { v[i >> 6] &= ~(1ULL << (i & 63)); }
 SGS_D void vset_range(uint64_t *v, int a, int b) { for (int i = a; i < b; i++) v[i >> 6] |= 1ULL << (i & 63); }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-cooperative group operations.  One warp owns one state: every lane holds identical copies of the
+// generator rows (uniform control flow), the 2^rank sign table and its back-pointers are split across the
+// lanes.
+//
 // canonical insertion of one '+' generator into a canonical all-'+' group with its sign table
 // (StabEnergies::add, cpp/stab.cpp:747-761 = concat_last + canonicalize :693-697 = transform :699-733 +
 // canonicalize_signs :685-691).  E/bk are the table and back-pointers (2^r entries in, 2^(r+1) out), tmpE/
 // tmpB scratch of the same size; `abit` is the sign bit this addition occupies in DpBack::signs.
-SGS_D void group_add(uint64_t *g, int &r, uint64_t P, double *E, DpBack *bk, double *tmpE, DpBack *tmpB, int abit)
+SGS_D void group_add(uint64_t *g, int &r, uint64_t P, double *E, DpBack *bk, double *tmpE, DpBack *tmpB, int abit, int lane)
 {
     // 1. new generator enters as the LAST axis: new = 2*old + b, b = 1 <=> '-'
     const int sz = 1 << r;
-    for (int o = sz - 1; o >= 0; o--) {
+    for (int o = lane; o < sz; o += 32) {
         const double e = E[o];
         DpBack b = bk[o];
         tmpE[2 * o] = e; tmpE[2 * o + 1] = e;
@@ -155,20 +159,21 @@ SGS_D void group_add(uint64_t *g, int &r, uint64_t P, double *E, DpBack *bk, dou
     //    '-' are reversed so that every stored generator is '+'
     uint32_t flip = 0;
     for (int i = 0; i < r; i++) if (q_sign(g[i], q[i]) < 0) flip |= 1u << (r - 1 - i);
+    __syncwarp();
     const int nsz = 1 << r;
-    for (int s = 0; s < nsz; s++) {
-        uint32_t smask = 0;
-        for (int j = 0; j < r; j++) if ((s >> (r - 1 - j)) & 1) smask |= 1u << j;
+    for (int sv = lane; sv < nsz; sv += 32) {
+        const uint32_t smask = __brev((uint32_t)sv) >> (32 - r);        // bit j of smask = bit r-1-j of sv
         uint32_t ns = 0;
         for (int i = 0; i < r; i++) if (__popc(U[i] & smask) & 1) ns |= 1u << (r - 1 - i);
         ns ^= flip;
-        E[ns] = tmpE[s];
-        bk[ns] = tmpB[s];
+        E[ns] = tmpE[sv];
+        bk[ns] = tmpB[sv];
     }
+    __syncwarp();
 }
 
 // StabEnergies::add_energy (cpp/stab.cpp:819-825) for a member term of a canonical all-'+' group
-SGS_D void group_add_energy(const uint64_t *g, int r, uint64_t P, double w, double *E)
+SGS_D void group_add_energy(const uint64_t *g, int r, uint64_t P, double w, double *E, int lane)
 {
     uint64_t acc = P;
     int qa = q_plus(P);
@@ -177,21 +182,23 @@ SGS_D void group_add_energy(const uint64_t *g, int r, uint64_t P, double w, doub
         if ((acc >> ctz64(g[i])) & 1) { mul1(acc, qa, g[i], q_plus(g[i])); xi |= 1u << (r - 1 - i); }
     const double ws = (qa & 2) ? -w : w;            // w * sign
     const int sz = 1 << r;
-    for (int o = 0; o < sz; o++) E[o] += (__popc(o & xi) & 1) ? -ws : ws;
+    for (int o = lane; o < sz; o += 32) E[o] += (__popc(o & xi) & 1) ? -ws : ws;
 }
 
 // StabEnergies::project_to_next (cpp/stab.cpp:782-801) for relative site 0
-SGS_D void group_project_site0(uint64_t *g, int &r, double *E, DpBack *bk)
+SGS_D void group_project_site0(uint64_t *g, int &r, double *E, DpBack *bk, int lane)
 {
+    __syncwarp();
     while (r > 0) {
         bool any = false;
         for (int i = 0; i < r; i++) any |= (g[i] & 3ULL) != 0;
         if (!any) break;
         const int half = 1 << (r - 1);
-        for (int o = 0; o < half; o++)
+        for (int o = lane; o < half; o += 32)
             if (!(E[o] < E[o + half])) { E[o] = E[o + half]; bk[o] = bk[o + half]; }   // strict '<': a tie keeps '-'
         for (int i = 0; i + 1 < r; i++) g[i] = g[i + 1];
         r--;
+        __syncwarp();
     }
 }
 
@@ -227,9 +234,9 @@ struct DpMoved {
     int r, sright, dead, nadd;
 };
 
-// State::move_to_next + project_to(k-1) (cpp/state.cpp:382-413, :460-466) for one state.
-SGS_D void dp_move_one(const DpTerms &H, int m, int s, const DpState &st, const double *inE, int tstride,
-                       const DpGroup *level, DpMoved &mv, double *E, double *tE, DpBack *B, DpBack *tB, DpHistAdd *hist, int *err)
+// State::move_to_next + project_to(k-1) (cpp/state.cpp:382-413, :460-466) for one state, by one warp.
+SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const double *inE, int tstride,
+                        const DpGroup *level, DpMoved &mv, double *E, double *tE, DpBack *B, DpBack *tB, DpHistAdd *hist, int *err, int lane)
 {
     const int k = H.k, o = m - k + 1;
     uint64_t g[kDpRows + 1];
@@ -237,10 +244,14 @@ SGS_D void dp_move_one(const DpTerms &H, int m, int s, const DpState &st, const 
     for (int i = 0; i < r; i++) g[i] = st.g[i];
     uint64_t valid[kDpVW];
     for (int i = 0; i < kDpVW; i++) valid[i] = st.valid[i];
-    for (int e = 0; e < (1 << r); e++) { E[e] = inE[(size_t)s * tstride + e]; B[e].state = s; B[e].entry = (uint16_t)e; B[e].signs = 0; }
+    for (int e = lane; e < (1 << r); e += 32) {
+        E[e] = inE[(size_t)s * tstride + e];
+        DpBack b; b.state = s; b.entry = (uint16_t)e; b.signs = 0;
+        B[e] = b;
+    }
+    __syncwarp();
     const DpGroup &sr = level[st.sright];
-    mv.sright = st.sright; mv.dead = 0; mv.nadd = 0; mv.r = 0;
-    if (hist) hist->nadd = 0;
+    if (lane == 0) { mv.sright = st.sright; mv.dead = 0; mv.nadd = 0; mv.r = 0; hist->nadd = 0; }
 
     // stab_tmp = <stab, Sright> (cpp/state.cpp:384-390), bits only
     Ech tmp; tmp.n = 0;
@@ -251,49 +262,54 @@ SGS_D void dp_move_one(const DpTerms &H, int m, int s, const DpState &st, const 
     for (int pos = b0; pos < b1; pos++) {
         const uint64_t P = rel_row(H.rows + (size_t)pos * H.W, H.W, o);
         if (ech_reduce(tmp, P) != 0) continue;
-        if (!in_rref(sr.g, sr.r, P)) { mv.dead = 1; return; }          // cpp/state.cpp:397-399
+        if (!in_rref(sr.g, sr.r, P)) { if (lane == 0) mv.dead = 1; return; }          // cpp/state.cpp:397-399
         if (in_rref(g, r, P)) continue;
-        if (r + 1 > kDpTab || r + 1 > kDpRows || nadd >= kDpMaxAdd) { atomicMax(err, 1); mv.dead = 1; return; }
-        group_add(g, r, P, E, B, tE, tB, nadd);                        // State::add, cpp/state.cpp:367-380
-        if (hist) hist->added[nadd] = (uint16_t)pos;
+        if (r + 1 > kDpTab || r + 1 > kDpRows || nadd >= kDpMaxAdd) { if (lane == 0) { atomicMax(err, 1); mv.dead = 1; } return; }
+        group_add(g, r, P, E, B, tE, tB, nadd, lane);                  // State::add, cpp/state.cpp:367-380
+        if (lane == 0) hist->added[nadd] = (uint16_t)pos;
         nadd++;
-        const int qhi = min(m + k, H.n);
-        for (int t = b0; t < H.boff[qhi]; t++) {
-            if (!vget(valid, t - b0)) continue;
-            const uint64_t Q = rel_row(H.rows + (size_t)t * H.W, H.W, o);
-            bool com = true;
-            for (int i = 0; i < r; i++) com &= !anti(g[i], Q);
-            if (!com) vclr(valid, t - b0);
+        // terms that stopped commuting with the group leave the valid set: lanes stride over the terms
+        const int nt = H.boff[min(m + k, H.n)] - b0;
+        for (int base = 0; base < nt; base += 32) {
+            const int t = base + lane;
+            bool kill = false;
+            if (t < nt && vget(valid, t)) {
+                const uint64_t Q = rel_row(H.rows + (size_t)(b0 + t) * H.W, H.W, o);
+                for (int i = 0; i < r; i++) kill |= anti(g[i], Q);
+            }
+            const unsigned km = __ballot_sync(0xffffffffu, kill);
+            valid[base >> 6] &= ~((uint64_t)km << (base & 63));
         }
     }
-    mv.nadd = nadd;
-    if (hist) hist->nadd = nadd;
+    if (lane == 0) { mv.nadd = nadd; hist->nadd = nadd; }
     for (int pos = b0; pos < b1; pos++) {                               // cpp/state.cpp:405-410
         const uint64_t P = rel_row(H.rows + (size_t)pos * H.W, H.W, o);
-        if (in_rref(g, r, P)) group_add_energy(g, r, P, H.w[pos], E);
+        if (in_rref(g, r, P)) group_add_energy(g, r, P, H.w[pos], E, lane);
     }
-    group_project_site0(g, r, E, B);                                    // project_to(k-1), cpp/stab.cpp:803-809 (site o_m; no-op while o_m < 0)
-    for (int i = 0; i < r; i++) mv.g[i] = g[i] >> 2;                    // origin o_{m+1}
-    for (int i = r; i < kDpRows; i++) mv.g[i] = 0;
-    mv.r = r;
+    group_project_site0(g, r, E, B, lane);                              // project_to(k-1), cpp/stab.cpp:803-809 (site o_m; no-op while o_m < 0)
     // valid bits relative to boff[m+1]; bucket m+k+1 (never filtered so far) enters as all-valid
     vshift_right(valid, b1 - b0);
     const int lo = H.boff[min(m + k + 1, H.n + 1)] - b1, hi = H.boff[min(m + k + 2, H.n + 1)] - b1;
-    if (hi > 64 * kDpVW) { atomicMax(err, 2); mv.dead = 1; return; }
+    if (hi > 64 * kDpVW) { if (lane == 0) { atomicMax(err, 2); mv.dead = 1; } return; }
     vset_range(valid, lo, hi);
-    for (int i = 0; i < kDpVW; i++) mv.valid[i] = valid[i];
+    if (lane == 0) {
+        for (int i = 0; i < r; i++) mv.g[i] = g[i] >> 2;                // origin o_{m+1}
+        for (int i = r; i < kDpRows; i++) mv.g[i] = 0;
+        mv.r = r;
+        for (int i = 0; i < kDpVW; i++) mv.valid[i] = valid[i];
+    }
 }
 
 // span of the valid terms with last site in [m+1, min(m+k+1, n)) truncated to [max(m-k+2,0), m+2):
 // State::check_Sright_validity (cpp/state.cpp:347-365)
-SGS_D void dp_valid_span(const DpTerms &H, int m, const DpMoved &mv, Ech &e)
+SGS_D void dp_valid_span(const DpTerms &H, int m, const uint64_t *valid, Ech &e)
 {
     const int k = H.k, o1 = m - k + 2;                     // origin of level m+1
     const uint64_t wmask = (2 * k >= 64) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
     e.n = 0;
     const int b1 = H.boff[m + 1], t1 = H.boff[min(m + k + 1, H.n)];
     for (int t = b1; t < t1; t++) {
-        if (!vget(mv.valid, t - b1)) continue;
+        if (!vget(valid, t - b1)) continue;
         ech_add(e, rel_row(H.rows + (size_t)t * H.W, H.W, o1) & wmask);
     }
 }
@@ -563,6 +579,7 @@ struct DpBufs {
     double *slabE;
     DpBack *slabB;
     DpMoved *moved;
+    Ech *span;                   // per moved state: span of its valid terms (check_Sright_validity)
     int *nacc, *off;
     DpKey *keys;
     int *parent;
@@ -598,21 +615,25 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
         DpState *outS = B.S[cur ^ 1];
         double *outE = B.E[cur ^ 1];
         if ((long long)hm_off + nin > hm_cap || step >= log_cap) { err = 7; break; }
-        // ---- P0
+        // ---- P0: one warp per state
         if (tid == 0) ctl->nuniq = 0;
-        for (int s = tid; s < nin; s += nth) {
+        for (int s = wid; s < nin; s += nw) {
             double *E = B.slabE + (size_t)s * 2 * slab_stride;
             DpBack *Bk = B.slabB + (size_t)s * 2 * slab_stride;
-            dp_move_one(H, m, s, inS[s], inE, tstride, L.groups, B.moved[s], E, E + slab_stride, Bk, Bk + slab_stride, B.hm + hm_off + s,
-                        &ctl->err);
+            DpMoved &mv = B.moved[s];
+            dp_move_warp(H, m, s, inS[s], inE, tstride, L.groups, mv, E, E + slab_stride, Bk, Bk + slab_stride, B.hm + hm_off + s,
+                         &ctl->err, lane);
+            __syncwarp();
             int cnt = 0;
-            if (!B.moved[s].dead) {
+            if (!mv.dead) {
                 Ech e;
-                dp_valid_span(H, m, B.moved[s], e);
-                const int sr = B.moved[s].sright;
-                for (int j = L.map_off[sr]; j < L.map_off[sr + 1]; j++) cnt += dp_accepts(e, Ln.groups[L.map_idx[j]]);
+                dp_valid_span(H, m, mv.valid, e);
+                if (lane == 0) B.span[s] = e;
+                const int j0 = L.map_off[mv.sright], j1 = L.map_off[mv.sright + 1];
+                for (int j = j0 + lane; j < j1; j += 32) cnt += dp_accepts(e, Ln.groups[L.map_idx[j]]);
+                for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
             }
-            B.nacc[s] = cnt;
+            if (lane == 0) B.nacc[s] = cnt;
         }
         grid.sync();
         SGS_PROF(ctl, 0);
@@ -634,22 +655,30 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
         {
             const int lo = H.boff[min(m1 + 1, H.n + 1)] - H.boff[m1];
             const int hi = H.boff[min(max(m1 + k - 1, m1 + 1), H.n)] - H.boff[m1];
-            for (int s = tid; s < nin; s += nth) {
+            for (int s = wid; s < nin; s += nw) {
                 const DpMoved &mv = B.moved[s];
                 if (mv.dead) continue;
-                Ech e;
-                dp_valid_span(H, m, mv, e);
+                const Ech &e = B.span[s];
+                uint64_t kv[kDpVW];
+                for (int i = 0; i < kDpVW; i++) kv[i] = 0;
+                for (int b = lo; b < hi; b++) if (vget(mv.valid, b)) kv[b >> 6] |= 1ULL << (b & 63);
                 int c = B.off[s];
-                for (int j = L.map_off[mv.sright]; j < L.map_off[mv.sright + 1]; j++) {
-                    if (!dp_accepts(e, Ln.groups[L.map_idx[j]])) continue;
-                    DpKey &K = B.keys[c];
-                    for (int i = 0; i < kDpRows; i++) K.g[i] = mv.g[i];
-                    for (int i = 0; i < kDpVW; i++) K.v[i] = 0;
-                    for (int b = lo; b < hi; b++) if (vget(mv.valid, b)) K.v[b >> 6] |= 1ULL << (b & 63);
-                    K.r = mv.r;
-                    K.sright = L.map_idx[j];
-                    B.parent[c] = s;
-                    c++;
+                const int j0 = L.map_off[mv.sright], j1 = L.map_off[mv.sright + 1];
+                for (int base = j0; base < j1; base += 32) {          // children in (parent, map) order
+                    const int j = base + lane;
+                    const int nx = j < j1 ? L.map_idx[j] : 0;
+                    const bool acc = j < j1 && dp_accepts(e, Ln.groups[nx]);
+                    const unsigned am = __ballot_sync(0xffffffffu, acc);
+                    if (acc) {
+                        const int cc = c + __popc(am & ((1u << lane) - 1u));
+                        DpKey &K = B.keys[cc];
+                        for (int i = 0; i < kDpRows; i++) K.g[i] = mv.g[i];
+                        for (int i = 0; i < kDpVW; i++) K.v[i] = kv[i];
+                        K.r = mv.r;
+                        K.sright = nx;
+                        B.parent[cc] = s;
+                    }
+                    c += __popc(am);
                 }
             }
         }

@@ -121,6 +121,7 @@ struct KlocalMachine::Impl {
     int m_ = 0, tstride = 1, slab_stride = 1;
     int caps = 0, capc = 0, hm_cap = 0, hb_cap = 0, log_cap = 1 << 14;
     int *d_trace = nullptr;
+    char *d_finish = nullptr;      // workspace of group_finish
     int trace_cap = 0;
     unsigned launches = 0;
     double dev_seconds = 0.0;
@@ -203,7 +204,7 @@ Status KlocalMachine::Impl::init()
     const int srcap = (int)std::min<long long>(65536ll * scale, 1ll << 24);
     const size_t srpool = ((size_t)64 << 20) * (size_t)std::min(scale, 64);
     {   // one cached arena for the tables, the DP batch buffers, the right-environment scratch and the level tables
-        const size_t dpb = (size_t)caps * (2 * sizeof(DpState) + sizeof(DpMoved) + 16) + (size_t)caps * tstride * 16 +
+        const size_t dpb = (size_t)caps * (2 * sizeof(DpState) + sizeof(DpMoved) + sizeof(Ech) + 16) + (size_t)caps * tstride * 16 +
                            (size_t)caps * 2 * slab_stride * 16 + (size_t)capc * (sizeof(DpKey) + 48 + 2 * sizeof(DdSlot)) +
                            (size_t)hm_cap * sizeof(DpHistAdd) + (size_t)hb_cap * sizeof(DpBack);
         const size_t srb = (size_t)srcap * (2 * sizeof(SrBranch) + 2 * sizeof(DpGroup) + 64 + 2 * sizeof(DdSlot)) + srpool;
@@ -272,13 +273,14 @@ Status KlocalMachine::Impl::alloc_dp()
 {
     for (int i = 0; i < 2; i++) { SGS_TRY(take(&dp.S[i], caps)); SGS_TRY(take(&dp.E[i], (size_t)caps * tstride)); }
     SGS_TRY(take(&dp.slabE, (size_t)caps * 2 * slab_stride)); SGS_TRY(take(&dp.slabB, (size_t)caps * 2 * slab_stride));
-    SGS_TRY(take(&dp.moved, caps)); SGS_TRY(take(&dp.nacc, (size_t)caps + 1)); SGS_TRY(take(&dp.off, (size_t)caps + 1));
+    SGS_TRY(take(&dp.moved, caps)); SGS_TRY(take(&dp.span, caps)); SGS_TRY(take(&dp.nacc, (size_t)caps + 1)); SGS_TRY(take(&dp.off, (size_t)caps + 1));
     SGS_TRY(take(&dp.keys, capc)); SGS_TRY(take(&dp.parent, capc));
     SGS_TRY(alloc_view(*this, dp.D, capc, st));
     SGS_TRY(take(&dp.hm, hm_cap)); SGS_TRY(take(&dp.hb, hb_cap));
     SGS_TRY(take(&dp.ctl, 1)); SGS_TRY(take(&dp.log, log_cap));
     trace_cap = T + 16;
     SGS_TRY(take(&d_trace, 2 * (size_t)trace_cap + 8));
+    SGS_TRY(take(&d_finish, group_finish_ws_bytes(T)));
     dp.levels = d_levels;
     dp.tstride = tstride; dp.slab_stride = slab_stride;
     hctl = DpCtl{};
@@ -518,12 +520,10 @@ Status KlocalMachine::Impl::ground_state(sgs_result *out)
         signs[i] = (int8_t)hist[i].second;
     }
     int rankc = 0;
-    s = group_canonicalize(device, n, mg, rows.data(), signs.data(), &rankc);     // K1 on the device
-    if (!s.ok()) return s;
     std::vector<uint64_t> P((size_t)std::max(T, 1) * Wout, 0);
     for (int t = 0; t < T; t++) for (int w = 0; w < Wout; w++) P[(size_t)t * Wout + w] = H.terms[t].w[w];
     std::vector<int8_t> ts(std::max(T, 1), 0);
-    s = group_energy(device, n, rankc, rows.data(), signs.data(), T, P.data(), nullptr, ts.data());   // K2
+    s = group_finish(st, d_finish, n, mg, rows.data(), signs.data(), &rankc, T, P.data(), ts.data());   // K1 + K2 on the device
     if (!s.ok()) return s;
     if (getenv("SGS_DP_TRACE"))
         fprintf(stderr, "  ground state: traceback %.3f ms, canonicalise + term signs %.3f ms\n", std::chrono::duration<double>(tg1 - tg0).count() * 1e3,
