@@ -341,7 +341,7 @@ SGS_D int key_cmp(const DpGroup &a, const DpGroup &b)
 // include/exclude branching over the terms whose last site is m, widen one site to the left, project onto
 // the k sites ending at m (Stab::project, cpp/stab.cpp:524-577).  Children are written to out[parent *
 // maxbranch + b] relative to origin o_m.
-struct SrBranch { uint64_t g[kDpRows]; int q[kDpRows]; int r; uint32_t excl; };
+struct SrBranch { uint64_t g[kDpRows]; int q[kDpRows]; int r; uint32_t excl; int par; };
 
 SGS_D void signed_add(uint64_t *g, int *q, int &r, uint64_t P, int qP)     // Stab::add: RREF with signs
 {
@@ -357,76 +357,61 @@ SGS_D void signed_add(uint64_t *g, int *q, int &r, uint64_t P, int qP)     // St
     r++;
 }
 
-SGS_D void sr_evolve_one(const DpTerms &H, int m, const DpGroup *next, int p, int maxbranch, DpGroup *out, int *nout,
-                         SrBranch *scratch, int *err)
+// evolve_stab (cpp/state.cpp:147-185) as breadth-first waves over ALL branches of a level at once, one
+// thread per branch.  Everything is done at the child origin o_m = o_{m+1} - 1.
+// wave 0: the groups of level m+1 become the initial branches
+SGS_D void sr_seed(const DpGroup &G, int p, SrBranch &b)
 {
-    const int k = H.k, o = m - k + 1;                       // everything is done at the child origin o_m = o_{m+1} - 1
-    SrBranch *br = scratch + (size_t)p * 2 * maxbranch, *nb = br + maxbranch;
-    int nbr = 1;
-    br[0].r = next[p].r; br[0].excl = 0;
-    for (int i = 0; i < next[p].r; i++) {
-        br[0].g[i] = next[p].g[i] << 2;
-        br[0].q[i] = (q_plus(next[p].g[i]) + (next[p].neg[i] ? 2 : 0)) & 3;
+    b.r = G.r; b.excl = 0; b.par = p;
+    for (int i = 0; i < G.r; i++) {
+        b.g[i] = G.g[i] << 2;
+        b.q[i] = (q_plus(G.g[i]) + (G.neg[i] ? 2 : 0)) & 3;
     }
-    const int b0 = H.boff[m], b1 = H.boff[m + 1];
-    if (b1 - b0 > 30) { atomicMax(err, 3); nout[p] = 0; return; }
-    for (int pos = b0; pos < b1; pos++) {
-        const uint64_t P = rel_row(H.rows + (size_t)pos * H.W, H.W, o);
-        int nn = 0;
-        for (int b = 0; b < nbr; b++) {
-            SrBranch &Bc = br[b];
-            bool com = true;
-            for (int i = 0; i < Bc.r; i++) com &= !anti(Bc.g[i], P);
-            if (com && !in_rref(Bc.g, Bc.r, P)) {
-                if (nn + 2 > maxbranch) { atomicMax(err, 4); nout[p] = 0; return; }
-                SrBranch inc = Bc;                                      // branch_include (cpp/state.cpp:129-138)
-                signed_add(inc.g, inc.q, inc.r, P, q_plus(P));
-                bool ok = inc.r <= kDpRows;
-                for (int t = b0; t < pos && ok; t++)
-                    if ((Bc.excl >> (t - b0)) & 1)
-                        ok = !in_rref(inc.g, inc.r, rel_row(H.rows + (size_t)t * H.W, H.W, o));
-                if (ok) nb[nn++] = inc;
-                Bc.excl |= 1u << (pos - b0);                            // branch_exclude (:140-145)
-                nb[nn++] = Bc;
-            } else {
-                if (nn + 1 > maxbranch) { atomicMax(err, 4); nout[p] = 0; return; }
-                nb[nn++] = Bc;
-            }
-        }
-        SrBranch *t = br; br = nb; nb = t;
-        nbr = nn;
-    }
-    // widen to [max(o,0), m+2), project onto [max(o,0), m+1): keep the subgroup with no support on site m+1
-    // (relative to o_m site m+1 is position k).
-    const int outpos = k;
-    for (int b = 0; b < nbr; b++) {
-        SrBranch &Bc = br[b];
-        // eliminate on the two columns of the outside site, keep rows that are clear there
-        uint64_t g[kDpRows]; int q[kDpRows]; int r = Bc.r;
-        for (int i = 0; i < r; i++) { g[i] = Bc.g[i]; q[i] = Bc.q[i]; }
-        int used = 0;
-        for (int bit = 2 * outpos; bit < 2 * outpos + 2; bit++) {
-            int pr = -1;
-            for (int i = used; i < r; i++) if ((g[i] >> bit) & 1) { pr = i; break; }
-            if (pr < 0) continue;
-            uint64_t tg = g[pr]; g[pr] = g[used]; g[used] = tg;
-            int tq = q[pr]; q[pr] = q[used]; q[used] = tq;
-            for (int i = 0; i < r; i++) if (i != used && ((g[i] >> bit) & 1)) mul1(g[i], q[i], g[used], q[used]);
-            used++;
-        }
-        DpGroup &G = out[(size_t)p * maxbranch + b];
-        uint64_t cg[kDpRows]; int cq[kDpRows]; int cr = 0;
-        for (int i = used; i < r; i++) signed_add(cg, cq, cr, g[i], q[i]);   // canonicalise the subgroup
-        G.r = cr;
-        for (int i = 0; i < kDpRows; i++) { G.g[i] = 0; G.neg[i] = 0; }
-        for (int i = 0; i < cr; i++) {
-            G.neg[i] = q_sign(cg[i], cq[i]) < 0;
-            G.g[i] = cg[i];
-        }
-    }
-    nout[p] = nbr;
 }
-
+// one term (position pos, bit `tbit` of the exclusion mask): branch_include / branch_exclude
+// (cpp/state.cpp:129-145).  Returns the number of branches written to out[0..2).
+SGS_D int sr_branch(const DpTerms &H, int o, int b0, int pos, const SrBranch &Bc, SrBranch *out)
+{
+    const uint64_t P = rel_row(H.rows + (size_t)pos * H.W, H.W, o);
+    bool com = true;
+    for (int i = 0; i < Bc.r; i++) com &= !anti(Bc.g[i], P);
+    if (!com || in_rref(Bc.g, Bc.r, P)) { out[0] = Bc; return 1; }
+    int nn = 0;
+    SrBranch inc = Bc;
+    signed_add(inc.g, inc.q, inc.r, P, q_plus(P));
+    bool ok = inc.r <= kDpRows;
+    for (int t = b0; t < pos && ok; t++)
+        if ((Bc.excl >> (t - b0)) & 1) ok = !in_rref(inc.g, inc.r, rel_row(H.rows + (size_t)t * H.W, H.W, o));
+    if (ok) out[nn++] = inc;
+    out[nn] = Bc;
+    out[nn].excl |= 1u << (pos - b0);
+    return nn + 1;
+}
+// last wave: widen to [max(o,0), m+2), project onto [max(o,0), m+1) — keep the subgroup with no support on
+// site m+1 (position k relative to o_m): Stab::project (cpp/stab.cpp:524-577), canonical with signs
+SGS_D void sr_project(const SrBranch &Bc, int k, DpGroup &G)
+{
+    uint64_t g[kDpRows]; int q[kDpRows]; int r = Bc.r;
+    for (int i = 0; i < r; i++) { g[i] = Bc.g[i]; q[i] = Bc.q[i]; }
+    int used = 0;
+    for (int bit = 2 * k; bit < 2 * k + 2; bit++) {
+        int pr = -1;
+        for (int i = used; i < r; i++) if ((g[i] >> bit) & 1) { pr = i; break; }
+        if (pr < 0) continue;
+        uint64_t tg = g[pr]; g[pr] = g[used]; g[used] = tg;
+        int tq = q[pr]; q[pr] = q[used]; q[used] = tq;
+        for (int i = 0; i < r; i++) if (i != used && ((g[i] >> bit) & 1)) mul1(g[i], q[i], g[used], q[used]);
+        used++;
+    }
+    uint64_t cg[kDpRows]; int cq[kDpRows]; int cr = 0;
+    for (int i = used; i < r; i++) signed_add(cg, cq, cr, g[i], q[i]);   // canonicalise the subgroup
+    G.r = cr;
+    for (int i = 0; i < kDpRows; i++) { G.g[i] = 0; G.neg[i] = 0; }
+    for (int i = 0; i < cr; i++) {
+        G.neg[i] = q_sign(cg[i], cq[i]) < 0;
+        G.g[i] = cg[i];
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Keyed de-duplication shared by the DP merge (keys = DpKey) and the right-environment levels (keys =
@@ -503,14 +488,33 @@ SGS_D void dd_insert(const DdView &D, unsigned gen, const K *keys, int c)
             cur = prev;
         }
         if (mine) break;
-        const int j = (int)(unsigned)cur;
-        if (key_cmp(keys[j], keys[c]) == 0) break;
+        if (key_cmp(keys[(int)(unsigned)cur], keys[c]) == 0) break;
         i = (i + 1) & D.mask;
     }
     D.owner[c] = (int)i;
     atomicMin(&D.tab[i].lead, tagv | (unsigned)c);
     const unsigned long long old = atomicExch(&D.tab[i].head, tagv | (unsigned)c);
     D.next[c] = ((old >> 32) == tw) ? (int)(unsigned)old : -1;
+}
+
+// set of integer pairs on the same table (a fresh generation): true for exactly one entry per distinct
+// (a[c], b[c]); which one is not significant
+SGS_D bool dd_pair_first(const DdView &D, unsigned gen, const int *a, const int *b, int c)
+{
+    const unsigned long long tw = 0xFFFFFFFFu - gen, tagv = tw << 32;
+    const uint64_t h = mix64(((uint64_t)(uint32_t)a[c] << 32) | (uint32_t)b[c], 0xABCDEFULL);
+    unsigned i = (unsigned)(h ^ (h >> 32)) & D.mask;
+    for (;;) {
+        unsigned long long cur = *(volatile unsigned long long *)&D.tab[i].claim;
+        while ((cur >> 32) != tw) {
+            const unsigned long long prev = atomicCAS(&D.tab[i].claim, cur, tagv | (unsigned)c);
+            if (prev == cur) return true;
+            cur = prev;
+        }
+        const int j = (int)(unsigned)cur;
+        if (a[j] == a[c] && b[j] == b[c]) return false;
+        i = (i + 1) & D.mask;
+    }
 }
 
 // leader of every entry; leaders are compacted (order irrelevant) for the all-pairs ranking
@@ -769,15 +773,15 @@ __global__ void k_dp_trace(const DpCtl *ctl, const DpStepLog *log, const DpHistA
 // (cpp/state.cpp:187-216) as keyed de-duplication + key order, level tables bump-allocated on the device.
 // The list of compatible next groups of a group is a set (py/state.py:523); its order is not significant.
 struct SrCtl {
-    int err, err_snap, total, nuniq, nlinks, done_m;
+    int err, err_snap, nuniq, done_m;
+    int nbr[3];                  // rotating branch counters of the waves
     unsigned gen;
     unsigned long long pool_used, pool_cap;
     unsigned long long prof[10];  // ns spent per phase (thread 0's view), for SGS_DP_TRACE
 };
 struct SrBufs {
-    SrBranch *scratch;           // [2 * cap]
-    DpGroup *strided, *flat;     // [cap]
-    int *nout, *offp;            // per parent
+    SrBranch *br[2];             // [cap] branch lists (ping-pong)
+    DpGroup *flat;               // [cap] projected children
     int *par, *cnt, *moff;       // per child / per group
     uint8_t *first;
     DdView D;
@@ -805,47 +809,52 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
     SrCtl *ctl = B.ctl;
     unsigned gen = ctl->gen;
     int err = ctl->err;
+    const int k = H.k;
     grid.sync();
     unsigned long long tprof = gtime();
     int m = m_hi - 1;
     for (; m >= m_lo && !err; m--) {
         const DpLevelDev Ln = B.levels[m + 1];
-        const int nnext = Ln.count;
-        const int nterm = H.boff[m + 1] - H.boff[m];
-        if (nterm > 16) { err = 3; break; }
-        const int maxbranch = 1 << nterm;
-        if ((long long)nnext * maxbranch > B.cap) { err = 4; break; }
-        // ---- S0: children of every parent group
-        if (tid == 0) ctl->nuniq = 0;
-        for (int p = tid; p < nnext; p += nth) sr_evolve_one(H, m, Ln.groups, p, maxbranch, B.strided, B.nout, B.scratch, &ctl->err);
+        const int o = m - k + 1, b0 = H.boff[m], b1 = H.boff[m + 1];
+        if (b1 - b0 > 30) { err = 3; break; }
+        if (Ln.count > B.cap) { err = 4; break; }
+        // ---- waves: seed, then one wave per term whose last site is m (branch order is not significant)
+        int nbr = Ln.count, cur = 0, w = 0;
+        for (int p = tid; p < nbr; p += nth) sr_seed(Ln.groups[p], p, B.br[0][p]);
+        if (tid == 0) { ctl->nbr[0] = 0; ctl->nbr[1] = 0; ctl->nuniq = 0; }
         grid.sync();
-        SGS_PROF(ctl, 0);
-        // ---- S1: offsets of the children in parent order
-        if (blockIdx.x == 0) {
-            const int tot = block_scan(B.nout, B.offp, nnext, part);
-            if (threadIdx.x == 0) { ctl->total = tot; ctl->err_snap = ctl->err; }
+        for (int pos = b0; pos < b1; pos++, w++) {
+            int *counter = &ctl->nbr[w % 3];
+            if (tid == 0) ctl->nbr[(w + 1) % 3] = 0;        // next wave's counter; last read two barriers ago
+            const SrBranch *in = B.br[cur];
+            SrBranch *out = B.br[cur ^ 1];
+            for (int b = tid; b < nbr; b += nth) {
+                SrBranch tmp[2];
+                const int nn = sr_branch(H, o, b0, pos, in[b], tmp);
+                const int at = atomicAdd(counter, nn);
+                if (at + nn <= B.cap) for (int i = 0; i < nn; i++) out[at + i] = tmp[i];
+            }
+            grid.sync();
+            nbr = *counter;
+            if (nbr > B.cap) break;                          // uniform
+            cur ^= 1;
         }
+        SGS_PROF(ctl, 0);
+        if (nbr > B.cap) { err = 4; break; }
+        const int total = nbr;
+        // ---- projection of every branch = the children, with their parent
+        for (int c = tid; c < total; c += nth) { sr_project(B.br[cur][c], k, B.flat[c]); B.par[c] = B.br[cur][c].par; }
         grid.sync();
         SGS_PROF(ctl, 1);
-        const int total = ctl->total;
-        err = ctl->err_snap;
-        if (err) break;
-        // ---- S2: compact
-        for (int p = tid; p < nnext; p += nth) {
-            const int o = B.offp[p], c = B.offp[p + 1] - o;
-            for (int j = 0; j < c; j++) { B.flat[o + j] = B.strided[(size_t)p * maxbranch + j]; B.par[o + j] = p; }
-        }
-        grid.sync();
-        SGS_PROF(ctl, 2);
-        // ---- S3 / S4: distinct groups
+        // ---- distinct groups
         for (int c = tid; c < total; c += nth) dd_insert(B.D, gen, B.flat, c);
         grid.sync();
-        SGS_PROF(ctl, 3);
+        SGS_PROF(ctl, 2);
         for (int c = tid; c < total; c += nth) dd_lead(B.D, c, &ctl->nuniq);
         grid.sync();
-        SGS_PROF(ctl, 4);
+        SGS_PROF(ctl, 3);
         const int nuniq = ctl->nuniq;
-        // ---- S5: key order; level storage; clear the per-group counters
+        // ---- key order; level storage; clear the per-group counters
         for (int p = wid; p < nuniq; p += nw) dd_rank_warp(B.D, B.flat, p, nuniq, lane);
         for (int g = tid; g <= nuniq; g += nth) B.cnt[g] = 0;
         if (tid == 0) {
@@ -856,24 +865,23 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
             ctl->err_snap = ctl->err;
         }
         grid.sync();
-        SGS_PROF(ctl, 5);
+        SGS_PROF(ctl, 4);
         err = ctl->err_snap;
         if (err) break;
-        // ---- S6: groups in key order; a (group, parent) link is counted once (first child of that parent in the group)
+        // ---- groups in key order; a (group, parent) link is counted once
         {
             DpGroup *groups = const_cast<DpGroup *>(B.levels[m].groups);
             for (int c = tid; c < total; c += nth) {
                 const int ld = B.D.leader[c], g = B.D.rank[ld];
                 if (ld == c) groups[g] = B.flat[c];
-                bool first = true;
-                for (int j = B.offp[B.par[c]]; j < c; j++) if (B.D.leader[j] == ld) { first = false; break; }
+                const bool first = dd_pair_first(B.D, gen + 1, B.D.leader, B.par, c);
                 B.first[c] = first;
                 if (first) atomicAdd(&B.cnt[g], 1);
             }
         }
         grid.sync();
-        SGS_PROF(ctl, 6);
-        // ---- S7: link offsets
+        SGS_PROF(ctl, 5);
+        // ---- link offsets
         if (blockIdx.x == 0) {
             const int nl = block_scan(B.cnt, B.moff, nuniq, part);
             int *map_off = const_cast<int *>(B.levels[m].map_off);
@@ -886,18 +894,18 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
             }
         }
         grid.sync();
-        SGS_PROF(ctl, 7);
+        SGS_PROF(ctl, 6);
         err = ctl->err_snap;
         if (err) break;
-        // ---- S8: fill the links (cnt[g] is now the group's write cursor)
+        // ---- fill the links (cnt[g] is now the group's write cursor)
         {
             int *map_idx = const_cast<int *>(B.levels[m].map_idx);
             for (int c = tid; c < total; c += nth)
                 if (B.first[c]) map_idx[atomicAdd(&B.cnt[B.D.rank[B.D.leader[c]]], 1)] = B.par[c];
         }
-        SGS_PROF(ctl, 8);
-        gen++;
-        // no barrier: the next level's S0/S1 touch none of S8's inputs and two barriers precede the first overwrite
+        grid.sync();
+        SGS_PROF(ctl, 7);
+        gen += 2;
     }
     grid.sync();
     if (tid == 0) {

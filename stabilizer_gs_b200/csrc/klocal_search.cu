@@ -254,9 +254,8 @@ static Status alloc_view(KlocalMachine::Impl &K, DdView &D, size_t entries, cuda
 Status KlocalMachine::Impl::alloc_sr(int cap, size_t pool_bytes)
 {
     sr.cap = cap;
-    SGS_TRY(take(&sr.scratch, 2 * (size_t)cap)); SGS_TRY(take(&sr.strided, cap)); SGS_TRY(take(&sr.flat, cap));
-    SGS_TRY(take(&sr.nout, (size_t)cap + 1)); SGS_TRY(take(&sr.offp, (size_t)cap + 1)); SGS_TRY(take(&sr.par, cap));
-    SGS_TRY(take(&sr.cnt, (size_t)cap + 1)); SGS_TRY(take(&sr.moff, (size_t)cap + 1)); SGS_TRY(take(&sr.first, cap));
+    SGS_TRY(take(&sr.br[0], cap)); SGS_TRY(take(&sr.br[1], cap)); SGS_TRY(take(&sr.flat, cap));
+    SGS_TRY(take(&sr.par, cap)); SGS_TRY(take(&sr.cnt, (size_t)cap + 1)); SGS_TRY(take(&sr.moff, (size_t)cap + 1)); SGS_TRY(take(&sr.first, cap));
     SGS_TRY(alloc_view(*this, sr.D, cap, st));
     SGS_TRY(take(&sr.ctl, 1));
     SGS_TRY(take(&sr.pool, pool_bytes));
@@ -618,10 +617,10 @@ Status klocal_search(const Hamiltonian &H, const sgs_opts &opts, sgs_result *out
         fprintf(stderr, "  DP phases (us): move+fanout %.0f, scan %.0f, emit %.0f, dedup %.0f, leaders %.0f, order %.0f, merge %.0f\n",
                 K.hctl.prof[0] * 1e-3, K.hctl.prof[1] * 1e-3, K.hctl.prof[2] * 1e-3, K.hctl.prof[3] * 1e-3, K.hctl.prof[4] * 1e-3,
                 K.hctl.prof[5] * 1e-3, K.hctl.prof[6] * 1e-3);
-        fprintf(stderr, "  right-environment phases (us): evolve %.0f, scan %.0f, compact %.0f, dedup %.0f, leaders %.0f, order %.0f, "
+        fprintf(stderr, "  right-environment phases (us): waves %.0f, project %.0f, dedup %.0f, leaders %.0f, order %.0f, "
                         "groups+links %.0f, offsets %.0f, fill %.0f\n",
                 K.hsr.prof[0] * 1e-3, K.hsr.prof[1] * 1e-3, K.hsr.prof[2] * 1e-3, K.hsr.prof[3] * 1e-3, K.hsr.prof[4] * 1e-3,
-                K.hsr.prof[5] * 1e-3, K.hsr.prof[6] * 1e-3, K.hsr.prof[7] * 1e-3, K.hsr.prof[8] * 1e-3);
+                K.hsr.prof[5] * 1e-3, K.hsr.prof[6] * 1e-3, K.hsr.prof[7] * 1e-3);
     }
     out->nsites = H.n;
     out->sright_counts = (int *)malloc(sizeof(int) * (H.n + 1));
