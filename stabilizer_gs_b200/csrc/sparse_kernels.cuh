@@ -581,27 +581,19 @@ template <int W>
 SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, int n, int nlow, int depth,
                    uint32_t *hc, double &bw, uint64_t &bm, int lane)
 {
-    // own rows: entries lane and lane + 32 (o = residue, s = its z/x-swapped copy for the symmetric
-    // commutation test popc(s_i & r_u), e = elimination copy)
+    // 1. independence of ALL n residues (lower-index entries included: a dependency through one of them would
+    //    make a later child non-canonical).  Own rows: entries lane and lane + 32; step u broadcasts the
+    //    (already reduced) copy of entry u and clears its lowest set bit from the later rows.
     const bool two = n > 32;
-    uint64_t s0[W], s1[W], e0[W], e1[W];
+    uint64_t e0[W], e1[W];
 #pragma unroll
     for (int k = 0; k < W; k++) {
         e0[k] = lane < n ? R[lane * W + k] : 0;
         e1[k] = lane + 32 < n ? R[(lane + 32) * W + k] : 0;
-        s0[k] = swapzx(e0[k]); s1[k] = swapzx(e1[k]);
     }
-    uint64_t adj0 = 0, adj1 = 0;
     bool dependent = false;
 #pragma unroll 1
     for (int u = 0; u < n; u++) {
-        uint64_t ru[W];
-#pragma unroll
-        for (int k = 0; k < W; k++) ru[k] = R[u * W + k];
-        // commutation row bits (the form is symmetric: popc(swap(a) & b) = popc(a & swap(b)))
-        adj0 |= (uint64_t)(row_anticommute_sw<W>(ru, s0) ^ 1) << u;
-        if (two) adj1 |= (uint64_t)(row_anticommute_sw<W>(ru, s1) ^ 1) << u;
-        // elimination step: pivot row = current (reduced) copy of entry u, pivot = its lowest set bit
         uint64_t cu[W], lm[W];
         bool nz = false;
 #pragma unroll
@@ -610,7 +602,7 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
             lm[k] = nz ? 0 : (cu[k] & (0 - cu[k]));
             nz |= cu[k] != 0;
         }
-        if (!nz) { dependent = true; continue; }
+        if (!nz) { dependent = true; break; }
         uint64_t h0 = 0, h1 = 0;
 #pragma unroll
         for (int k = 0; k < W; k++) { h0 |= e0[k] & lm[k]; h1 |= e1[k] & lm[k]; }
@@ -623,9 +615,27 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
             for (int k = 0; k < W; k++) e1[k] ^= cu[k];
         }
     }
-    const uint64_t vmask = n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL);
-    adj0 = lane < n ? (adj0 & vmask & ~(1ULL << lane)) : 0;
-    adj1 = lane + 32 < n ? (adj1 & vmask & ~(1ULL << (lane + 32))) : 0;
+    uint64_t adj0 = 0, adj1 = 0;
+    if (dependent) {
+        // commutation rows of all n entries (the form is symmetric: popc(swap(a) & b) = popc(a & swap(b)))
+        uint64_t s0[W], s1[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            s0[k] = lane < n ? swapzx(R[lane * W + k]) : 0;
+            s1[k] = lane + 32 < n ? swapzx(R[(lane + 32) * W + k]) : 0;
+        }
+#pragma unroll 1
+        for (int u = 0; u < n; u++) {
+            uint64_t ru[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) ru[k] = R[u * W + k];
+            adj0 |= (uint64_t)(row_anticommute_sw<W>(ru, s0) ^ 1) << u;
+            if (two) adj1 |= (uint64_t)(row_anticommute_sw<W>(ru, s1) ^ 1) << u;
+        }
+        const uint64_t vmask = n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL);
+        adj0 = lane < n ? (adj0 & vmask & ~(1ULL << lane)) : 0;
+        adj1 = lane + 32 < n ? (adj1 & vmask & ~(1ULL << (lane + 32))) : 0;
+    }
     if (dependent) {
         // Second elimination, now tracking which original residues are XORed into each row, to obtain the
         // dependencies themselves.  A dependent term can only ever appear below this frame if the support of
@@ -683,22 +693,45 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
             if (!__any_sync(0xffffffffu, bad)) return false;      // a commuting dependency: not certified
         }
     }
-    // candidates = list positions nlow..n-1; keep only higher-position neighbours (cliques grow upward)
+    // 2. commutation graph of the candidates only (list positions nlow..n-1; vertex = position - nlow): lane
+    //    owns vertices lane and lane + 32, keeps the higher-numbered neighbours (cliques grow upward)
     const int ncand = n - nlow;
-    const uint64_t up0 = adj0 & ~((2ULL << lane) - 1ULL);
-    const uint64_t up1 = lane == 31 ? 0ULL : (adj1 & ~((2ULL << (lane + 32)) - 1ULL));
+    const uint64_t *Rc = R + (size_t)nlow * W;
     if (ncand <= 32) {
-        // 32-bit masks relative to nlow
-        if (lane >= nlow && lane < n) AD32[lane - nlow] = (uint32_t)(up0 >> nlow);
-        if (lane + 32 >= nlow && lane + 32 < n) AD32[lane + 32 - nlow] = (uint32_t)(up1 >> nlow);
+        uint64_t sc[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) sc[k] = lane < ncand ? swapzx(Rc[lane * W + k]) : 0;
+        uint32_t a32 = 0;
+#pragma unroll 1
+        for (int u = 1; u < ncand; u++) {
+            uint64_t ru[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) ru[k] = Rc[u * W + k];
+            a32 |= (uint32_t)(row_anticommute_sw<W>(ru, sc) ^ 1) << u;
+        }
+        if (lane < ncand) AD32[lane] = a32 & ~((2u << lane) - 1u);
         __syncwarp();
         uint32_t bm32 = 0;
         lb_walk<uint32_t>(AD32, WA + nlow, ncand, depth, hc, bw, bm32, lane);
         bm = (uint64_t)bm32 << nlow;
     } else {
-        // 64-bit masks, vertices = positions - nlow
-        if (lane >= nlow && lane < n) AD[lane - nlow] = up0 >> nlow;
-        if (lane + 32 >= nlow && lane + 32 < n) AD[lane + 32 - nlow] = up1 >> nlow;
+        uint64_t sc0[W], sc1[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            sc0[k] = swapzx(Rc[lane * W + k]);
+            sc1[k] = lane + 32 < ncand ? swapzx(Rc[(lane + 32) * W + k]) : 0;
+        }
+        uint64_t a0 = 0, a1 = 0;
+#pragma unroll 1
+        for (int u = 1; u < ncand; u++) {
+            uint64_t ru[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) ru[k] = Rc[u * W + k];
+            a0 |= (uint64_t)(row_anticommute_sw<W>(ru, sc0) ^ 1) << u;
+            a1 |= (uint64_t)(row_anticommute_sw<W>(ru, sc1) ^ 1) << u;
+        }
+        AD[lane] = a0 & ~((2ULL << lane) - 1ULL);
+        if (lane + 32 < ncand) AD[lane + 32] = lane == 31 ? 0ULL : (a1 & ~((2ULL << (lane + 32)) - 1ULL));
         __syncwarp();
         uint64_t bmr = 0;
         lb_walk<uint64_t>(AD, WA + nlow, ncand, depth, hc, bw, bmr, lane);
