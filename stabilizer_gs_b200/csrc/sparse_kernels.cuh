@@ -536,34 +536,35 @@ SGS_D int popc_mask(uint32_t v) { return __popc(v); }
 SGS_D int popc_mask(uint64_t v) { return __popcll(v); }
 
 // lane-private walk over the cliques of the candidates (vertices 0..ncand-1 = list positions nlow..n-1,
-// ADm[v] = neighbours of v with a higher index): lane l starts the cliques whose lowest vertex is l and, with
-// more than 32 candidates, 63 - l (big subtrees are paired with small ones).  Counts candidates per rank in
-// hc[], keeps the heaviest clique (ties: lowest first vertex, then first found = lexicographic order).
+// ADm[v] = neighbours of v with a higher index).  Work is dealt by the SECOND vertex: lane l (and l + 32)
+// walks every clique {f, l, ...} over its lower neighbours f (dn = bitmask of them) — far better balanced
+// than dealing by the lowest vertex — plus the singleton {l}.  Counts candidates per rank in hc[], keeps the
+// heaviest maximal clique; within a lane the first found wins ties (= lexicographic order, a longer tuple
+// before its prefix); lanes are ordered afterwards by (first vertex, second vertex).
 template <typename M>
-SGS_D void lb_walk(const M *ADm, const double *WAc, int ncand, int depth, uint32_t *hc, double &bw, M &bm, int lane)
+SGS_D void lb_walk(const M *ADm, const double *WAc, int ncand, int depth, uint32_t *hc, double &bw, M &bm, M dn0, M dn1, int lane)
 {
     M cand[kMaxLB], cm[kMaxLB];
     double ws[kMaxLB];
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
-        const int f = pass == 0 ? lane : 63 - lane;
-        if (f >= ncand || (pass == 1 && f < 32)) continue;
-        const M c = ADm[f];
-        const double w = WAc[f];
+        const int l = pass == 0 ? lane : lane + 32;
+        if (l >= ncand) break;
+        M dn = pass == 0 ? dn0 : dn1;
+        const M upl = ADm[l];
+        const double wl = WAc[l];
         hc[depth + 1] += 1;
-        if (c == 0) {
-            if (w > bw) { bw = w; bm = (M)1 << f; }
-            continue;
-        }
+        hc[depth + 2] += popc_mask(dn);
+        // one flat loop: frame 0 deals the lower neighbours f (its children are upl & AD[f]), deeper frames are
+        // the usual "candidates & AD[v]" — the same instruction path for every lane whatever its depth
         int d = 0;
-        cand[0] = c; ws[0] = w; cm[0] = (M)1 << f;
-        hc[depth + 2] += popc_mask(c);
+        cand[0] = dn; ws[0] = wl; cm[0] = (M)1 << l;
         while (d >= 0) {
             const M cc = cand[d];
             if (cc == 0) { d--; continue; }
             const int v = ctz_mask(cc);
             cand[d] = cc & (cc - 1);
-            const M nc = cc & ADm[v];
+            const M nc = (d == 0 ? upl : cc) & ADm[v];
             const double nw = ws[d] + WAc[v];
             if (nc == 0) {
                 if (nw > bw) { bw = nw; bm = cm[d] | ((M)1 << v); }
@@ -574,6 +575,7 @@ SGS_D void lb_walk(const M *ADm, const double *WAc, int ncand, int depth, uint32
                 cand[d] = nc; ws[d] = nw;
             }
         }
+        if (upl == 0 && wl > bw) { bw = wl; bm = (M)1 << l; }      // the singleton comes after every {f, l, ...}
     }
 }
 
@@ -703,7 +705,7 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
         for (int k = 0; k < W; k++) sc[k] = lane < ncand ? swapzx(Rc[lane * W + k]) : 0;
         uint32_t a32 = 0;
 #pragma unroll 1
-        for (int u = 1; u < ncand; u++) {
+        for (int u = 0; u < ncand; u++) {
             uint64_t ru[W];
 #pragma unroll
             for (int k = 0; k < W; k++) ru[k] = Rc[u * W + k];
@@ -712,7 +714,7 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
         if (lane < ncand) AD32[lane] = a32 & ~((2u << lane) - 1u);
         __syncwarp();
         uint32_t bm32 = 0;
-        lb_walk<uint32_t>(AD32, WA + nlow, ncand, depth, hc, bw, bm32, lane);
+        lb_walk<uint32_t>(AD32, WA + nlow, ncand, depth, hc, bw, bm32, a32 & ((1u << lane) - 1u), 0u, lane);
         bm = (uint64_t)bm32 << nlow;
     } else {
         uint64_t sc0[W], sc1[W];
@@ -723,7 +725,7 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
         }
         uint64_t a0 = 0, a1 = 0;
 #pragma unroll 1
-        for (int u = 1; u < ncand; u++) {
+        for (int u = 0; u < ncand; u++) {
             uint64_t ru[W];
 #pragma unroll
             for (int k = 0; k < W; k++) ru[k] = Rc[u * W + k];
@@ -734,7 +736,7 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
         if (lane + 32 < ncand) AD[lane + 32] = lane == 31 ? 0ULL : (a1 & ~((2ULL << (lane + 32)) - 1ULL));
         __syncwarp();
         uint64_t bmr = 0;
-        lb_walk<uint64_t>(AD, WA + nlow, ncand, depth, hc, bw, bmr, lane);
+        lb_walk<uint64_t>(AD, WA + nlow, ncand, depth, hc, bw, bmr, a0 & ((1ULL << lane) - 1ULL), a1 & ((1ULL << (lane + 32)) - 1ULL), lane);
         bm = bmr << nlow;
     }
     __syncwarp();
@@ -797,9 +799,13 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         // does any lane's best clique reach the incumbent?
         const bool cand = bm != 0 && (Ef - bw) <= bestE;
         if (__any_sync(0xffffffffu, cand)) {
-            // warp argmax of (weight, then lowest first vertex)
+            // warp argmax of (weight, then lowest first vertex, then lowest second vertex; a singleton last)
             double w = bm ? bw : -1.0;
-            int key = bm ? ctz64(bm) : 64;
+            int key = 1 << 20;
+            if (bm) {
+                const uint64_t rest = bm & (bm - 1);
+                key = ctz64(bm) * 128 + (rest ? ctz64(rest) : 127);
+            }
             int src = lane;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
