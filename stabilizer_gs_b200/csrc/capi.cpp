@@ -1,4 +1,6 @@
 // capi.cpp — the extern "C" boundary declared in include/sgs.h.  No exception crosses it.
+#include <chrono>
+#include <cstdlib>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -155,10 +157,18 @@ void sgs_sparse_plan_free(sgs_sparse_plan *p) { delete p; }
 int sgs_sparse_search(const sgs_ham *h, const sgs_opts *opts, sgs_result *out)
 {
     sgs_sparse_plan *p = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = sgs_sparse_plan_create(h, opts, &p);
     if (rc != SGS_OK) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     rc = sgs_sparse_plan_run(p, out);
+    const auto t2 = std::chrono::steady_clock::now();
     sgs_sparse_plan_free(p);
+    if (getenv("SGS_TRACE"))
+        fprintf(stderr, "sgs_sparse_search: plan %.3f ms, run %.3f ms (device %.3f ms), free %.3f ms\n",
+                std::chrono::duration<double>(t1 - t0).count() * 1e3, std::chrono::duration<double>(t2 - t1).count() * 1e3,
+                rc == SGS_OK ? out->seconds_device * 1e3 : 0.0,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count() * 1e3);
     return rc;
 }
 

@@ -176,9 +176,7 @@ Status SparsePlan::Impl::init()
 Status SparsePlan::Impl::init_device(DevCtx &c)
 {
     SGS_CUDA_TRY(cudaSetDevice(c.device));
-    cudaDeviceProp prop{};
-    SGS_CUDA_TRY(cudaGetDeviceProperties(&prop, c.device));
-    c.sms = prop.multiProcessorCount;
+    SGS_CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, c.device));   // (cudaGetDeviceProperties costs milliseconds)
     SGS_CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     SGS_CUDA_TRY(cudaEventCreate(&c.ev0));
     SGS_CUDA_TRY(cudaEventCreate(&c.ev1));
