@@ -53,6 +53,7 @@ struct SparseStats {
     unsigned long long slow_nodes;        // candidates evaluated by k_general
     unsigned int error;                   // SGS_ERR_* (positive) set by a kernel
     unsigned int pad;
+    unsigned long long dbg[8];            // SGS_TRACE diagnostics of the walk (see k_dfs)
 };
 
 struct SparseDev {
@@ -66,10 +67,12 @@ struct SparseDev {
     uint16_t *slow;              // work stack of nodes needing k_general
     unsigned int *slow_count;
     unsigned int slow_cap;
+    int trace;                   // SGS_TRACE: per-root timing diagnostics into stats->dbg
 };
 
 enum { kErrOverflow = 8, kErrLimit = 6 };
 
+SGS_D unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 SGS_D uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
 // lexicographic order on generating tuples with "end of tuple" sorting last: the order in which the
@@ -469,6 +472,51 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
 }
 
 // ------------------------------------------------------------------------------------------------
+// Heavy-first order of the subtree roots.  The size of a root's subtree grows steeply with the number of
+// alive terms after its last generator, i.e. falls with the index of that generator; the expansion kernel
+// emits roots in atomic order.  A counting sort into kRootClasses classes of the last generator index gives
+// the walk a longest-first schedule (order inside a class is arbitrary: results do not depend on it).
+constexpr int kRootClasses = 8;
+SGS_D int root_class(const uint16_t *rec, int T) { const int m = rec[0]; return m ? (int)(((unsigned)rec[1 + m] * kRootClasses) / (unsigned)max(T, 1)) : 0; }
+
+__global__ void k_class_count(const uint16_t *__restrict__ items, unsigned n, const unsigned *n_dev, int S, int T, unsigned *cls)
+{
+    if (n_dev) n = *n_dev;
+    __shared__ unsigned loc[kRootClasses];
+    if (threadIdx.x < kRootClasses) loc[threadIdx.x] = 0;
+    __syncthreads();
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&loc[min(root_class(items + (size_t)i * S, T), kRootClasses - 1)], 1u);
+    __syncthreads();
+    if (threadIdx.x < kRootClasses && loc[threadIdx.x]) atomicAdd(&cls[threadIdx.x], loc[threadIdx.x]);
+}
+
+__global__ void k_class_scatter(const uint16_t *__restrict__ items, unsigned n, const unsigned *n_dev, int S, int T, const unsigned *cls,
+                                unsigned *cursor, unsigned *__restrict__ perm)
+{
+    if (n_dev) n = *n_dev;
+    __shared__ unsigned loc[kRootClasses], base[kRootClasses];
+    if (threadIdx.x < kRootClasses) loc[threadIdx.x] = 0;
+    __syncthreads();
+    // block-local counts first, one global atomic per class and block, then the scatter
+    const unsigned per = (n + gridDim.x - 1) / gridDim.x, lo = min(n, blockIdx.x * per), hi = min(n, lo + per);
+    for (unsigned i = lo + threadIdx.x; i < hi; i += blockDim.x)
+        atomicAdd(&loc[min(root_class(items + (size_t)i * S, T), kRootClasses - 1)], 1u);
+    __syncthreads();
+    if (threadIdx.x < kRootClasses) {
+        unsigned off = 0;
+        for (int c = 0; c < (int)threadIdx.x; c++) off += cls[c];
+        base[threadIdx.x] = off + (loc[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], loc[threadIdx.x]) : 0u);
+        loc[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (unsigned i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const int c = min(root_class(items + (size_t)i * S, T), kRootClasses - 1);
+        perm[base[c] + atomicAdd(&loc[c], 1u)] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_dfs: the hot kernel.
 template <int W>
 __host__ __device__ inline size_t dfs_smem_bytes(int cap)
@@ -529,6 +577,7 @@ SGS_D bool has_duplicate(const uint64_t *R, int n, int lane)
 // Returns false (nothing counted) if the residues are dependent.
 constexpr int kMaxLB = 64;
 constexpr int kMaxDep = 6;
+constexpr float kSplitCliques = 2500.f;   // expected cliques from which a root's children go to the next k_dfs round (multi-shard runs)
 
 SGS_D int ctz_mask(uint32_t v) { return __ffs((int)v) - 1; }
 SGS_D int ctz_mask(uint64_t v) { return __ffsll((long long)v) - 1; }
@@ -579,9 +628,23 @@ SGS_D void lb_walk(const M *ADm, const double *WAc, int ncand, int depth, uint32
     }
 }
 
+// expected number of cliques of a graph with n vertices and e edges (edge density p): sum_k C(n,k) p^(k(k-1)/2)
+SGS_D float expected_cliques(int n, int e)
+{
+    const float p = n > 1 ? (float)e / (0.5f * (float)n * (float)(n - 1)) : 0.f;
+    float term = (float)n, sum = term, pk = 1.f;
+    for (int k = 2; k <= n && k <= 24; k++) {
+        pk *= p;                                   // p^(k-1)
+        term *= (float)(n - k + 1) / (float)k * pk;
+        sum += term;
+        if (term < 0.5f) break;
+    }
+    return sum;
+}
+
 template <int W>
-SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, int n, int nlow, int depth,
-                   uint32_t *hc, double &bw, uint64_t &bm, int lane)
+SGS_D int level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, int n, int nlow, int depth,
+                  uint32_t *hc, double &bw, uint64_t &bm, int lane, float split_cliques)
 {
     // 1. independence of ALL n residues (lower-index entries included: a dependency through one of them would
     //    make a later child non-canonical).  Own rows: entries lane and lane + 32; step u broadcasts the
@@ -684,7 +747,7 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
                 cmb1 ^= cmu;
             }
         }
-        if (fail) return false;
+        if (fail) return 0;
 #pragma unroll 1
         for (int gcode = 1; gcode < (1 << ndep); gcode++) {
             uint64_t S = 0;
@@ -692,7 +755,7 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
             for (int k = 0; k < kMaxDep; k++) if ((gcode >> k) & 1) S ^= deps[k];
             const bool in0 = (S >> lane) & 1, in1 = (S >> (lane + 32)) & 1;
             const bool bad = (in0 && (S & ~adj0 & ~(1ULL << lane)) != 0) || (in1 && (S & ~adj1 & ~(1ULL << (lane + 32))) != 0);
-            if (!__any_sync(0xffffffffu, bad)) return false;      // a commuting dependency: not certified
+            if (!__any_sync(0xffffffffu, bad)) return 0;          // a commuting dependency: not certified
         }
     }
     // 2. commutation graph of the candidates only (list positions nlow..n-1; vertex = position - nlow): lane
@@ -711,7 +774,13 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
             for (int k = 0; k < W; k++) ru[k] = Rc[u * W + k];
             a32 |= (uint32_t)(row_anticommute_sw<W>(ru, sc) ^ 1) << u;
         }
-        if (lane < ncand) AD32[lane] = a32 & ~((2u << lane) - 1u);
+        const uint32_t up32 = lane < ncand ? (a32 & ~((2u << lane) - 1u)) : 0u;
+        if (split_cliques > 0.f && ncand >= 24) {      // too big a walk for one warp of a short kernel: let the caller split it
+            int e = __popc(up32);
+            for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            if (expected_cliques(ncand, e) > split_cliques) return 2;
+        }
+        if (lane < ncand) AD32[lane] = up32;
         __syncwarp();
         uint32_t bm32 = 0;
         lb_walk<uint32_t>(AD32, WA + nlow, ncand, depth, hc, bw, bm32, a32 & ((1u << lane) - 1u), 0u, lane);
@@ -732,26 +801,39 @@ SGS_D bool level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *
             a0 |= (uint64_t)(row_anticommute_sw<W>(ru, sc0) ^ 1) << u;
             a1 |= (uint64_t)(row_anticommute_sw<W>(ru, sc1) ^ 1) << u;
         }
-        AD[lane] = a0 & ~((2ULL << lane) - 1ULL);
-        if (lane + 32 < ncand) AD[lane + 32] = lane == 31 ? 0ULL : (a1 & ~((2ULL << (lane + 32)) - 1ULL));
+        const uint64_t up0 = a0 & ~((2ULL << lane) - 1ULL);
+        const uint64_t up1 = (lane + 32 < ncand && lane != 31) ? (a1 & ~((2ULL << (lane + 32)) - 1ULL)) : 0ULL;
+        if (split_cliques > 0.f) {
+            int e = popc64(up0) + popc64(up1);
+            for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            if (expected_cliques(ncand, e) > split_cliques) return 2;
+        }
+        AD[lane] = up0;
+        if (lane + 32 < ncand) AD[lane + 32] = up1;
         __syncwarp();
         uint64_t bmr = 0;
         lb_walk<uint64_t>(AD, WA + nlow, ncand, depth, hc, bw, bmr, a0 & ((1ULL << lane) - 1ULL), a1 & ((1ULL << (lane + 32)) - 1ULL), lane);
         bm = bmr << nlow;
     }
     __syncwarp();
-    return true;
+    return 1;
 }
 
 template <int W>
 __global__ void __launch_bounds__(256, 3)
 k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned int *item_counter,
-      int shard, int nshards, int cap, int smem_per_warp, const unsigned int *nitems_dev)
+      int shard, int nshards, int cap, int smem_per_warp, const unsigned int *nitems_dev, const unsigned int *__restrict__ perm,
+      uint16_t *retry_out, unsigned int *retry_count, unsigned retry_cap, const unsigned int *valid_end)
 {
+    // retry_out != null: a root whose residues cannot be certified (a commuting dependency: its subtree needs
+    // the warp-cooperative level A, hundreds of instructions per candidate) is not walked here; its children
+    // are appended to retry_out as roots of the next k_dfs round, so that one such subtree is shared by many
+    // warps instead of pinning one warp for up to a millisecond.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const unsigned ltmask = lanemask_lt();
-    if (nitems_dev) nitems = *nitems_dev;          // queue length produced by a parent-sharded expansion
+    if (nitems_dev) nitems = min(nitems, *nitems_dev);   // queue length produced on the device (parent-sharded expansion, retry round)
+    if (valid_end) nitems = min(nitems, *valid_end);
     unsigned char *p = smem_raw + (size_t)warp * smem_per_warp;
     uint64_t *R = (uint64_t *)p;        p += (size_t)cap * W * 8;
     double *WA = (double *)p;           p += (size_t)cap * 8;
@@ -792,10 +874,11 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
 
     // run level B on the list at lb (n entries, candidates from position nlow, group rank `depth`,
     // energy Ef); false if the residues are linearly dependent
-    auto run_level_b = [&](int lb, int n, int nlow, int depth, double Ef) -> bool {
+    auto run_level_b = [&](int lb, int n, int nlow, int depth, double Ef, float split) -> int {
         double bw = -1.0;
         uint64_t bm = 0;
-        if (!level_b<W>(R + lb * W, WA + lb, AD, AD32, n, nlow, depth, hc, bw, bm, lane)) return false;
+        const int rc = level_b<W>(R + lb * W, WA + lb, AD, AD32, n, nlow, depth, hc, bw, bm, lane, split);
+        if (rc != 1) return rc;
         // does any lane's best clique reach the incumbent?
         const bool cand = bm != 0 && (Ef - bw) <= bestE;
         if (__any_sync(0xffffffffu, cand)) {
@@ -828,17 +911,36 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                 try_best(Eb, len);
             }
         }
-        return true;
+        return 1;
     };
 
+    const bool trace = D.trace != 0;
+    unsigned long long troot = 0;
+    bool tfail = false;
+    unsigned tinfo = 0;
+    const unsigned tround = valid_end ? (retry_out ? 2u : 3u) : 1u;
 #pragma unroll 1
     for (;;) {
         // ---- fetch the next subtree root owned by this shard ----
         unsigned it = 0;
         if (lane == 0) it = atomicAdd(item_counter, 1u);
         it = __shfl_sync(0xffffffffu, it, 0);
+        if (trace) {
+            const unsigned long long tn = gtimer();
+            if (troot) {
+                const unsigned long long dt = tn - troot;
+                if (lane == 0) {
+                    atomicMax(&D.stats->dbg[7], (dt << 24) | ((unsigned long long)tinfo << 1) | (tfail ? 1ull : 0ull));
+                    atomicMax(&D.stats->dbg[0], dt);
+                    atomicAdd(&D.stats->dbg[3], dt);
+                    if (tfail) { atomicAdd(&D.stats->dbg[1], 1ull); atomicAdd(&D.stats->dbg[2], dt); }
+                    if (dt > 50000ull) { atomicAdd(&D.stats->dbg[5], 1ull); atomicAdd(&D.stats->dbg[6], dt); }
+                }
+            }
+            troot = tn; tfail = false; tinfo = 0;
+        }
         if (it >= nitems) break;
-        const uint16_t *rec = items + (size_t)it * D.S;
+        const uint16_t *rec = items + (size_t)(perm ? perm[it] : it) * D.S;
         const int m0 = rec[0];
         const unsigned flags = rec[1];
         if (nshards > 1 && (int)(tuple_hash(rec + 2, m0) % (unsigned)nshards) != shard) continue;
@@ -912,12 +1014,33 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         for (int d = 16; d > 0; d >>= 1) q0 += __shfl_xor_sync(0xffffffffu, q0, d);
 
         if (lane == 0) hist[m0]++;
+        tinfo = (tround << 20) | ((unsigned)m0 << 14) | ((unsigned)min(a, 127) << 7) | (unsigned)min(a - q0, 127);
         if (q0 >= a) { try_best(E0, m0); continue; }                      // no extension: a leaf
-        if (a <= 64 && m0 + (a - q0) < kMaxG && run_level_b(0, a, q0, m0, E0)) continue;
+        // (a certified root whose clique walk alone would outlast the rest of a short kernel is split the same way
+        //  when a next round exists: level_b answers 2)
+        if (a <= 64 && m0 + (a - q0) < kMaxG && run_level_b(0, a, q0, m0, E0, retry_out ? kSplitCliques : 0.f) == 1) continue;
+        tfail = true;
         if (has_duplicate<W>(R, a, lane)) {
             try_best(E0, m0);
             push_slow(D, path, m0, flags | kFlagExpandOnly, lane);
             continue;
+        }
+        if (retry_out && a - q0 >= 4 && m0 + 1 < kMaxG) {
+            // every entry from q0 on is a valid child (residues pairwise distinct); each counts itself as a root
+            unsigned slot = 0;
+            if (lane == 0) slot = atomicAdd(retry_count, (unsigned)(a - q0));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot + (unsigned)(a - q0) <= retry_cap) {
+                for (int j = q0 + lane; j < a; j += 32) {
+                    uint16_t *o = retry_out + (size_t)(slot + (unsigned)(j - q0)) * D.S;
+                    o[0] = (uint16_t)(m0 + 1);
+                    o[1] = 0;
+                    for (int k = 0; k < m0; k++) o[2 + k] = path[k];
+                    o[2 + m0] = TT[j];
+                }
+                continue;
+            }
+            if (lane == 0) atomicMin(retry_count + 1, slot);               // queue full: records end here; walk it locally
         }
         if (lane == 0) hist[m0 + 1] += (uint32_t)(a - q0);
 
@@ -1007,7 +1130,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                 off += __popc(bal);
             }
             __syncwarp();
-            if (nal <= 64 && depth + 1 + (nal - nlow) < kMaxG && run_level_b(cb, nal, nlow, depth + 1, Ec)) continue;
+            if (nal <= 64 && depth + 1 + (nal - nlow) < kMaxG && run_level_b(cb, nal, nlow, depth + 1, Ec, 0.f) == 1) continue;
             // residues pairwise distinct ⇒ every child of this child is a new group whose only members
             // are its generators.  Otherwise the exact kernel expands it.
             if (has_duplicate<W>(R + cb * W, nal, lane)) {

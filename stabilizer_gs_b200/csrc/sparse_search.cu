@@ -28,7 +28,7 @@ struct DevCtx {
     int device = 0;
     int shard = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evh0 = nullptr, evh1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evh0 = nullptr, evh1 = nullptr, evA = nullptr, evB = nullptr;
     int sms = 0;
     // device buffers
     uint64_t *rows = nullptr, *adj = nullptr;
@@ -38,7 +38,9 @@ struct DevCtx {
     SparseStats *stats = nullptr;
     unsigned long long *hist_sum = nullptr;
     uint16_t *qA = nullptr, *qB = nullptr, *slow = nullptr, *work = nullptr;
-    unsigned int *counters = nullptr;   // [0] next-level count, [1] item counter, [2] slow count
+    unsigned int *counters = nullptr;   // [0] next-level count, [1] item counter, [2] slow count, [8..15] root class counts, [16..23] cursors
+    unsigned int *perm = nullptr;       // [qcap] heavy-first order of the subtree roots
+    uint16_t *retry[2] = {nullptr, nullptr};   // [retry_cap * S] roots of the 2nd / 3rd k_dfs round (counters[24..27]: count, valid end)
     FinalOut *fin = nullptr;
     int8_t *term_signs = nullptr;
     uint64_t *memX = nullptr;
@@ -57,6 +59,8 @@ struct DevCtx {
 
 
 }  // namespace
+
+constexpr unsigned kRetryCap = 1u << 20;   // roots handed to the next k_dfs round (multi-shard runs)
 
 struct SparsePlan::Impl {
     Hamiltonian H;
@@ -83,6 +87,8 @@ struct SparsePlan::Impl {
     Status init();
     Status init_device(DevCtx &c);
     template <int W_> Status search_local(DevCtx &c);
+    template <int W_> Status launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
+                                        unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm);
     template <int W_> Status finalize(DevCtx &c, const BestRec *host_best, sgs_result *out);
     template <int W_> Status run_replay(sgs_result *out);
     void fill_stats(const SparseStats &tot, sgs_result *out);
@@ -100,6 +106,8 @@ SparsePlan::Impl::~Impl()
         if (c.ev1) cudaEventDestroy(c.ev1);
         if (c.evh0) cudaEventDestroy(c.evh0);
         if (c.evh1) cudaEventDestroy(c.evh1);
+        if (c.evA) cudaEventDestroy(c.evA);
+        if (c.evB) cudaEventDestroy(c.evB);
         if (c.stream) cudaStreamDestroy(c.stream);
     }
 }
@@ -111,6 +119,7 @@ SparseDev SparsePlan::Impl::dev_view(const DevCtx &c) const
     D.rows = c.rows; D.wgt = c.wgt; D.wabs = c.wabs; D.adj = c.adj;
     D.wbest = c.wbest; D.stats = c.stats;
     D.slow = c.slow; D.slow_count = c.counters + 2; D.slow_cap = slow_cap;
+    D.trace = getenv("SGS_TRACE") ? 1 : 0;
     return D;
 }
 
@@ -182,6 +191,8 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
     SGS_CUDA_TRY(cudaEventCreate(&c.ev1));
     SGS_CUDA_TRY(cudaEventCreate(&c.evh0));
     SGS_CUDA_TRY(cudaEventCreate(&c.evh1));
+    SGS_CUDA_TRY(cudaEventCreate(&c.evA));
+    SGS_CUDA_TRY(cudaEventCreate(&c.evB));
     const int Tn = std::max(T, 1);
     c.nwbest = c.sms * 64;
     // one arena, carved into 256-byte aligned buffers
@@ -202,7 +213,10 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
     want(&c.qB, (size_t)qcap * S);
     want(&c.slow, (size_t)slow_cap * S);
     want(&c.work, (size_t)chunk * S);
-    want(&c.counters, 4);
+    want(&c.counters, 32);
+    want(&c.perm, qcap);
+    want(&c.retry[0], (size_t)kRetryCap * S);
+    want(&c.retry[1], (size_t)kRetryCap * S);
     want(&c.fin, 1);
     want(&c.term_signs, Tn);
     want(&c.memX, Tn);
@@ -239,6 +253,33 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
         SGS_CUDA_TRY(cudaGetLastError());
         SGS_CUDA_TRY(cudaStreamSynchronize(c.stream));
     }
+    return Status();
+}
+
+// The walk below the subtree roots.  With several shards the walk is short, so a root that cannot be certified
+// at once (a commuting dependency below it) would pin one warp for most of the kernel: such roots hand their
+// children to a second round, and those of the second round to a third (counts stay on the device).
+template <int W_>
+Status SparsePlan::Impl::launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
+                                    unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm)
+{
+    cudaStream_t st = c.stream;
+    const bool split = nshards > 1;
+    unsigned *rc = c.counters + 24;      // [0] round-2 count, [1] its valid end, [2] round-3 count, [3] its valid end, [4], [5] item counters
+    if (split) {
+        SGS_CUDA_TRY(cudaMemsetAsync(rc, 0, 6 * sizeof(unsigned), st));
+        SGS_CUDA_TRY(cudaMemsetAsync(rc + 1, 0xFF, sizeof(unsigned), st));
+        SGS_CUDA_TRY(cudaMemsetAsync(rc + 3, 0xFF, sizeof(unsigned), st));
+    }
+    k_dfs<W_><<<grid, wpb * 32, pw * wpb, st>>>(D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm,
+                                               split ? c.retry[0] : nullptr, rc, kRetryCap, nullptr);
+    c.launches++;
+    if (split) {
+        k_dfs<W_><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[0], kRetryCap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, kRetryCap, rc + 1);
+        k_dfs<W_><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[1], kRetryCap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3);
+        c.launches += 2;
+    }
+    SGS_CUDA_TRY(cudaGetLastError());
     return Status();
 }
 
@@ -344,8 +385,17 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
             rp.dfs_grid = grid; rp.gen_wpb = gen_wpb; rp.gen_pw = gen_pw; rp.gen_maxgrid = gen_maxgrid;
         }
         SGS_CUDA_TRY(cudaEventRecord(c.evh0, st));
-        k_dfs<W_><<<grid, dfs_wpb * 32, dfs_pw * dfs_wpb, st>>>(D, cur, count, c.counters + 1, c.shard, nshards, dfs_cap, (int)dfs_pw, nullptr);
-        c.launches++;
+        // heavy-first order pays when the walk is short (several shards): the longest subtrees must not start last
+        const bool use_perm = nshards > 1;
+        if (use_perm) {
+            SGS_CUDA_TRY(cudaMemsetAsync(c.counters + 8, 0, 16 * sizeof(unsigned), st));
+            const unsigned cg = std::min<unsigned>((count + 255) / 256, (unsigned)c.sms * 4);
+            k_class_count<<<cg, 256, 0, st>>>(cur, count, nullptr, S, T, c.counters + 8);
+            k_class_scatter<<<cg, 256, 0, st>>>(cur, count, nullptr, S, T, c.counters + 8, c.counters + 16, c.perm);
+            c.launches += 2;
+        }
+        Status sd = launch_dfs<W_>(c, D, grid, dfs_wpb, dfs_pw, dfs_cap, cur, count, nshards, nullptr, use_perm ? c.perm : nullptr);
+        if (!sd.ok()) return sd;
         SGS_CUDA_TRY(cudaGetLastError());
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
     } else {
@@ -452,15 +502,29 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
             c.launches++;
             std::swap(cur, nxt);
         }
+        const bool use_perm = nshards > 1;
+        if (use_perm) {
+            const unsigned cnt = rp.counts[rp.depth];
+            const unsigned cg = std::max(1u, std::min<unsigned>((cnt + 255) / 256, (unsigned)c.sms * 4));
+            const unsigned *ndev = (nshards > 1 && rp.depth > 0) ? c.counters : nullptr;
+            SGS_CUDA_TRY(cudaMemsetAsync(c.counters + 8, 0, 16 * sizeof(unsigned), st));
+            k_class_count<<<cg, 256, 0, st>>>(cur, cnt, ndev, S, T, c.counters + 8);
+            k_class_scatter<<<cg, 256, 0, st>>>(cur, cnt, ndev, S, T, c.counters + 8, c.counters + 16, c.perm);
+            c.launches += 2;
+        }
         SGS_CUDA_TRY(cudaEventRecord(c.evh0, st));
         // with a parent-sharded last level the queue length is only known on the device: counters[0]
-        k_dfs<W_><<<rp.dfs_grid, rp.dfs_wpb * 32, rp.dfs_pw * rp.dfs_wpb, st>>>(D, cur, rp.counts[rp.depth], c.counters + 1, c.shard,
-                                                                              (nshards > 1 && rp.depth > 0) ? 1 : nshards, rp.dfs_cap, (int)rp.dfs_pw,
-                                                                              (nshards > 1 && rp.depth > 0) ? c.counters : nullptr);
+        {
+            Status sd = launch_dfs<W_>(c, D, rp.dfs_grid, rp.dfs_wpb, rp.dfs_pw, rp.dfs_cap, cur, rp.counts[rp.depth],
+                                       (nshards > 1 && rp.depth > 0) ? 1 : nshards, (nshards > 1 && rp.depth > 0) ? c.counters : nullptr,
+                                       use_perm ? c.perm : nullptr);
+            if (!sd.ok()) return sd;
+        }
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
         k_reduce_best<<<1, 1024, 0, st>>>(c.wbest, c.nwbest, c.gbest);
-        c.launches += 2;
+        c.launches += 1;
         SGS_CUDA_TRY(cudaGetLastError());
+        SGS_CUDA_TRY(cudaEventRecord(c.evA, st));
     }
     if (nccl) {
         std::vector<void *> sendb, recvb, sumb;
@@ -478,6 +542,7 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
     }
     DevCtx &c0 = devs[0];
     SGS_CUDA_TRY(cudaSetDevice(c0.device));
+    SGS_CUDA_TRY(cudaEventRecord(c0.evB, c0.stream));
     {
         const SparseDev D = dev_view(c0);
         k_finalize<W_><<<1, 256, 0, c0.stream>>>(D, c0.gbest, c0.order, c0.fin, c0.term_signs, c0.memX, c0.memA, c0.memT, c0.memCount);
@@ -502,6 +567,18 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         SGS_CUDA_TRY(cudaEventElapsedTime(&a, c.ev0, c.ev1));
         SGS_CUDA_TRY(cudaEventElapsedTime(&b, c.evh0, c.evh1));
         msd = std::max(msd, a); msh = std::max(msh, b); launches += c.launches;
+    }
+    if (getenv("SGS_TRACE")) {
+        float e1 = 0, e2 = 0, e3 = 0, e4 = 0, e5 = 0;
+        cudaEventElapsedTime(&e1, c0.ev0, c0.evh0); cudaEventElapsedTime(&e2, c0.evh0, c0.evh1); cudaEventElapsedTime(&e3, c0.evh1, c0.evA);
+        cudaEventElapsedTime(&e4, c0.evA, c0.evB); cudaEventElapsedTime(&e5, c0.evB, c0.ev1);
+        fprintf(stderr, "replay shard %d: expansion %.3f ms, walk %.3f ms, reduce %.3f ms, collective %.3f ms, finalise+copy %.3f ms, host total %.3f ms\n",
+                c0.shard, e1, e2, e3, e4, e5, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3);
+        const unsigned long long *g = c0.hstats.dbg;
+        fprintf(stderr, "  walk: longest root %.1f us; roots not certified at the root %llu (%.3f warp-ms of %.3f); roots > 50 us: %llu (%.3f warp-ms)\n",
+                g[0] * 1e-3, g[1], g[2] * 1e-6, g[3] * 1e-6, g[5], g[6] * 1e-6);
+        fprintf(stderr, "  longest root: round %llu, rank %llu, alive %llu, candidates %llu, certified %d\n", (g[7] >> 21) & 7, (g[7] >> 15) & 63,
+                (g[7] >> 8) & 127, (g[7] >> 1) & 127, (int)!(g[7] & 1));
     }
     if (c0.hstats.error || hcnt[2] != 0 || !c0.hbest.valid || fo.error) {
         rp.ok = false;      // should not happen (the sequence is deterministic); fall back to the adaptive path
