@@ -642,8 +642,10 @@ SGS_D float expected_cliques(int n, int e)
     return sum;
 }
 
+// (not inlined: it is called from two places of k_dfs and a single copy keeps the hot loops inside the
+//  instruction cache)
 template <int W>
-SGS_D int level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, int n, int nlow, int depth,
+__device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, int n, int nlow, int depth,
                   uint32_t *hc, double &bw, uint64_t &bm, int lane, float split_cliques)
 {
     // 1. independence of ALL n residues (lower-index entries included: a dependency through one of them would
@@ -819,12 +821,13 @@ SGS_D int level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *A
     return 1;
 }
 
-template <int W>
+template <int W, bool SPLIT>
 __global__ void __launch_bounds__(256, 3)
 k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned int *item_counter,
       int shard, int nshards, int cap, int smem_per_warp, const unsigned int *nitems_dev, const unsigned int *__restrict__ perm,
-      uint16_t *retry_out, unsigned int *retry_count, unsigned retry_cap, const unsigned int *valid_end)
+      uint16_t *retry_out_, unsigned int *retry_count, unsigned retry_cap, const unsigned int *valid_end)
 {
+    uint16_t *const retry_out = SPLIT ? retry_out_ : nullptr;      // single-shard build: the hand-off code is compiled out
     // retry_out != null: a root whose residues cannot be certified (a commuting dependency: its subtree needs
     // the warp-cooperative level A, hundreds of instructions per candidate) is not walked here; its children
     // are appended to retry_out as roots of the next k_dfs round, so that one such subtree is shared by many
@@ -914,7 +917,10 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         return 1;
     };
 
-    const bool trace = D.trace != 0;
+#ifndef SGS_WALK_TRACE
+#define SGS_WALK_TRACE 0      // per-root timing diagnostics (SGS_TRACE=1) cost ~5 % of the walk: opt-in at build time
+#endif
+    const bool trace = SGS_WALK_TRACE && D.trace != 0;
     unsigned long long troot = 0;
     bool tfail = false;
     unsigned tinfo = 0;

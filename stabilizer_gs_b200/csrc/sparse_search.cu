@@ -271,13 +271,16 @@ Status SparsePlan::Impl::launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid
         SGS_CUDA_TRY(cudaMemsetAsync(rc + 1, 0xFF, sizeof(unsigned), st));
         SGS_CUDA_TRY(cudaMemsetAsync(rc + 3, 0xFF, sizeof(unsigned), st));
     }
-    k_dfs<W_><<<grid, wpb * 32, pw * wpb, st>>>(D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm,
-                                               split ? c.retry[0] : nullptr, rc, kRetryCap, nullptr);
-    c.launches++;
     if (split) {
-        k_dfs<W_><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[0], kRetryCap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, kRetryCap, rc + 1);
-        k_dfs<W_><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[1], kRetryCap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3);
-        c.launches += 2;
+        k_dfs<W_, true><<<grid, wpb * 32, pw * wpb, st>>>(D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc,
+                                                         kRetryCap, nullptr);
+        k_dfs<W_, true><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[0], kRetryCap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, kRetryCap,
+                                                         rc + 1);
+        k_dfs<W_, false><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[1], kRetryCap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3);
+        c.launches += 3;
+    } else {
+        k_dfs<W_, false><<<grid, wpb * 32, pw * wpb, st>>>(D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, nullptr);
+        c.launches++;
     }
     SGS_CUDA_TRY(cudaGetLastError());
     return Status();
@@ -374,9 +377,12 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         const size_t dfs_pw = dfs_smem_bytes<W_>(dfs_cap);
         int dfs_wpb = 8;
         while (dfs_wpb > 1 && dfs_pw * dfs_wpb > 200 * 1024) dfs_wpb >>= 1;
-        SGS_CUDA_TRY(cudaFuncSetAttribute(k_dfs<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dfs_pw * dfs_wpb)));
-        int dfs_occ = 1;
-        SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dfs_occ, k_dfs<W_>, dfs_wpb * 32, dfs_pw * dfs_wpb));
+        SGS_CUDA_TRY(cudaFuncSetAttribute(k_dfs<W_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dfs_pw * dfs_wpb)));
+        SGS_CUDA_TRY(cudaFuncSetAttribute(k_dfs<W_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dfs_pw * dfs_wpb)));
+        int dfs_occ = 1, dfs_occ2 = 1;
+        SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dfs_occ, k_dfs<W_, false>, dfs_wpb * 32, dfs_pw * dfs_wpb));
+        SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dfs_occ2, k_dfs<W_, true>, dfs_wpb * 32, dfs_pw * dfs_wpb));
+        dfs_occ = std::min(dfs_occ, dfs_occ2);
         dfs_occ = std::max(1, dfs_occ);
         const unsigned dfs_maxgrid = (unsigned)std::min<long long>((long long)c.sms * dfs_occ, c.nwbest / dfs_wpb);
         const unsigned grid = std::min<unsigned>(dfs_maxgrid, (count + dfs_wpb - 1) / dfs_wpb);
