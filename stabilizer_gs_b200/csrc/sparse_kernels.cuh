@@ -659,8 +659,31 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         e1[k] = lane + 32 < n ? R[(lane + 32) * W + k] : 0;
     }
     bool dependent = false;
+    // Multi-word rows: if the images under a linear map onto 64 bits (the words folded together by rotations)
+    // are independent, so are the rows — one-word elimination at half the cost or less; with <= 58 entries it
+    // rarely fails, and when it does the full-width elimination below decides.
+    bool proven = false;
+    if (W > 1 && n <= 58) {
+        uint64_t p0 = e0[0], p1 = e1[0];
+#pragma unroll
+        for (int k = 1; k < W; k++) {
+            const int rot = (23 * k) & 63;
+            p0 ^= (e0[k] << rot) | (e0[k] >> (64 - rot));
+            p1 ^= (e1[k] << rot) | (e1[k] >> (64 - rot));
+        }
+        bool dep = false;
 #pragma unroll 1
-    for (int u = 0; u < n; u++) {
+        for (int u = 0; u < n; u++) {
+            const uint64_t cu = __shfl_sync(0xffffffffu, u < 32 ? p0 : p1, u & 31);
+            if (cu == 0) { dep = true; break; }
+            const uint64_t lm = cu & (0 - cu);
+            if (lane > u && (p0 & lm)) p0 ^= cu;
+            if (two && lane + 32 > u && (p1 & lm)) p1 ^= cu;
+        }
+        proven = !dep;
+    }
+#pragma unroll 1
+    for (int u = 0; u < n && !proven; u++) {
         uint64_t cu[W], lm[W];
         bool nz = false;
 #pragma unroll
