@@ -660,10 +660,10 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
     }
     bool dependent = false;
     // Multi-word rows: if the images under a linear map onto 64 bits (the words folded together by rotations)
-    // are independent, so are the rows — one-word elimination at half the cost or less; with <= 58 entries it
+    // are independent, so are the rows — one-word elimination at half the cost or less; with <= 62 entries it
     // rarely fails, and when it does the full-width elimination below decides.
     bool proven = false;
-    if (W > 1 && n <= 58) {
+    if (W > 1 && n <= 62) {
         uint64_t p0 = e0[0], p1 = e1[0];
 #pragma unroll
         for (int k = 1; k < W; k++) {
