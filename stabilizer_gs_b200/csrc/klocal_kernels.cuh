@@ -740,7 +740,8 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
     grid.sync();                                             // every exit above is uniform; nobody reads ctl any more
     if (tid == 0) {
         if (err) { atomicMax(&ctl->err, err); nin = 0; }
-        ctl->nin = nin; ctl->cur = cur; ctl->hm_off = hm_off; ctl->hb_off = hb_off; ctl->step = step; ctl->gen = gen;
+        ctl->nin = nin; ctl->cur = cur; ctl->hm_off = hm_off; ctl->hb_off = hb_off; ctl->step = step;
+        ctl->gen = gen + 1;                  // an aborted step may have left claims of generation gen in the table
         ctl->total = 0; ctl->nuniq = nin;
     }
 }
@@ -910,7 +911,7 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
     grid.sync();
     if (tid == 0) {
         if (err) atomicMax(&ctl->err, err);
-        ctl->gen = gen;
+        ctl->gen = gen + 2;                  // an aborted level may have left claims of generations gen, gen + 1 in the table
         ctl->done_m = m + 1;
     }
 }

@@ -196,13 +196,15 @@ Status KlocalMachine::Impl::init()
     tstride = 1 << std::min(k, kDpTab);
     slab_stride = tstride;
     max_m = std::max(max_m, n);
-    const long long base = std::max<long long>(2048, (1ll << 22) / ((long long)slab_stride * 16));   // k=4: 16384 states
+    // SGS_DP_CAPS / SGS_SR_CAP / SGS_SR_POOL_KB: start capacities for tests of the grow-and-redo paths
+    auto env_ll = [](const char *name, long long dflt) { const char *v = getenv(name); return v && atoll(v) > 0 ? atoll(v) : dflt; };
+    const long long base = env_ll("SGS_DP_CAPS", std::max<long long>(2048, (1ll << 22) / ((long long)slab_stride * 16)));   // k=4: 16384 states
     caps = (int)std::min<long long>(base * scale, 1ll << 22);
     capc = (int)std::min<long long>((long long)caps * 8, 1ll << 25);
     hm_cap = (int)std::min<long long>((long long)caps * 64, 1ll << 27);
     hb_cap = (int)std::min<long long>((long long)caps * 64 * std::min(tstride, 64), 1ll << 29);
-    const int srcap = (int)std::min<long long>(65536ll * scale, 1ll << 24);
-    const size_t srpool = ((size_t)64 << 20) * (size_t)std::min(scale, 64);
+    const int srcap = (int)std::min<long long>(env_ll("SGS_SR_CAP", 65536) * scale, 1ll << 24);
+    const size_t srpool = (size_t)env_ll("SGS_SR_POOL_KB", 64 << 10) * 1024 * (size_t)std::min(scale, 64);
     {   // one cached arena for the tables, the DP batch buffers, the right-environment scratch and the level tables
         const size_t dpb = (size_t)caps * (2 * sizeof(DpState) + sizeof(DpMoved) + sizeof(Ech) + 16) + (size_t)caps * tstride * 16 +
                            (size_t)caps * 2 * slab_stride * 16 + (size_t)capc * (sizeof(DpKey) + 48 + 2 * sizeof(DdSlot)) +

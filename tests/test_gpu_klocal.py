@@ -114,3 +114,42 @@ def test_periodic_vs_oracle_other_cells(tmp_path):
         assert r['sright_log'] == ref['sright_log'] and r['fixed_point_sizes'] == ref['fixed_point_sizes']
         key = lambda o: (round(o['energy'], 9), o['begin'], o['end'], o['generators'])
         assert sorted(map(key, r['results'])) == sorted(map(key, ref['results']))
+
+
+@pytest.mark.parametrize('env', [{'SGS_DP_CAPS': '16'}, {'SGS_SR_CAP': '64'}, {'SGS_SR_POOL_KB': '16'},
+                                 {'SGS_DP_CAPS': '8', 'SGS_SR_CAP': '32', 'SGS_SR_POOL_KB': '8'}])
+def test_capacity_overflow_is_redone_with_larger_buffers(monkeypatch, env):
+    """Device-side capacity checks (states, children, right-environment branches, level pool) end the persistent
+    kernels with an error code; the host grows the buffers and redoes the search: same result as the default."""
+    S = sgs()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    r = S.klocal_search(S.HamHandle.from_text(G.klocal_text(64, 4, 3, 0)))
+    assert r['energy'] == pytest.approx(-30.9918743342, abs=1e-9)
+    assert len(r['generators']) == 47
+    assert max(r['states_per_site']) == 113 and r['transitions'] == 2850
+    g = json.load(open(os.path.join(GOLDEN, 'periodic_example.json')))['periodic']
+    p = S.klocal_periodic(os.path.join(ROOT, 'examples', 'hamiltonian_periodic.txt'), cmax=g['cmax'], c=g['c'])
+    key = lambda o: (o['energy'], o['begin'], o['end'], o['generators'])
+    assert sorted(map(key, p['results'])) == sorted(map(key, g['results']))
+
+
+def test_per_site_api_matches_one_shot():
+    """sgs_klocal_create / evolve / nstates / ground_state (the loop of cpp/klocal_sparse.cpp) = sgs_klocal_search"""
+    S = sgs()
+    H = S.HamHandle.from_text(G.klocal_text(20, 4, 3, 7))
+    one = S.klocal_search(H)
+    from stabilizer_gs_b200.state import Hamiltonian, StateMachine, generate_Sright_all
+    import tempfile
+    with tempfile.NamedTemporaryFile('w', suffix='.txt', delete=False) as f:
+        f.write(G.klocal_text(20, 4, 3, 7))
+    Hm = Hamiltonian.from_file(f.name)
+    SM = StateMachine(Hm, generate_Sright_all(Hm))
+    sizes = [len(SM.state_dict)]
+    while SM.m < Hm.n:
+        SM.evolve()
+        sizes.append(len(SM.state_dict))
+    SM.generate_gs()
+    assert sizes == one['states_per_site']
+    assert SM.energy_gs == pytest.approx(one['energy'], rel=1e-12)
+    os.unlink(f.name)
