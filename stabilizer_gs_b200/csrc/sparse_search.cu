@@ -60,7 +60,6 @@ struct DevCtx {
 
 }  // namespace
 
-constexpr unsigned kRetryCap = 1u << 20;   // roots handed to the next k_dfs round (multi-shard runs)
 
 struct SparsePlan::Impl {
     Hamiltonian H;
@@ -68,6 +67,7 @@ struct SparsePlan::Impl {
     int W = 1, T = 0, TW = 0, S = 0, n = 0;
     int nshards = 1;
     unsigned qcap = 0, slow_cap = 0, chunk = 0;
+    unsigned retry_cap = 1u << 20;      // roots handed to the next k_dfs round (multi-shard runs); SGS_RETRY_CAP for tests
     int dfs_cap = 0;
     std::vector<DevCtx> devs;
     std::shared_ptr<NcclWorld> nccl;
@@ -140,6 +140,7 @@ Status SparsePlan::Impl::init()
     qcap = (unsigned)std::min<unsigned long long>(want, 1ull << 25);
     slow_cap = 1u << 22;
     chunk = 1u << 16;
+    if (const char *v = getenv("SGS_RETRY_CAP")) if (atoi(v) > 0) retry_cap = (unsigned)atoi(v);
     dfs_cap = 128;     // re-derived per search from the measured branching of the last expanded level
 
     int ndev = 0;
@@ -215,8 +216,8 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
     want(&c.work, (size_t)chunk * S);
     want(&c.counters, 32);
     want(&c.perm, qcap);
-    want(&c.retry[0], (size_t)kRetryCap * S);
-    want(&c.retry[1], (size_t)kRetryCap * S);
+    want(&c.retry[0], (size_t)retry_cap * S);
+    want(&c.retry[1], (size_t)retry_cap * S);
     want(&c.fin, 1);
     want(&c.term_signs, Tn);
     want(&c.memX, Tn);
@@ -273,10 +274,10 @@ Status SparsePlan::Impl::launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid
     }
     if (split) {
         k_dfs<W_, true><<<grid, wpb * 32, pw * wpb, st>>>(D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc,
-                                                         kRetryCap, nullptr);
-        k_dfs<W_, true><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[0], kRetryCap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, kRetryCap,
+                                                         retry_cap, nullptr);
+        k_dfs<W_, true><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap,
                                                          rc + 1);
-        k_dfs<W_, false><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[1], kRetryCap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3);
+        k_dfs<W_, false><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3);
         c.launches += 3;
     } else {
         k_dfs<W_, false><<<grid, wpb * 32, pw * wpb, st>>>(D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, nullptr);

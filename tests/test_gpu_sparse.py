@@ -142,6 +142,36 @@ def test_virtual_shards_partition_the_search():
         assert best['energy'] == full['energy'] and best['generators'] == full['generators']
 
 
+@pytest.mark.parametrize('retry_cap', [None, '8'])
+@pytest.mark.parametrize('n,T,seed,worlds', [(18, 110, 5, (2, 5)), (24, 300, 0, (8,))])
+def test_multi_round_walk_hand_off(monkeypatch, retry_cap, n, T, seed, worlds):
+    """With several shards, roots that cannot be certified at once (or are very heavy) hand their children to a
+    second / third k_dfs round; a full hand-off queue (SGS_RETRY_CAP=8) falls back to walking locally.  Counts per
+    rank add up to the single-shard run and the best shard holds the global answer, for the adaptive first run of a
+    plan and for its recorded launch sequence (second run)."""
+    S = sgs()
+    H = S.HamHandle.from_text(G.sparse_text(n, T, seed))
+    full = S.sparse_search(H)
+    if retry_cap:
+        monkeypatch.setenv('SGS_RETRY_CAP', retry_cap)
+    for world in worlds:
+        first, second = [], []
+        for r in range(world):
+            plan = S.SparsePlan(H, rank=r, world=world)
+            first.append(plan.run())       # adaptive, host-synchronised run: roots owned by hash(root)
+            second.append(plan.run())      # recorded launch sequence: last expansion level owned by hash(parent)
+            plan.close()
+        for parts in (first, second):      # two different, equally valid partitions of the same tree
+            assert sum(p['candidates'] for p in parts) == full['candidates']
+            merged = {}
+            for p in parts:
+                for k, v in p['rank_hist'].items():
+                    merged[k] = merged.get(k, 0) + v
+            assert {k: v for k, v in merged.items() if v} == {k: v for k, v in full['rank_hist'].items() if v}
+            best = min(parts, key=lambda p: p['energy'])
+            assert best['energy'] == full['energy'] and best['generators'] == full['generators']
+
+
 def _check_invariants(S, text, r):
     H = S.HamHandle.from_text(text)
     rows, w, b, e = H.terms()
