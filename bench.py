@@ -116,7 +116,13 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='config4', choices=['config4', 'config5'],
+                    help='config4 = n=24/T=300 (default, the bench line); config5 = n=40/T=1000 (28 s per step on one B200: use --steps 1)')
     args = ap.parse_args()
+    if args.workload == 'config5':
+        global N_QUBITS, N_TERMS, WORKLOAD
+        N_QUBITS, N_TERMS = 40, 1000
+        WORKLOAD = f"sparse random Pauli Hamiltonian n={N_QUBITS} T={N_TERMS} seed={SEED} (BASELINE configs[4]), full enumeration"
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -161,7 +167,7 @@ def main():
 
     peaks = C.measure_int_peaks(device) if rank == 0 else None
     plan = S.SparsePlan(ham, device=device, rank=rank, world=world, nccl_id=nccl_id)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) if args.workload == 'config4' else max(args.warmup, 1)):   # (a config-5 step is 28 s)
         C.flush_l2(device)
         plan.run()
     sampler = ClockSampler(device) if rank == 0 else None
@@ -188,7 +194,7 @@ def main():
     zx = (ctypes.c_uint64 * (T * W))(*[x for r in rows for x in r])
     wv = (ctypes.c_double * T)(*w)
     o, keep = C.make_opts(device=device, rank=rank, world=world, nccl_id=nccl_id)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 10)) if args.workload == 'config4' else 1
 
     def one_shot():
         hp = ctypes.c_void_p()
