@@ -116,7 +116,8 @@ __global__ void k_adjacency(int T, int TW, const uint64_t *__restrict__ rows, ui
 }
 
 // push one node record onto the slow work stack (warp-uniform call)
-SGS_D void push_slow(const SparseDev &D, const uint16_t *g, int m, unsigned flags, int lane)
+// (cold paths are kept out of line: the hot kernel's code must stay inside the instruction caches)
+__device__ __noinline__ void push_slow(const SparseDev &D, const uint16_t *g, int m, unsigned flags, int lane)
 {
     unsigned slot = 0;
     if (lane == 0) slot = atomicAdd(D.slow_count, 1u);
@@ -844,6 +845,46 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
     return 1;
 }
 
+// cold half of try_best: ties by tuple order, then the copy of the tuple
+__device__ __noinline__ bool best_update(double Eval, int len, double bestE, int bestM, uint16_t *bestG, const uint16_t *path, int lane)
+{
+    __syncwarp();
+    if (Eval == bestE && !tuple_before(path, len, bestG, bestM)) return false;
+    for (int i = lane; i < len; i += 32) bestG[i] = path[i];
+    __syncwarp();
+    return true;
+}
+
+// cold tail of a level-B walk whose best clique reaches the incumbent: warp argmax of (weight, then lowest first
+// vertex, then lowest second vertex; a singleton last), the clique's terms appended to path[depth..).  Returns the
+// clique size and its weight.
+__device__ __noinline__ int level_b_pick(double bw, uint64_t bm, const uint16_t *TTlb, uint16_t *path, int depth, int lane, double *wout)
+{
+    double w = bm ? bw : -1.0;
+    int key = 1 << 20;
+    if (bm) {
+        const uint64_t rest = bm & (bm - 1);
+        key = ctz64(bm) * 128 + (rest ? ctz64(rest) : 127);
+    }
+    int src = lane;
+#pragma unroll 1
+    for (int d = 16; d > 0; d >>= 1) {
+        const double ow = __shfl_xor_sync(0xffffffffu, w, d);
+        const int ok = __shfl_xor_sync(0xffffffffu, key, d);
+        const int os = __shfl_xor_sync(0xffffffffu, src, d);
+        if (ow > w || (ow == w && ok < key)) { w = ow; key = ok; src = os; }
+    }
+    const uint64_t mask = __shfl_sync(0xffffffffu, bm, src);
+    if (lane == 0) {
+        uint64_t mm = mask;
+        int l2 = depth;
+        while (mm) { path[l2++] = TTlb[ctz64(mm)]; mm &= mm - 1; }
+    }
+    __syncwarp();
+    *wout = w;
+    return popc64(mask);
+}
+
 template <int W, bool SPLIT>
 __global__ void __launch_bounds__(256, 3)
 k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned int *item_counter,
@@ -887,11 +928,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     // record path[0..len) as the best tuple if Eval beats the incumbent (ties: tuple order)
     auto try_best = [&](double Eval, int len) {
         if (Eval > bestE) return;
-        __syncwarp();
-        if (Eval == bestE && !tuple_before(path, len, bestG, bestM)) return;
-        bestE = Eval; bestM = len;
-        for (int i = lane; i < len; i += 32) bestG[i] = path[i];
-        __syncwarp();
+        if (best_update(Eval, len, bestE, bestM, bestG, path, lane)) { bestE = Eval; bestM = len; }
     };
 
     uint32_t hc[kMaxG + 4];                              // per-lane candidate counts by rank (level B)
@@ -908,34 +945,9 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         // does any lane's best clique reach the incumbent?
         const bool cand = bm != 0 && (Ef - bw) <= bestE;
         if (__any_sync(0xffffffffu, cand)) {
-            // warp argmax of (weight, then lowest first vertex, then lowest second vertex; a singleton last)
-            double w = bm ? bw : -1.0;
-            int key = 1 << 20;
-            if (bm) {
-                const uint64_t rest = bm & (bm - 1);
-                key = ctz64(bm) * 128 + (rest ? ctz64(rest) : 127);
-            }
-            int src = lane;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                const double ow = __shfl_xor_sync(0xffffffffu, w, d);
-                const int ok = __shfl_xor_sync(0xffffffffu, key, d);
-                const int os = __shfl_xor_sync(0xffffffffu, src, d);
-                if (ow > w || (ow == w && ok < key)) { w = ow; key = ok; src = os; }
-            }
-            const uint64_t mask = __shfl_sync(0xffffffffu, bm, src);
-            const double Eb = Ef - w;
-            if (Eb <= bestE) {
-                int len = depth;
-                if (lane == 0) {
-                    uint64_t mm = mask;
-                    int l2 = depth;
-                    while (mm) { path[l2++] = TT[lb + ctz64(mm)]; mm &= mm - 1; }
-                }
-                len = depth + popc64(mask);
-                __syncwarp();
-                try_best(Eb, len);
-            }
+            double w;
+            const int sz = level_b_pick(bw, bm, TT + lb, path, depth, lane, &w);
+            try_best(Ef - w, depth + sz);
         }
         return 1;
     };
