@@ -153,3 +153,21 @@ def test_per_site_api_matches_one_shot():
     assert sizes == one['states_per_site']
     assert SM.energy_gs == pytest.approx(one['energy'], rel=1e-12)
     os.unlink(f.name)
+
+
+@pytest.mark.parametrize('kind,k', [('tfim8', 2), ('heisenberg6', 2), ('cluster7', 3), ('tfim8', 4)])
+def test_structured_chains_vs_oracle(kind, k):
+    """degenerate, commuting-heavy chains through the DP: exact ties must be broken like the oracle does"""
+    import test_gpu_sparse as TS
+    S = sgs()
+    text = TS._structured(kind)
+    n = int(text.split()[0])
+    text = f"{n} {k}\n" + text.split('\n', 1)[1]
+    ref = O.klocal(text=text, threads=2)
+    r = S.klocal_search(S.HamHandle.from_text(text))
+    assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12)
+    assert r['generators'] == ref['generators']
+    assert r['term_signs'] == ref['term_signs']
+    assert r['sright_counts'] == ref['sright_counts'] and r['states_per_site'] == ref['states_per_site']
+    sp = S.sparse_search(S.HamHandle.from_text(text))
+    assert sp['energy'] == pytest.approx(r['energy'], rel=1e-10, abs=1e-12)

@@ -142,6 +142,54 @@ def test_virtual_shards_partition_the_search():
         assert best['energy'] == full['energy'] and best['generators'] == full['generators']
 
 
+def _structured(kind):
+    """small structured (non-random) Hamiltonians: many commuting terms, dependent products, degenerate weights"""
+    lines = []
+    if kind == 'tfim8':                       # transverse-field Ising chain
+        n = 8
+        lines += [f"-1.0 ZZ {i} {i + 1}" for i in range(n - 1)] + [f"-0.7 X {i}" for i in range(n)]
+    elif kind == 'heisenberg6':               # XXX chain: XX, YY, ZZ on every bond (XX*YY = -ZZ: dependent members)
+        n = 6
+        for i in range(n - 1):
+            lines += [f"{w} {p}{p} {i} {i + 1}" for p, w in (('X', 1.0), ('Y', 1.0), ('Z', 1.0))]
+    elif kind == 'cluster7':                  # cluster-state stabilizers plus fields
+        n = 7
+        lines += [f"-1.0 ZXZ {i} {i + 1} {i + 2}" for i in range(n - 2)] + [f"0.3 Z {i}" for i in range(n)]
+    elif kind == 'zonly9':                    # all terms commute: one clique, ranks up to n, dependent Z strings
+        n = 9
+        import random
+        rnd = random.Random(5)
+        seen = set()
+        while len(lines) < 16:
+            sites = sorted(rnd.sample(range(n), rnd.randint(1, 4)))
+            if tuple(sites) in seen:
+                continue
+            seen.add(tuple(sites))
+            lines.append(f"{rnd.uniform(-1, 1):.6f} {'Z' * len(sites)} {' '.join(map(str, sites))}")
+    elif kind == 'toric2x2':                  # plaquette / star operators of a small torus (commuting, dependent) + fields
+        n = 8
+        stars = [(0, 1, 4, 6), (0, 1, 5, 7), (2, 3, 4, 6), (2, 3, 5, 7)]
+        plaqs = [(0, 2, 4, 5), (1, 3, 4, 5), (0, 2, 6, 7), (1, 3, 6, 7)]
+        lines += [f"-1.0 XXXX {' '.join(map(str, q))}" for q in stars] + [f"-1.0 ZZZZ {' '.join(map(str, q))}" for q in plaqs]
+        lines += [f"0.25 Z {i}" for i in range(0, n, 2)]
+    return f"{n} {n}\n" + "".join(" " + l + "\n" for l in lines)
+
+
+@pytest.mark.parametrize('kind', ['tfim8', 'heisenberg6', 'cluster7', 'zonly9', 'toric2x2'])
+@pytest.mark.parametrize('depth', [0, 1])
+def test_structured_hamiltonians_vs_oracle(kind, depth):
+    """SURVEY §8(f)4 territory: commuting-heavy instances where most groups contain dependent terms (exact kernel,
+    entangled sign variables, degenerate energies)."""
+    S = sgs()
+    text = _structured(kind)
+    ref = O.sparse(text=text)
+    r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=depth)
+    assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12)
+    assert r['candidates'] == ref['candidates']
+    assert r['generators'] == ref['generators']
+    assert r['term_signs'] == ref['term_signs']
+
+
 @pytest.mark.parametrize('retry_cap', [None, '8'])
 @pytest.mark.parametrize('n,T,seed,worlds', [(18, 110, 5, (2, 5)), (24, 300, 0, (8,))])
 def test_multi_round_walk_hand_off(monkeypatch, retry_cap, n, T, seed, worlds):
