@@ -79,7 +79,10 @@ typedef struct {
                                 shard's only (no collective).                                  */
     int verbose;             /* klocal: -v level (cpp/klocal_sparse.cpp:10)                    */
     int expand_depth;        /* sparse: force the prefix depth handed to the DFS kernel; 0=auto */
-    int reserved[8];
+    int prune;               /* sparse: 1 = branch and bound: subtrees that cannot reach the best
+                                energy found so far are skipped.  Same energy, generators and term signs as the
+                                exhaustive search (ties included); `candidates` then counts the visited groups only */
+    int reserved[7];
 } sgs_opts;
 void sgs_opts_default(sgs_opts *o);
 

@@ -26,8 +26,8 @@ class SgsError(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [('device', C.c_int), ('ngpus', C.c_int), ('rank', C.c_int), ('world', C.c_int),
-                ('nccl_id', C.c_void_p), ('verbose', C.c_int), ('expand_depth', C.c_int),
-                ('reserved', C.c_int * 8)]
+                ('nccl_id', C.c_void_p), ('verbose', C.c_int), ('expand_depth', C.c_int), ('prune', C.c_int),
+                ('reserved', C.c_int * 7)]
 
 
 class Result(C.Structure):
@@ -121,10 +121,11 @@ def check(rc):
         raise SgsError(rc, (lib().sgs_last_error() or b'').decode())
 
 
-def make_opts(device=0, ngpus=1, rank=0, world=1, nccl_id=None, verbose=0, expand_depth=0):
+def make_opts(device=0, ngpus=1, rank=0, world=1, nccl_id=None, verbose=0, expand_depth=0, prune=0):
     o = Opts()
     lib().sgs_opts_default(C.byref(o))
     o.device, o.ngpus, o.rank, o.world, o.verbose, o.expand_depth = device, ngpus, rank, world, verbose, expand_depth
+    o.prune = int(prune)
     keep = None
     if nccl_id is not None:
         keep = C.create_string_buffer(bytes(nccl_id), SGS_NCCL_ID_BYTES)

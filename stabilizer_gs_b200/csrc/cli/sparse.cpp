@@ -1,5 +1,6 @@
 // cli/sparse.cpp — drop-in for the reference's `./sparse <file>` (cpp/sparse.cpp:4-18): same stdout.
-// Extra flags (ours): --gpus N, --device D, --expand-depth K, --stats (one JSON line on stderr).
+// Extra flags (ours): --gpus N, --device D, --expand-depth K, --stats (one JSON line on stderr), --prune (branch and
+// bound: same printed result, only the groups that could still beat the incumbent are visited).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,9 +29,10 @@ int main(int argc, char **argv)
         else if (a == "--device" && i + 1 < argc) opts.device = atoi(argv[++i]);
         else if (a == "--expand-depth" && i + 1 < argc) opts.expand_depth = atoi(argv[++i]);
         else if (a == "--stats") stats = true;
+        else if (a == "--prune") opts.prune = 1;
         else path = a;
     }
-    if (path.empty()) { fprintf(stderr, "usage: %s [--gpus N] [--device D] [--stats] <hamiltonian file>\n", argv[0]); return 2; }
+    if (path.empty()) { fprintf(stderr, "usage: %s [--gpus N] [--device D] [--stats] [--prune] <hamiltonian file>\n", argv[0]); return 2; }
     sgs_ham *H = nullptr;
     if (sgs_ham_load(path.c_str(), 0, 0, &H) != SGS_OK) { fprintf(stderr, "error: %s\n", sgs_last_error()); return 1; }
     sgs_result r;

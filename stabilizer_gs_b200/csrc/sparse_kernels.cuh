@@ -68,11 +68,27 @@ struct SparseDev {
     unsigned int *slow_count;
     unsigned int slow_cap;
     int trace;                   // SGS_TRACE: per-root timing diagnostics into stats->dbg
+    unsigned long long *inc;     // branch-and-bound mode: best energy found so far on this device (order-encoded double)
 };
 
 enum { kErrOverflow = 8, kErrLimit = 6 };
 
 SGS_D unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// order-preserving encoding of a double into an unsigned key (atomicMin on the key = min on the double)
+SGS_D unsigned long long enc_double(double x)
+{
+    const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+SGS_D double dec_double(unsigned long long k)
+{
+    const unsigned long long u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k;
+    return __longlong_as_double((long long)u);
+}
+// pruning threshold of the branch-and-bound mode: a subtree whose energy lower bound exceeds it cannot reach
+// the incumbent, not even tie it (the margin covers the different summation orders of bound and energy)
+SGS_D double prune_threshold(double inc) { return inc >= 1e299 ? 1e300 : inc + 1e-9 * (1.0 + fabs(inc)); }
+
 SGS_D uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
 // lexicographic order on generating tuples with "end of tuple" sorting last: the order in which the
@@ -415,6 +431,7 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
                 slowNodes++;
                 if (!haveBest || E < bestE || (E == bestE && tuple_before(g, m, bestG, bestM))) {
                     haveBest = 1; bestE = E; bestM = m;
+                    if (D.inc && lane == 0) atomicMin(D.inc, enc_double(E));
                     __syncwarp();
                     for (int i = lane; i < m; i += 32) bestG[i] = g[i];
                     __syncwarp();
@@ -532,7 +549,8 @@ __host__ __device__ inline size_t dfs_smem_bytes(int cap)
     b += (size_t)(kMaxG + 1) * 4 + 4;  // hist
     b += (size_t)cap * 2;              // term indices
     b += (size_t)kMaxG * 2 * 2;        // path, best tuple
-    b += 32;                           // basis pivots
+    b += 64;                           // basis pivots
+    b += 64 * 8 + 8;                   // suffix sums of the candidate weights (branch-and-bound mode), 8-byte aligned
     return (b + 15) & ~(size_t)15;
 }
 
@@ -591,8 +609,11 @@ SGS_D int popc_mask(uint64_t v) { return __popcll(v); }
 // than dealing by the lowest vertex — plus the singleton {l}.  Counts candidates per rank in hc[], keeps the
 // heaviest maximal clique; within a lane the first found wins ties (= lexicographic order, a longer tuple
 // before its prefix); lanes are ordered afterwards by (first vertex, second vertex).
-template <typename M>
-SGS_D void lb_walk(const M *ADm, const double *WAc, int ncand, int depth, uint32_t *hc, double &bw, M &bm, M dn0, M dn1, int lane)
+// PRUNE (branch and bound): SW[v] = sum of the weights of the vertices >= v; a branch whose best conceivable
+// weight (current + every vertex from its lowest remaining candidate on) stays below `need` is not entered.
+template <typename M, bool PRUNE>
+SGS_D void lb_walk(const M *ADm, const double *WAc, int ncand, int depth, uint32_t *hc, double &bw, M &bm, M dn0, M dn1, int lane,
+                   const double *SW, double need)
 {
     M cand[kMaxLB], cm[kMaxLB];
     double ws[kMaxLB];
@@ -618,6 +639,8 @@ SGS_D void lb_walk(const M *ADm, const double *WAc, int ncand, int depth, uint32
             const double nw = ws[d] + WAc[v];
             if (nc == 0) {
                 if (nw > bw) { bw = nw; bm = cm[d] | ((M)1 << v); }
+            } else if (PRUNE && nw + SW[ctz_mask(nc)] < need) {
+                // nothing below can reach the incumbent; the clique itself cannot either (it is lighter still)
             } else {
                 hc[depth + 3 + d] += popc_mask(nc);
                 cm[d + 1] = cm[d] | ((M)1 << v);
@@ -645,9 +668,9 @@ SGS_D float expected_cliques(int n, int e)
 
 // (not inlined: it is called from two places of k_dfs and a single copy keeps the hot loops inside the
 //  instruction cache)
-template <int W>
+template <int W, bool PRUNE>
 __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, int n, int nlow, int depth,
-                  uint32_t *hc, double &bw, uint64_t &bm, int lane, float split_cliques)
+                  uint32_t *hc, double &bw, uint64_t &bm, int lane, float split_cliques, double *SW, double need)
 {
     // 1. independence of ALL n residues (lower-index entries included: a dependency through one of them would
     //    make a later child non-canonical).  Own rows: entries lane and lane + 32; step u broadcasts the
@@ -788,6 +811,20 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
     //    owns vertices lane and lane + 32, keeps the higher-numbered neighbours (cliques grow upward)
     const int ncand = n - nlow;
     const uint64_t *Rc = R + (size_t)nlow * W;
+    if (PRUNE) {
+        // certified: below this frame members = generators, so no group can weigh more than all candidates
+        // together.  Suffix sums of the candidate weights (warp scan), then the frame-level bound.
+        double x1 = lane + 32 < ncand ? WA[nlow + lane + 32] : 0.0, x0 = lane < ncand ? WA[nlow + lane] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y1 = __shfl_down_sync(0xffffffffu, x1, o), y0 = __shfl_down_sync(0xffffffffu, x0, o);
+            if (lane + o < 32) { x1 += y1; x0 += y0; }
+        }
+        x0 += __shfl_sync(0xffffffffu, x1, 0);
+        if (__shfl_sync(0xffffffffu, x0, 0) < need) return 1;          // the whole frame is out of reach
+        SW[lane] = x0; SW[lane + 32] = x1;
+        __syncwarp();
+    }
     if (ncand <= 32) {
         uint64_t sc[W];
 #pragma unroll
@@ -809,7 +846,7 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         if (lane < ncand) AD32[lane] = up32;
         __syncwarp();
         uint32_t bm32 = 0;
-        lb_walk<uint32_t>(AD32, WA + nlow, ncand, depth, hc, bw, bm32, a32 & ((1u << lane) - 1u), 0u, lane);
+        lb_walk<uint32_t, PRUNE>(AD32, WA + nlow, ncand, depth, hc, bw, bm32, a32 & ((1u << lane) - 1u), 0u, lane, SW, need);
         bm = (uint64_t)bm32 << nlow;
     } else {
         uint64_t sc0[W], sc1[W];
@@ -838,7 +875,8 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         if (lane + 32 < ncand) AD[lane + 32] = up1;
         __syncwarp();
         uint64_t bmr = 0;
-        lb_walk<uint64_t>(AD, WA + nlow, ncand, depth, hc, bw, bmr, a0 & ((1ULL << lane) - 1ULL), a1 & ((1ULL << (lane + 32)) - 1ULL), lane);
+        lb_walk<uint64_t, PRUNE>(AD, WA + nlow, ncand, depth, hc, bw, bmr, a0 & ((1ULL << lane) - 1ULL), a1 & ((1ULL << (lane + 32)) - 1ULL), lane, SW,
+                                 need);
         bm = bmr << nlow;
     }
     __syncwarp();
@@ -885,7 +923,7 @@ __device__ __noinline__ int level_b_pick(double bw, uint64_t bm, const uint16_t 
     return popc64(mask);
 }
 
-template <int W, bool SPLIT>
+template <int W, bool SPLIT, bool PRUNE>
 __global__ void __launch_bounds__(256, 3)
 k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned int *item_counter,
       int shard, int nshards, int cap, int smem_per_warp, const unsigned int *nitems_dev, const unsigned int *__restrict__ perm,
@@ -915,7 +953,9 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     uint16_t *TT = (uint16_t *)p;       p += (size_t)cap * 2;
     uint16_t *path = (uint16_t *)p;     p += (size_t)kMaxG * 2;
     uint16_t *bestG = (uint16_t *)p;    p += (size_t)kMaxG * 2;
-    uint8_t *pivB = (uint8_t *)p;
+    uint8_t *pivB = (uint8_t *)p;       p += 64;
+    p = smem_raw + (((size_t)(p - smem_raw) + 7) & ~(size_t)7);
+    double *SW = (double *)p;           // [64] suffix sums of the candidate weights (branch-and-bound mode)
 
     const unsigned gw = blockIdx.x * wpb + warp;
     BestRec *myrec = D.wbest + gw;
@@ -926,9 +966,16 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     __syncwarp();
 
     // record path[0..len) as the best tuple if Eval beats the incumbent (ties: tuple order)
+    double thr = 1e300;                                   // branch and bound: see prune_threshold()
     auto try_best = [&](double Eval, int len) {
         if (Eval > bestE) return;
-        if (best_update(Eval, len, bestE, bestM, bestG, path, lane)) { bestE = Eval; bestM = len; }
+        if (best_update(Eval, len, bestE, bestM, bestG, path, lane)) {
+            bestE = Eval; bestM = len;
+            if (PRUNE) {
+                if (lane == 0) atomicMin(D.inc, enc_double(Eval));
+                thr = fmin(thr, prune_threshold(Eval));
+            }
+        }
     };
 
     uint32_t hc[kMaxG + 4];                              // per-lane candidate counts by rank (level B)
@@ -940,7 +987,8 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     auto run_level_b = [&](int lb, int n, int nlow, int depth, double Ef, float split) -> int {
         double bw = -1.0;
         uint64_t bm = 0;
-        const int rc = level_b<W>(R + lb * W, WA + lb, AD, AD32, n, nlow, depth, hc, bw, bm, lane, split);
+        // a clique of weight w gives the energy Ef - w: it reaches the incumbent iff w >= Ef - thr
+        const int rc = level_b<W, PRUNE>(R + lb * W, WA + lb, AD, AD32, n, nlow, depth, hc, bw, bm, lane, split, SW, Ef - thr);
         if (rc != 1) return rc;
         // does any lane's best clique reach the incumbent?
         const bool cand = bm != 0 && (Ef - bw) <= bestE;
@@ -981,6 +1029,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             troot = tn; tfail = false; tinfo = 0;
         }
         if (it >= nitems) break;
+        if (PRUNE) thr = fmin(prune_threshold(bestE), prune_threshold(dec_double(*(volatile unsigned long long *)D.inc)));
         const uint16_t *rec = items + (size_t)(perm ? perm[it] : it) * D.S;
         const int m0 = rec[0];
         const unsigned flags = rec[1];
@@ -1029,6 +1078,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         if (a < 0) { push_slow(D, path, m0, flags, lane); continue; }
         bool member = false;
         int q0 = 0;
+        double wall = 0.0;                                  // weight of all alive entries (branch-and-bound mode)
         const int core0 = m0 ? (int)path[m0 - 1] : -1;
 #pragma unroll 1
         for (int i = lane; i < a; i += 32) {
@@ -1048,6 +1098,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
 #pragma unroll
             for (int k = 0; k < W; k++) R[i * W + k] = v[k];
             WA[i] = D.wabs[t];
+            if (PRUNE) wall += D.wabs[t];
         }
         __syncwarp();
         if (__any_sync(0xffffffffu, member)) { push_slow(D, path, m0, flags | kFlagUnclean, lane); continue; }
@@ -1055,6 +1106,13 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         for (int d = 16; d > 0; d >>= 1) q0 += __shfl_xor_sync(0xffffffffu, q0, d);
 
         if (lane == 0) hist[m0]++;
+        if (PRUNE) {
+            // every group below contains the root's generators plus alive terms only (as generators or as dependent
+            // members), each worth at most |w|: E >= E0 - sum of all alive weights
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) wall += __shfl_xor_sync(0xffffffffu, wall, d);
+            if (E0 - wall > thr) continue;
+        }
         tinfo = (tround << 20) | ((unsigned)m0 << 14) | ((unsigned)min(a, 127) << 7) | (unsigned)min(a - q0, 127);
         if (q0 >= a) { try_best(E0, m0); continue; }                      // no extension: a leaf
         // (a certified root whose clique walk alone would outlast the rest of a short kernel is split the same way
@@ -1146,6 +1204,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             // pass 2: child list = surviving entries, reduced by the new generator at its pivot bit
             const int pv = row_lowbit<W>(rj);
             int off = cb;
+            double csum = 0.0;                              // weight of the child's list (branch-and-bound mode)
 #pragma unroll 1
             for (int r0 = 0; r0 < a; r0 += 32) {
                 const int i = r0 + lane;
@@ -1167,10 +1226,16 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                     for (int k = 0; k < W; k++) R[pos * W + k] = v[k];
                     TT[pos] = TT[base + i];
                     WA[pos] = WA[base + i];
+                    if (PRUNE) csum += WA[base + i];
                 }
                 off += __popc(bal);
             }
             __syncwarp();
+            if (PRUNE) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, d);
+                if (Ec - csum > thr) { try_best(Ec, depth + 1); continue; }     // (the child itself is still a candidate)
+            }
             if (nal <= 64 && depth + 1 + (nal - nlow) < kMaxG && run_level_b(cb, nal, nlow, depth + 1, Ec, 0.f) == 1) continue;
             // residues pairwise distinct ⇒ every child of this child is a new group whose only members
             // are its generators.  Otherwise the exact kernel expands it.

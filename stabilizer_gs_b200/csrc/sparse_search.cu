@@ -40,6 +40,7 @@ struct DevCtx {
     uint16_t *qA = nullptr, *qB = nullptr, *slow = nullptr, *work = nullptr;
     unsigned int *counters = nullptr;   // [0] next-level count, [1] item counter, [2] slow count, [8..15] root class counts, [16..23] cursors
     unsigned int *perm = nullptr;       // [qcap] heavy-first order of the subtree roots
+    unsigned long long *inc = nullptr;  // branch-and-bound mode: incumbent energy key
     uint16_t *retry[2] = {nullptr, nullptr};   // [retry_cap * S] roots of the 2nd / 3rd k_dfs round (counters[24..27]: count, valid end)
     FinalOut *fin = nullptr;
     int8_t *term_signs = nullptr;
@@ -60,6 +61,14 @@ struct DevCtx {
 
 }  // namespace
 
+
+// order-encoded +1e300 (enc_double in sparse_kernels.cuh): "no incumbent yet" of the branch-and-bound mode
+static const unsigned long long kNoIncumbent = [] {
+    const double x = 1e300;
+    unsigned long long u;
+    memcpy(&u, &x, 8);
+    return u | 0x8000000000000000ULL;
+}();
 
 struct SparsePlan::Impl {
     Hamiltonian H;
@@ -120,6 +129,7 @@ SparseDev SparsePlan::Impl::dev_view(const DevCtx &c) const
     D.wbest = c.wbest; D.stats = c.stats;
     D.slow = c.slow; D.slow_count = c.counters + 2; D.slow_cap = slow_cap;
     D.trace = getenv("SGS_TRACE") ? 1 : 0;
+    D.inc = opts.prune ? c.inc : nullptr;
     return D;
 }
 
@@ -216,6 +226,7 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
     want(&c.work, (size_t)chunk * S);
     want(&c.counters, 32);
     want(&c.perm, qcap);
+    want(&c.inc, 1);
     want(&c.retry[0], (size_t)retry_cap * S);
     want(&c.retry[1], (size_t)retry_cap * S);
     want(&c.fin, 1);
@@ -272,17 +283,25 @@ Status SparsePlan::Impl::launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid
         SGS_CUDA_TRY(cudaMemsetAsync(rc + 1, 0xFF, sizeof(unsigned), st));
         SGS_CUDA_TRY(cudaMemsetAsync(rc + 3, 0xFF, sizeof(unsigned), st));
     }
+    const bool prune = opts.prune != 0;
+#define SGS_DFS(SPL, PRN, ...) k_dfs<W_, SPL, PRN><<<grid, wpb * 32, pw * wpb, st>>>(__VA_ARGS__)
     if (split) {
-        k_dfs<W_, true><<<grid, wpb * 32, pw * wpb, st>>>(D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc,
-                                                         retry_cap, nullptr);
-        k_dfs<W_, true><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap,
-                                                         rc + 1);
-        k_dfs<W_, false><<<grid, wpb * 32, pw * wpb, st>>>(D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3);
+        if (prune) {
+            SGS_DFS(true, true, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc, retry_cap, nullptr);
+            SGS_DFS(true, true, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap, rc + 1);
+            SGS_DFS(false, true, D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3);
+        } else {
+            SGS_DFS(true, false, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc, retry_cap, nullptr);
+            SGS_DFS(true, false, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap, rc + 1);
+            SGS_DFS(false, false, D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3);
+        }
         c.launches += 3;
     } else {
-        k_dfs<W_, false><<<grid, wpb * 32, pw * wpb, st>>>(D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, nullptr);
+        if (prune) SGS_DFS(false, true, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, nullptr);
+        else SGS_DFS(false, false, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, nullptr);
         c.launches++;
     }
+#undef SGS_DFS
     SGS_CUDA_TRY(cudaGetLastError());
     return Status();
 }
@@ -297,6 +316,7 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
     SGS_CUDA_TRY(cudaMemsetAsync(c.wbest, 0, sizeof(BestRec) * c.nwbest, st));
     SGS_CUDA_TRY(cudaMemsetAsync(c.stats, 0, sizeof(SparseStats), st));
     SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, 4 * sizeof(unsigned), st));
+        if (opts.prune) SGS_CUDA_TRY(cudaMemcpyAsync(c.inc, &kNoIncumbent, sizeof(kNoIncumbent), cudaMemcpyHostToDevice, st));
     // root record: the empty group
     std::vector<uint16_t> root(S, 0);
     SGS_CUDA_TRY(cudaMemcpyAsync(c.qA, root.data(), S * 2, cudaMemcpyHostToDevice, st));
@@ -378,12 +398,17 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         const size_t dfs_pw = dfs_smem_bytes<W_>(dfs_cap);
         int dfs_wpb = 8;
         while (dfs_wpb > 1 && dfs_pw * dfs_wpb > 200 * 1024) dfs_wpb >>= 1;
-        SGS_CUDA_TRY(cudaFuncSetAttribute(k_dfs<W_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dfs_pw * dfs_wpb)));
-        SGS_CUDA_TRY(cudaFuncSetAttribute(k_dfs<W_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dfs_pw * dfs_wpb)));
-        int dfs_occ = 1, dfs_occ2 = 1;
-        SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dfs_occ, k_dfs<W_, false>, dfs_wpb * 32, dfs_pw * dfs_wpb));
-        SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dfs_occ2, k_dfs<W_, true>, dfs_wpb * 32, dfs_pw * dfs_wpb));
-        dfs_occ = std::min(dfs_occ, dfs_occ2);
+        int dfs_occ = 1 << 30;
+        {
+            const void *variants[4] = {(const void *)k_dfs<W_, false, false>, (const void *)k_dfs<W_, true, false>,
+                                       (const void *)k_dfs<W_, false, true>, (const void *)k_dfs<W_, true, true>};
+            for (const void *f : variants) {
+                int o = 1;
+                SGS_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dfs_pw * dfs_wpb)));
+                SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, f, dfs_wpb * 32, dfs_pw * dfs_wpb));
+                dfs_occ = std::min(dfs_occ, o);
+            }
+        }
         dfs_occ = std::max(1, dfs_occ);
         const unsigned dfs_maxgrid = (unsigned)std::min<long long>((long long)c.sms * dfs_occ, c.nwbest / dfs_wpb);
         const unsigned grid = std::min<unsigned>(dfs_maxgrid, (count + dfs_wpb - 1) / dfs_wpb);
@@ -494,6 +519,7 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         SGS_CUDA_TRY(cudaMemsetAsync(c.wbest, 0, sizeof(BestRec) * c.nwbest, st));
         SGS_CUDA_TRY(cudaMemsetAsync(c.stats, 0, sizeof(SparseStats), st));
         SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, 4 * sizeof(unsigned), st));
+        if (opts.prune) SGS_CUDA_TRY(cudaMemcpyAsync(c.inc, &kNoIncumbent, sizeof(kNoIncumbent), cudaMemcpyHostToDevice, st));
         SGS_CUDA_TRY(cudaMemsetAsync(c.qA, 0, (size_t)S * 2, st));          // root record: the empty group
         SGS_CUDA_TRY(cudaEventRecord(c.ev0, st));
         uint16_t *cur = c.qA, *nxt = c.qB;

@@ -190,6 +190,41 @@ def test_structured_hamiltonians_vs_oracle(kind, depth):
     assert r['term_signs'] == ref['term_signs']
 
 
+@pytest.mark.parametrize('case', ['r10', 'r16', 'r20', 'w2', 'ties', 'tfim8', 'heisenberg6', 'zonly9', 'toric2x2'])
+def test_branch_and_bound_returns_the_exhaustive_answer(case):
+    """opts.prune: subtrees that cannot reach the incumbent are skipped — energy, generators and term signs are those
+    of the exhaustive search (exact ties included), on one shard and on virtual shards; fewer groups are visited."""
+    S = sgs()
+    if case.startswith('r'):
+        n = int(case[1:])
+        text = G.sparse_text(n, {10: 34, 16: 70, 20: 130}[n], 3)
+    elif case == 'w2':
+        text = G.sparse_text(36, 90, 2)
+    elif case == 'ties':
+        import random
+        rnd = random.Random(11)
+        lines = set()
+        while len(lines) < 40:
+            lines.add(''.join(rnd.choice('IXYZ') for _ in range(8)))
+        lines.discard('I' * 8)
+        text = "8 8\n" + "".join(f" {rnd.choice([-1.0, -0.5, 0.5, 1.0])} {p} {' '.join(map(str, range(8)))}\n" for p in sorted(lines))
+    else:
+        text = _structured(case)
+    H = S.HamHandle.from_text(text)
+    full = S.sparse_search(H)
+    for depth in (0, 1):
+        r = S.sparse_search(H, prune=1, expand_depth=depth)
+        assert r['energy'] == full['energy'] and r['generators'] == full['generators'] and r['term_signs'] == full['term_signs']
+        assert r['candidates'] <= full['candidates']
+    parts = [S.sparse_search(H, prune=1, rank=k, world=3) for k in range(3)]
+    best = min(parts, key=lambda p: p['energy'])
+    assert best['energy'] == full['energy']
+    plan = S.SparsePlan(H, prune=1)
+    a, b = plan.run(), plan.run()
+    plan.close()
+    assert (a['energy'], a['generators']) == (b['energy'], b['generators']) == (full['energy'], full['generators'])
+
+
 @pytest.mark.parametrize('retry_cap', [None, '8'])
 @pytest.mark.parametrize('n,T,seed,worlds', [(18, 110, 5, (2, 5)), (24, 300, 0, (8,))])
 def test_multi_round_walk_hand_off(monkeypatch, retry_cap, n, T, seed, worlds):
