@@ -52,7 +52,9 @@ def test_config3_golden():
 
 
 @pytest.mark.parametrize('n,k,per,seed', [(8, 2, 2, 0), (10, 3, 2, 1), (10, 3, 3, 2), (12, 4, 2, 3), (9, 4, 4, 4), (14, 3, 3, 5),
-                                          (8, 4, 6, 3), (16, 5, 2, 6), (20, 4, 3, 7), (6, 6, 5, 8), (12, 1, 2, 9)])
+                                          (8, 4, 6, 3), (16, 5, 2, 6), (20, 4, 3, 7), (6, 6, 5, 8), (12, 1, 2, 9),
+                                          (10, 7, 2, 1), (12, 8, 3, 3), (14, 10, 2, 4), (9, 9, 4, 5), (24, 6, 3, 6), (12, 8, 6, 7),
+                                          (16, 7, 5, 8), (18, 12, 3, 9), (20, 15, 2, 10)])
 def test_random_vs_oracle(n, k, per, seed):
     S = sgs()
     per = min(per, 4 ** k - 1)
