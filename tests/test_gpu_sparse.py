@@ -235,6 +235,7 @@ def test_multi_round_walk_hand_off(monkeypatch, retry_cap, n, T, seed, worlds):
     S = sgs()
     H = S.HamHandle.from_text(G.sparse_text(n, T, seed))
     full = S.sparse_search(H)
+    monkeypatch.setenv('SGS_SPLIT', '1')          # (the rounds are switched on from 5 shards by default)
     if retry_cap:
         monkeypatch.setenv('SGS_RETRY_CAP', retry_cap)
     for world in worlds:
