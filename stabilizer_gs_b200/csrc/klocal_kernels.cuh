@@ -7,13 +7,18 @@
 // (cpp/state.cpp:129-216).
 //
 // Design (not a port): every object a DP step touches lives on at most 2k sites, so all rows are ONE u64
-// relative to the step's origin o_m = m - k + 1 (site s at bits 2(s-o), 2(s-o)+1).  One thread owns one
-// state / one right-environment group; the 2^rank sign tables and their back-pointers live in a per-state
-// global scratch slab.  Instead of the reference's per-entry history arrays (2n ints per table entry,
-// cpp/stab.cpp:752-759) every table entry keeps one back-pointer (parent state, parent entry, signs of the
-// generators added at this site); the generator list is recovered by a traceback at the end.
+// relative to the step's origin o_m = m - k + 1 (site s at bits 2(s-o), 2(s-o)+1).  The DP is latency-bound, so
+// the whole of it runs in two persistent cooperative kernels (k_sr_run: right environments of every site,
+// k_dp_run: any number of consecutive site steps) whose phases are separated by grid barriers and whose batch
+// sizes live in a device control block — no host round trip and no kernel boundary inside the site loop.
+// One warp owns one state (generator rows replicated per lane, the 2^rank sign table and its back-pointers
+// split across the lanes, in a per-state global slab); one thread owns one right-environment branch.
+// Instead of the reference's per-entry history arrays (2n ints per table entry, cpp/stab.cpp:752-759) every
+// table entry keeps one back-pointer (parent state, parent entry, signs of the generators added at this site)
+// in a history pool; the generator list is recovered by a device traceback at the end.
 // The reference's keyed merge (std::map on a boost hash + omp critical, cpp/state.cpp:494-517) becomes a
-// deterministic group-by-full-key with "later in (parent, child) order wins exact ties" = its strict '<'.
+// generation-tagged open-addressing table (claim by CAS, lowest entry per key by atomicMin, children of a key on a
+// linked list), keys ranked in full-key order, and "later in (parent, child) order wins exact ties" = its strict '<'.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -337,10 +342,9 @@ SGS_D int key_cmp(const DpGroup &a, const DpGroup &b)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Right environments.  k_sr_evolve: evolve_stab (cpp/state.cpp:147-185) for one parent group per thread:
-// include/exclude branching over the terms whose last site is m, widen one site to the left, project onto
-// the k sites ending at m (Stab::project, cpp/stab.cpp:524-577).  Children are written to out[parent *
-// maxbranch + b] relative to origin o_m.
+// Right environments: evolve_stab (cpp/state.cpp:147-185) = include/exclude branching over the terms whose last
+// site is m, widen one site to the left, project onto the k sites ending at m (Stab::project,
+// cpp/stab.cpp:524-577).  A branch carries the group at origin o_m, the exclusion mask and its parent group.
 struct SrBranch { uint64_t g[kDpRows]; int q[kDpRows]; int r; uint32_t excl; int par; };
 
 SGS_D void signed_add(uint64_t *g, int *q, int &r, uint64_t P, int qP)     // Stab::add: RREF with signs
