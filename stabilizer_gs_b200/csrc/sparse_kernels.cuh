@@ -24,7 +24,13 @@
 //                 generator's residue at its pivot bit, __ballot_sync compaction, __match_any_sync
 //                 duplicate-residue detection.  While residues stay pairwise distinct no term outside
 //                 the generating set can enter the group, so E_min = -sum |w_g| exactly; the first
-//                 duplicate hands that node to k_general.
+//                 duplicate hands that node to k_general.  Once a list has <= 64 entries the warp proves by
+//                 Gaussian elimination that no dependent term can appear anywhere below it (level_b); the
+//                 subtree is then the set of cliques of the candidates' commutation graph, walked by the
+//                 lanes independently with bit masks (lb_walk).  Template flags: SPLIT (multi-shard runs:
+//                 heavy or uncertifiable roots hand their children to a next round), PRUNE (optional
+//                 branch and bound against a device-wide incumbent).
+//   k_class_count / k_class_scatter : heavy-first order of the subtree roots (multi-shard runs).
 //   k_reduce_best / k_finalize : deterministic argmin over per-warp records, then canonical RREF with
 //                 sign tracking, per-term signs and the reference's first-minimum sign pattern.
 #pragma once
