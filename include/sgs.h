@@ -129,6 +129,10 @@ int sgs_klocal_search(const sgs_ham *h, const sgs_opts *opts, sgs_result *out);
 
 /* Finer-grained DP handle for the periodic driver (py/klocal_periodic.py):
  * generate_Sright_all / generate_Sright_periodic + StateMachine / StateMachinePeriodic. */
+/* Site steps are enqueued on the device without a host round trip; errors met on the device (a limit, or a batch
+ * that outgrew the handle's buffers: SGS_ERR_OVERFLOW) surface at the next call that synchronises — nstates
+ * (which then returns -1), ground_state, or the next evolve.  sgs_klocal_search / sgs_klocal_periodic redo the
+ * search with larger buffers by themselves; with this stepwise handle the caller sees the error. */
 int sgs_klocal_create(const sgs_ham *h, const sgs_opts *opts, int periodic_cmax, sgs_klocal **out);
 void sgs_klocal_free(sgs_klocal *k);
 int sgs_klocal_m(const sgs_klocal *k);                 /* StateMachine.m                          */
