@@ -189,6 +189,7 @@ Status KlocalMachine::Impl::init()
     SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dp, k_dp_run, 256, 0));
     SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_sr_run, 256, 0));
     if (!coop || occ_dp < 1 || occ_sr < 1) return Status::fail(SGS_ERR_CUDA, "device cannot co-schedule the persistent DP kernels");
+    if (const char *v = getenv("SGS_DP_GRID")) if (atoi(v) > 0) nsm = std::min(nsm, atoi(v));     // persistent grid size (experiments)
     SGS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     SGS_CUDA_TRY(cudaEventCreate(&e0));
     SGS_CUDA_TRY(cudaEventCreate(&e1));
