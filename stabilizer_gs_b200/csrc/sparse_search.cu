@@ -216,21 +216,22 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
     want(&c.wabs, Tn);
     want(&c.order, Tn);
     want(&c.wbest, c.nwbest);
-    want(&c.gbest, 1);
     want(&c.allbest, std::max(nshards, 1));
-    want(&c.stats, 1);
     want(&c.hist_sum, kMaxG + 2);
     want(&c.qA, (size_t)qcap * S);
     want(&c.qB, (size_t)qcap * S);
     want(&c.slow, (size_t)slow_cap * S);
     want(&c.work, (size_t)chunk * S);
-    want(&c.counters, 32);
     want(&c.perm, qcap);
     want(&c.inc, 1);
     want(&c.retry[0], (size_t)retry_cap * S);
     want(&c.retry[1], (size_t)retry_cap * S);
+    // result span: everything the host reads after a search, contiguous so that one copy fetches it
     want(&c.fin, 1);
     want(&c.term_signs, Tn);
+    want(&c.stats, 1);
+    want(&c.gbest, 1);
+    want(&c.counters, 32);
     want(&c.memX, Tn);
     want(&c.memA, Tn);
     want(&c.memT, Tn);
@@ -583,14 +584,10 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         c0.launches++;
         SGS_CUDA_TRY(cudaGetLastError());
     }
-    FinalOut fo;
-    std::vector<int8_t> ts(std::max(T, 1));
-    unsigned hcnt[4] = {0, 0, 0, 0};
-    SGS_CUDA_TRY(cudaMemcpyAsync(&fo, c0.fin, sizeof(FinalOut), cudaMemcpyDeviceToHost, c0.stream));
-    SGS_CUDA_TRY(cudaMemcpyAsync(ts.data(), c0.term_signs, std::max(T, 1), cudaMemcpyDeviceToHost, c0.stream));
-    SGS_CUDA_TRY(cudaMemcpyAsync(&c0.hstats, c0.stats, sizeof(SparseStats), cudaMemcpyDeviceToHost, c0.stream));
-    SGS_CUDA_TRY(cudaMemcpyAsync(&c0.hbest, c0.gbest, sizeof(BestRec), cudaMemcpyDeviceToHost, c0.stream));
-    SGS_CUDA_TRY(cudaMemcpyAsync(hcnt, c0.counters, sizeof(hcnt), cudaMemcpyDeviceToHost, c0.stream));
+    // one device-to-host copy of the result span (FinalOut, term signs, statistics, best record, counters)
+    const size_t span = (size_t)((const char *)(c0.counters + 4) - (const char *)c0.fin);
+    std::vector<char> hostspan(span);
+    SGS_CUDA_TRY(cudaMemcpyAsync(hostspan.data(), c0.fin, span, cudaMemcpyDeviceToHost, c0.stream));
     for (auto &c : devs) { SGS_CUDA_TRY(cudaSetDevice(c.device)); SGS_CUDA_TRY(cudaEventRecord(c.ev1, c.stream)); }
     float msd = 0.f, msh = 0.f;
     unsigned launches = 0;
@@ -602,6 +599,14 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         SGS_CUDA_TRY(cudaEventElapsedTime(&b, c.evh0, c.evh1));
         msd = std::max(msd, a); msh = std::max(msh, b); launches += c.launches;
     }
+    FinalOut fo;
+    std::vector<int8_t> ts(std::max(T, 1));
+    unsigned hcnt[4] = {0, 0, 0, 0};
+    memcpy(&fo, hostspan.data(), sizeof(FinalOut));
+    memcpy(ts.data(), hostspan.data() + ((const char *)c0.term_signs - (const char *)c0.fin), std::max(T, 1));
+    memcpy(&c0.hstats, hostspan.data() + ((const char *)c0.stats - (const char *)c0.fin), sizeof(SparseStats));
+    memcpy(&c0.hbest, hostspan.data() + ((const char *)c0.gbest - (const char *)c0.fin), sizeof(BestRec));
+    memcpy(hcnt, hostspan.data() + ((const char *)c0.counters - (const char *)c0.fin), sizeof(hcnt));
     if (getenv("SGS_TRACE")) {
         float e1 = 0, e2 = 0, e3 = 0, e4 = 0, e5 = 0;
         cudaEventElapsedTime(&e1, c0.ev0, c0.evh0); cudaEventElapsedTime(&e2, c0.evh0, c0.evh1); cudaEventElapsedTime(&e3, c0.evh1, c0.evA);
