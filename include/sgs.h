@@ -115,6 +115,9 @@ void sgs_result_free(sgs_result *r);     /* frees the buffers inside *r (not r i
 
 /* FullState(paulis).evolve() (cpp/state.cpp:555-564,636-687; py/state.py:88-147) + the
  * per-term signs of cpp/sparse.cpp:13-16.  Runs entirely on the GPU(s). */
+/* With opts.world > 1 and no nccl_id the call returns the result of shard opts.rank alone (counts add up over
+ * the ranks, the minimum over the ranks is the global answer); a shard that owns no candidate returns
+ * energy = +inf and m = 0. */
 int sgs_sparse_search(const sgs_ham *h, const sgs_opts *opts, sgs_result *out);
 
 /* Device-resident variant for repeated searches: upload once, search many times. */

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -101,6 +102,7 @@ struct SparsePlan::Impl {
     template <int W_> Status finalize(DevCtx &c, const BestRec *host_best, sgs_result *out);
     template <int W_> Status run_replay(sgs_result *out);
     void fill_stats(const SparseStats &tot, sgs_result *out);
+    void fill_empty(const SparseStats &tot, sgs_result *out);
     Status run(sgs_result *out);
     SparseDev dev_view(const DevCtx &c) const;
 };
@@ -509,6 +511,18 @@ void SparsePlan::Impl::fill_stats(const SparseStats &tot, sgs_result *out)
     out->slow_nodes = tot.slow_nodes;
 }
 
+// result of a shard (rank of a world without communicator) that owns no candidate: energy +inf, no generator
+void SparsePlan::Impl::fill_empty(const SparseStats &tot, sgs_result *out)
+{
+    const int Wout = (2 * n + 63) / 64;
+    out->energy = HUGE_VAL;
+    out->n = n; out->m = 0; out->W = Wout; out->T = T;
+    out->gens = (uint64_t *)calloc((size_t)Wout, 8);
+    out->gen_signs = (int8_t *)calloc(1, 1);
+    out->term_signs = (int8_t *)calloc(std::max(T, 1), 1);
+    fill_stats(tot, out);
+}
+
 template <int W_>
 Status SparsePlan::Impl::run_replay(sgs_result *out)
 {
@@ -619,6 +633,12 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         fprintf(stderr, "  longest root: round %llu, rank %llu, alive %llu, candidates %llu, certified %d\n", (g[7] >> 21) & 7, (g[7] >> 15) & 63,
                 (g[7] >> 8) & 127, (g[7] >> 1) & 127, (int)!(g[7] & 1));
     }
+    if (!c0.hstats.error && hcnt[2] == 0 && !c0.hbest.valid && nshards > 1 && !nccl) {
+        fill_empty(c0.hstats, out);
+        out->seconds_device = msd * 1e-3; out->seconds_hot_kernel = msh * 1e-3; out->kernel_launches = launches;
+        out->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return Status();
+    }
     if (c0.hstats.error || hcnt[2] != 0 || !c0.hbest.valid || fo.error) {
         rp.ok = false;      // should not happen (the sequence is deterministic); fall back to the adaptive path
         return Status::fail(SGS_ERR_CUDA, "sparse search: replayed launch sequence diverged from the recorded run");
@@ -706,7 +726,14 @@ Status SparsePlan::Impl::run(sgs_result *out)
             (void)b;
         }
     }
-    if (!best.valid) return Status::fail(SGS_ERR_CUDA, "sparse search produced no candidate");
+    if (!best.valid) {
+        if (nshards > 1 && !nccl) {          // a shard without communicator that owns no candidate: empty result
+            fill_empty(tot, out);
+            out->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            return Status();
+        }
+        return Status::fail(SGS_ERR_CUDA, "sparse search produced no candidate");
+    }
 
     DevCtx &c0 = devs[0];
     Status s;

@@ -256,6 +256,19 @@ def test_multi_round_walk_hand_off(monkeypatch, retry_cap, n, T, seed, worlds):
             assert best['energy'] == full['energy'] and best['generators'] == full['generators']
 
 
+def test_shard_without_candidates_is_empty_not_an_error():
+    """a tiny instance split over more virtual shards than it has groups: the empty shards return energy = +inf"""
+    S = sgs()
+    text = "2 2\n 1.0 ZZ 0 1\n -0.5 XX 0 1\n"
+    H = S.HamHandle.from_text(text)
+    full = S.sparse_search(H)
+    parts = [S.sparse_search(H, rank=r, world=8) for r in range(8)]
+    assert sum(p['candidates'] for p in parts) == full['candidates']
+    assert any(p['candidates'] == 0 and p['energy'] == float('inf') and p['m'] == 0 for p in parts)
+    best = min(parts, key=lambda p: p['energy'])
+    assert best['energy'] == full['energy'] and best['generators'] == full['generators']
+
+
 def _check_invariants(S, text, r):
     H = S.HamHandle.from_text(text)
     rows, w, b, e = H.terms()
