@@ -41,6 +41,28 @@ while time.time() - t0 < budget:
         if sum(p['candidates'] for p in parts) != ref['candidates'] or best['generators'] != ref['generators']:
             bad += 1
             print('MISMATCH shards', n, T, seed, world, sum(p['candidates'] for p in parts), ref['candidates'], flush=True)
+    elif rnd.random() < 0.1:
+        # periodic cell: l sites per period, terms of span <= k starting inside the cell
+        l, k = rnd.choice([1, 2]), rnd.choice([2, 3])
+        lines = []
+        for st in range(l):
+            for _ in range(rnd.randint(1, 2)):
+                length = rnd.randint(1, k)
+                letters = rnd.choice('XYZ') + ''.join(rnd.choice('IXYZ') for _ in range(length - 2)) + (rnd.choice('XYZ') if length > 1 else '')
+                lines.append(f" {rnd.uniform(-1, 1):.6f} {letters} {' '.join(str(st + j) for j in range(length))}")
+        text = f"{l} {k}\n" + "\n".join(sorted(set(lines))) + "\n"
+        path = f"/tmp/fuzz_periodic_{os.getpid()}.txt"
+        open(path, 'w').write(text)
+        try:
+            ref = O.periodic(path, cmax=8, c=2)
+            r = S.klocal_periodic(path, cmax=8, c=2)
+            key = lambda o: (round(o['energy'], 9), o['begin'], o['end'], o['generators'])
+            if r['sright_log'] != ref['sright_log'] or r['fixed_point_sizes'] != ref['fixed_point_sizes'] or \
+               sorted(map(key, r['results'])) != sorted(map(key, ref['results'])):
+                bad += 1
+                print('MISMATCH periodic', repr(text), flush=True)
+        except Exception as e:       # both sides must agree on what is rejected
+            print('periodic exception', repr(text), e, flush=True)
     else:
         k = rnd.randint(1, 8)
         n = rnd.randint(k, k + 14)
