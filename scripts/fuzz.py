@@ -21,11 +21,15 @@ def same(a, b, keys):
 
 while time.time() - t0 < budget:
     seed = rnd.randrange(1 << 30)
-    if rnd.random() < 0.6:
-        n = rnd.choice([3, 4, 5, 6, 8, 10, 12, 14, 16, 33, 36])
-        T = min(rnd.randint(4, 44 if n <= 16 else 30), 4 ** n - 1)
+    if rnd.random() < 0.6 or os.environ.get('FUZZ_MID'):
+        if os.environ.get('FUZZ_MID'):      # mid-size: the level-B certificate / clique walk dominates
+            n = rnd.choice([12, 14, 16, 18, 20, 34])
+            T = rnd.randint(50, 100)
+        else:
+            n = rnd.choice([3, 4, 5, 6, 8, 10, 12, 14, 16, 33, 36])
+            T = min(rnd.randint(4, 44 if n <= 16 else 30), 4 ** n - 1)
         text = G.sparse_text(n, T, seed)
-        ref = O.sparse(text=text, threads=4)
+        ref = O.sparse(text=text, threads=os.cpu_count())
         H = S.HamHandle.from_text(text)
         for kw in ({}, {'expand_depth': rnd.randint(1, 3)}, {'prune': 1}):
             r = S.sparse_search(H, **kw)
