@@ -275,7 +275,7 @@ def main():
             cores = os.cpu_count() or 1
             r = O.sparse_sample(text=text, threads=cores, seconds=12.0)
             line['cpu_baseline'] = dict(value=r['candidates'] / r['seconds'], unit='candidates/s', cores=cores, kind='port',
-                                        sample='12 s wall-time-bounded include-first walk of the same n=24/T=300 instance '
+                                        sample=f'12 s wall-time-bounded include-first walk of the same n={N_QUBITS}/T={N_TERMS} instance '
                                                '(oracle/sparse.c = restatement of FullState::evolve, OpenMP tasks)')
         print(json.dumps(line), flush=True)
     if dist is not None:
