@@ -658,6 +658,35 @@ SGS_D void lb_walk(const M *ADm, const double *WAc, int ncand, int depth, uint32
     }
 }
 
+// Are the n one-word rows (row i in p0 of lane i, row i + 32 in p1 of lane i) linearly DEPENDENT?  Forward
+// elimination across the lanes, two pivots per step so that the shuffle -> lowest bit -> test -> XOR chains of
+// consecutive pivots overlap (the loop is latency-bound).
+SGS_D bool rows_dependent_1w(uint64_t p0, uint64_t p1, int n, int lane)
+{
+    const bool two = n > 32;
+    int u = 0;
+#pragma unroll 1
+    for (; u + 1 < n; u += 2) {
+        const uint64_t c0 = __shfl_sync(0xffffffffu, u < 32 ? p0 : p1, u & 31);
+        uint64_t c1 = __shfl_sync(0xffffffffu, u + 1 < 32 ? p0 : p1, (u + 1) & 31);
+        if (c0 == 0) return true;
+        const uint64_t l0 = c0 & (0 - c0);
+        if (c1 & l0) c1 ^= c0;
+        if (c1 == 0) return true;
+        const uint64_t l1 = c1 & (0 - c1);
+        if (lane > u + 1) {
+            if (p0 & l0) p0 ^= c0;
+            if (p0 & l1) p0 ^= c1;
+        }
+        if (two && lane + 32 > u + 1) {
+            if (p1 & l0) p1 ^= c0;
+            if (p1 & l1) p1 ^= c1;
+        }
+    }
+    if (u < n) return __shfl_sync(0xffffffffu, u < 32 ? p0 : p1, u & 31) == 0;
+    return false;
+}
+
 // expected number of cliques of a graph with n vertices and e edges (edge density p): sum_k C(n,k) p^(k(k-1)/2)
 SGS_D float expected_cliques(int n, int e)
 {
@@ -701,16 +730,12 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
             p0 ^= (e0[k] << rot) | (e0[k] >> (64 - rot));
             p1 ^= (e1[k] << rot) | (e1[k] >> (64 - rot));
         }
-        bool dep = false;
-#pragma unroll 1
-        for (int u = 0; u < n; u++) {
-            const uint64_t cu = __shfl_sync(0xffffffffu, u < 32 ? p0 : p1, u & 31);
-            if (cu == 0) { dep = true; break; }
-            const uint64_t lm = cu & (0 - cu);
-            if (lane > u && (p0 & lm)) p0 ^= cu;
-            if (two && lane + 32 > u && (p1 & lm)) p1 ^= cu;
-        }
+        const bool dep = rows_dependent_1w(p0, p1, n, lane);
         proven = !dep;
+    }
+    if (W == 1) {
+        dependent = rows_dependent_1w(e0[0], e1[0], n, lane);
+        proven = true;
     }
 #pragma unroll 1
     for (int u = 0; u < n && !proven; u++) {
