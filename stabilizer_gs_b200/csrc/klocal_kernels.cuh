@@ -241,7 +241,8 @@ struct DpMoved {
 
 // State::move_to_next + project_to(k-1) (cpp/state.cpp:382-413, :460-466) for one state, by one warp.
 SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const double *inE, int tstride,
-                        const DpGroup *level, DpMoved &mv, double *E, double *tE, DpBack *B, DpBack *tB, DpHistAdd *hist, int *err, int lane)
+                        const DpGroup *level, DpMoved &mv, double *E, double *tE, DpBack *B, DpBack *tB, DpHistAdd *hist, int *err, int lane,
+                        const uint64_t *relw /* shared: rows of the terms from position boff[m] on, relative to o_m */)
 {
     const int k = H.k, o = m - k + 1;
     uint64_t g[kDpRows + 1];
@@ -265,7 +266,7 @@ SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const
     const int b0 = H.boff[m], b1 = H.boff[m + 1];
     int nadd = 0;
     for (int pos = b0; pos < b1; pos++) {
-        const uint64_t P = rel_row(H.rows + (size_t)pos * H.W, H.W, o);
+        const uint64_t P = relw[pos - b0];
         if (ech_reduce(tmp, P) != 0) continue;
         if (!in_rref(sr.g, sr.r, P)) { if (lane == 0) mv.dead = 1; return; }          // cpp/state.cpp:397-399
         if (in_rref(g, r, P)) continue;
@@ -279,7 +280,7 @@ SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const
             const int t = base + lane;
             bool kill = false;
             if (t < nt && vget(valid, t)) {
-                const uint64_t Q = rel_row(H.rows + (size_t)(b0 + t) * H.W, H.W, o);
+                const uint64_t Q = relw[t];
                 for (int i = 0; i < r; i++) kill |= anti(g[i], Q);
             }
             const unsigned km = __ballot_sync(0xffffffffu, kill);
@@ -288,7 +289,7 @@ SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const
     }
     if (lane == 0) { mv.nadd = nadd; hist->nadd = nadd; }
     for (int pos = b0; pos < b1; pos++) {                               // cpp/state.cpp:405-410
-        const uint64_t P = rel_row(H.rows + (size_t)pos * H.W, H.W, o);
+        const uint64_t P = relw[pos - b0];
         if (in_rref(g, r, P)) group_add_energy(g, r, P, H.w[pos], E, lane);
     }
     group_project_site0(g, r, E, B, lane);                              // project_to(k-1), cpp/stab.cpp:803-809 (site o_m; no-op while o_m < 0)
@@ -307,15 +308,15 @@ SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const
 
 // span of the valid terms with last site in [m+1, min(m+k+1, n)) truncated to [max(m-k+2,0), m+2):
 // State::check_Sright_validity (cpp/state.cpp:347-365)
-SGS_D void dp_valid_span(const DpTerms &H, int m, const uint64_t *valid, Ech &e)
+SGS_D void dp_valid_span(const DpTerms &H, int m, const uint64_t *valid, Ech &e, const uint64_t *relw)
 {
-    const int k = H.k, o1 = m - k + 2;                     // origin of level m+1
+    const int k = H.k, b0 = H.boff[m];
     const uint64_t wmask = (2 * k >= 64) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
     e.n = 0;
     const int b1 = H.boff[m + 1], t1 = H.boff[min(m + k + 1, H.n)];
     for (int t = b1; t < t1; t++) {
         if (!vget(valid, t - b1)) continue;
-        ech_add(e, rel_row(H.rows + (size_t)t * H.W, H.W, o1) & wmask);
+        ech_add(e, (relw[t - b0] >> 2) & wmask);             // origin o_{m+1} = o_m + 1; no window term reaches site o_m + 32
     }
 }
 SGS_D bool dp_accepts(const Ech &e, const DpGroup &G)
@@ -605,6 +606,7 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ int part[256];
+    __shared__ uint64_t relw[64 * kDpVW];                    // window terms of the current site, relative to o_m
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, wid = tid >> 5, nw = nth >> 5;
     DpCtl *ctl = B.ctl;
@@ -623,19 +625,27 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
         DpState *outS = B.S[cur ^ 1];
         double *outE = B.E[cur ^ 1];
         if ((long long)hm_off + nin > hm_cap || step >= log_cap) { err = 7; break; }
-        // ---- P0: one warp per state
+        // ---- P0: one warp per state.  Every block first extracts the rows of the window's terms (last site in
+        //      [m, m+k+2)) relative to o_m into shared memory: the serial loops below would otherwise wait for a
+        //      global load per term.
         if (tid == 0) ctl->nuniq = 0;
+        {
+            const int b0 = H.boff[m], nwin = min(H.boff[min(m + k + 2, H.n + 1)] - b0, 64 * kDpVW);
+            __syncthreads();
+            for (int i = threadIdx.x; i < nwin; i += blockDim.x) relw[i] = rel_row(H.rows + (size_t)(b0 + i) * H.W, H.W, m - k + 1);
+            __syncthreads();
+        }
         for (int s = wid; s < nin; s += nw) {
             double *E = B.slabE + (size_t)s * 2 * slab_stride;
             DpBack *Bk = B.slabB + (size_t)s * 2 * slab_stride;
             DpMoved &mv = B.moved[s];
             dp_move_warp(H, m, s, inS[s], inE, tstride, L.groups, mv, E, E + slab_stride, Bk, Bk + slab_stride, B.hm + hm_off + s,
-                         &ctl->err, lane);
+                         &ctl->err, lane, relw);
             __syncwarp();
             int cnt = 0;
             if (!mv.dead) {
                 Ech e;
-                dp_valid_span(H, m, mv.valid, e);
+                dp_valid_span(H, m, mv.valid, e, relw);
                 if (lane == 0) B.span[s] = e;
                 const int j0 = L.map_off[mv.sright], j1 = L.map_off[mv.sright + 1];
                 for (int j = j0 + lane; j < j1; j += 32) cnt += dp_accepts(e, Ln.groups[L.map_idx[j]]);
