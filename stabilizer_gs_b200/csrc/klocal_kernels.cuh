@@ -464,24 +464,56 @@ SGS_D uint64_t key_hash(const DpGroup &k)
     return h;
 }
 // order prefixes: pre(a) < pre(b) implies key_cmp(a, b) < 0; equal prefixes decide nothing.  Never all-ones.
-SGS_D uint64_t key_prefix(const DpKey &k)
+// The prefix packs the leading fields of the key's lexicographic order into 64 bits.  A field of `width` bits
+// holds min(value, 2^width - 1); a field that reaches its maximum closes the prefix (every later bit is zero),
+// so the packing is monotone for ANY choice of widths - the widths in PrefixSpec only decide how many ties are
+// left to the full-key comparison.
+struct PrefixSpec {
+    int srw;                     // bits for the right-environment index
+    int wb;                      // bits per generator row
+    int vlo, vw;                 // valid-term field: (v[0] >> vlo), vw bits (bits of v[0] below vlo are zero)
+};
+struct PrefixPacker {
+    uint64_t acc;
+    int left;
+    bool open;
+    SGS_D void add(uint64_t value, int width)
+    {
+        if (!open) return;
+        width = min(width, left);
+        if (width <= 0) { open = false; return; }
+        const uint64_t maxv = width >= 64 ? ~0ULL : (1ULL << width) - 1;
+        const uint64_t f = value >= maxv ? maxv : value;
+        acc = width >= 64 ? f : (acc << width) | f;
+        left -= width;
+        if (f == maxv) open = false;
+    }
+    SGS_D uint64_t done() const { return left > 0 ? acc << left : acc; }
+};
+SGS_D uint64_t key_prefix(const DpKey &k, const PrefixSpec &ps)
 {
-    const uint64_t g0 = k.r > 0 ? (k.g[0] > 0xFFFFFFFFULL ? 0xFFFFFFFFULL : k.g[0]) : 0;
-    return ((uint64_t)k.r << 58) | ((uint64_t)(k.sright & 0x3FFFFFF) << 32) | g0;
+    PrefixPacker P{(uint64_t)k.r, 59, true};                 // r <= kDpRows = 16 < 31: the top field never saturates
+    P.add((uint64_t)(uint32_t)k.sright, ps.srw);
+    for (int i = 0; i < k.r; i++) P.add(k.g[i], ps.wb);     // rows i >= r are zero in every key of this rank
+    P.add(k.v[0] >> ps.vlo, ps.vw);
+    return P.done();
 }
-SGS_D uint64_t key_prefix(const DpGroup &k)
+SGS_D uint64_t key_prefix(const DpGroup &k, const PrefixSpec &ps)
 {
-    const uint64_t lim = (1ULL << 58) - 1;
-    const uint64_t g0 = k.r > 0 ? (k.g[0] > lim ? lim : k.g[0]) : 0;
-    return ((uint64_t)k.r << 58) | g0;
+    PrefixPacker P{(uint64_t)k.r, 59, true};
+    for (int i = 0; i < k.r; i++) P.add(k.g[i], ps.wb);
+    uint64_t sg = 0;                                         // neg[0] is the most significant sign
+    for (int i = 0; i < k.r; i++) sg = (sg << 1) | (k.neg[i] ? 1 : 0);
+    P.add(sg, k.r);
+    return P.done();
 }
 
 // entry c looks up / claims the slot of its key, then joins the slot's minimum and list
 template <typename K>
-SGS_D void dd_insert(const DdView &D, unsigned gen, const K *keys, int c)
+SGS_D void dd_insert(const DdView &D, unsigned gen, const K *keys, int c, const PrefixSpec &ps)
 {
     const uint64_t h = key_hash(keys[c]);
-    D.pre[c] = key_prefix(keys[c]);
+    D.pre[c] = key_prefix(keys[c], ps);
     const unsigned long long tw = 0xFFFFFFFFu - gen, tagv = tw << 32;
     unsigned i = (unsigned)(h ^ (h >> 32)) & D.mask;
     for (;;) {
@@ -528,28 +560,50 @@ SGS_D void dd_lead(const DdView &D, int c, int *nuniq)
     const int ld = (int)(unsigned)D.tab[D.owner[c]].lead;
     D.leader[c] = ld;
     if (ld == c) {
+        D.rank[c] = 0;
         const int p = atomicAdd(nuniq, 1);
         D.lidx[p] = c;
         D.lpre[p] = D.pre[c];
     }
 }
 
-// rank of compacted leader p = number of distinct smaller keys; the warp's lanes stride over the leaders.
-// This is the deterministic total order that replaces the reference's iteration order of a std::map on a
-// boost hash.
+// rank of every compacted leader = number of distinct smaller keys.  This is the deterministic total order that
+// replaces the reference's iteration order of a std::map on a boost hash.  All-pairs, tiled: a warp
+// task is (32 leaders, one per lane) x (a chunk of kRankChunk prefixes); the chunk is loaded coalesced, 32
+// prefixes at a time, and broadcast lane by lane with shuffles, so every prefix is read from L2 once per 32
+// leaders instead of once per leader.  Partial counts are added to rank[] (zeroed by dd_lead).  A padding
+// prefix is all-ones, which key_prefix never produces.
+constexpr int kRankChunk = 64;
 template <typename K>
-SGS_D void dd_rank_warp(const DdView &D, const K *keys, int p, int nuniq, int lane)
+__device__ __noinline__ int dd_rank_ties(const DdView &D, const K *keys, int c, int qb, unsigned ties)
 {
-    const int c = D.lidx[p];
-    const uint64_t pc = D.lpre[p];
     int cnt = 0;
-    for (int q = lane; q < nuniq; q += 32) {
-        const uint64_t pq = D.lpre[q];
-        if (pq < pc) cnt++;
-        else if (pq == pc && q != p && key_cmp(keys[D.lidx[q]], keys[c]) < 0) cnt++;
+    for (; ties; ties &= ties - 1) cnt += key_cmp(keys[D.lidx[qb + __ffs(ties) - 1]], keys[c]) < 0;
+    return cnt;
+}
+template <typename K>
+SGS_D void dd_rank_tiles(const DdView &D, const K *keys, int nuniq, int wid, int nw, int lane)
+{
+    const int ntl = (nuniq + 31) >> 5, nqc = (nuniq + kRankChunk - 1) / kRankChunk;
+    for (int task = wid; task < ntl * nqc; task += nw) {
+        const int p = (task % ntl) * 32 + lane, q0 = (task / ntl) * kRankChunk, q1 = min(q0 + kRankChunk, nuniq);
+        const bool valid = p < nuniq;
+        const uint64_t pc = valid ? D.lpre[p] : 0;                  // an invalid lane counts nothing that is used
+        int cnt = 0;
+        for (int qb = q0; qb < q1; qb += 32) {
+            const uint64_t mine = qb + lane < q1 ? D.lpre[qb + lane] : ~0ULL;
+            unsigned ties = 0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint64_t pq = __shfl_sync(0xffffffffu, mine, j);
+                cnt += pq < pc;
+                ties |= (unsigned)(pq == pc) << j;
+            }
+            if (qb == (p & ~31)) ties &= ~(1u << (p & 31));         // the leader itself
+            if (valid && ties) cnt += dd_rank_ties(D, keys, D.lidx[p], qb, ties);
+        }
+        if (valid && cnt) atomicAdd(&D.rank[D.lidx[p]], cnt);
     }
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) D.rank[c] = cnt;
 }
 
 // exclusive scan of v[0..n) into off[0..n] by one block; returns the total to every thread of the block
@@ -579,7 +633,7 @@ SGS_D int block_scan(const int *v, int *off, int n, int *part /* shared, blockDi
 //   P0 move every state to the next site (one thread per state) and count its accepted next environments
 //   P1 block 0: exclusive scan -> child offsets, capacity checks, error snapshot
 //   P2 emit the children (key + parent) in deterministic (parent, map) order
-//   P3 key de-duplication   P4 leaders   P5 key order of the leaders (warp per leader)
+//   P3 key de-duplication   P4 leaders   P5 key order of the leaders (tiled all-pairs)
 //   P6 merge: element-wise table minimum over the children of a key (warp per key), back-pointers to the
 //      history pool, merged states in key order
 struct DpBufs {
@@ -703,7 +757,13 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
         grid.sync();
         SGS_PROF(ctl, 2);
         // ---- P3
-        for (int c = tid; c < total; c += nth) dd_insert(B.D, gen, B.keys, c);
+        {
+            const int lo = H.boff[min(m1 + 1, H.n + 1)] - H.boff[m1];
+            const int hi = H.boff[min(max(m1 + k - 1, m1 + 1), H.n)] - H.boff[m1];
+            const int vlo = min(lo, 63);
+            const PrefixSpec ps{32 - __clz(max(Ln.count, 1)), 2 * (k + 1), vlo, max(min(hi, 64) - vlo, 0)};
+            for (int c = tid; c < total; c += nth) dd_insert(B.D, gen, B.keys, c, ps);
+        }
         grid.sync();
         SGS_PROF(ctl, 3);
         // ---- P4
@@ -714,7 +774,7 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
         if (nuniq > caps) { err = 5; break; }
         if ((long long)hb_off + (long long)nuniq * tstride > hb_cap) { err = 7; break; }
         // ---- P5
-        for (int p = wid; p < nuniq; p += nw) dd_rank_warp(B.D, B.keys, p, nuniq, lane);
+        dd_rank_tiles(B.D, B.keys, nuniq, wid, nw, lane);
         grid.sync();
         SGS_PROF(ctl, 5);
         // ---- P6: exact ties are won by the later child (merge_gs keeps the newcomer unless the incumbent is
@@ -843,11 +903,18 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
             if (tid == 0) ctl->nbr[(w + 1) % 3] = 0;        // next wave's counter; last read two barriers ago
             const SrBranch *in = B.br[cur];
             SrBranch *out = B.br[cur ^ 1];
-            for (int b = tid; b < nbr; b += nth) {
+            for (int bw = tid - lane; bw < nbr; bw += nth) {          // warp-uniform: one allocation per warp
+                const int b = bw + lane;
                 SrBranch tmp[2];
-                const int nn = sr_branch(H, o, b0, pos, in[b], tmp);
-                const int at = atomicAdd(counter, nn);
-                if (at + nn <= B.cap) for (int i = 0; i < nn; i++) out[at + i] = tmp[i];
+                const int nn = b < nbr ? sr_branch(H, o, b0, pos, in[b], tmp) : 0;
+                const unsigned m1 = __ballot_sync(0xffffffffu, nn >= 1), m2 = __ballot_sync(0xffffffffu, nn == 2);
+                const int tot = __popc(m1) + __popc(m2);
+                int base = 0;
+                if (lane == 0 && tot) base = atomicAdd(counter, tot);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned lt = (1u << lane) - 1u;
+                const int at = base + __popc(m1 & lt) + __popc(m2 & lt);
+                if (base + tot <= B.cap) for (int i = 0; i < nn; i++) out[at + i] = tmp[i];
             }
             grid.sync();
             nbr = *counter;
@@ -862,7 +929,10 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
         grid.sync();
         SGS_PROF(ctl, 1);
         // ---- distinct groups
-        for (int c = tid; c < total; c += nth) dd_insert(B.D, gen, B.flat, c);
+        {
+            const PrefixSpec ps{0, 2 * (k + 1), 0, 0};
+            for (int c = tid; c < total; c += nth) dd_insert(B.D, gen, B.flat, c, ps);
+        }
         grid.sync();
         SGS_PROF(ctl, 2);
         for (int c = tid; c < total; c += nth) dd_lead(B.D, c, &ctl->nuniq);
@@ -870,7 +940,7 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
         SGS_PROF(ctl, 3);
         const int nuniq = ctl->nuniq;
         // ---- key order; level storage; clear the per-group counters
-        for (int p = wid; p < nuniq; p += nw) dd_rank_warp(B.D, B.flat, p, nuniq, lane);
+        dd_rank_tiles(B.D, B.flat, nuniq, wid, nw, lane);
         for (int g = tid; g <= nuniq; g += nth) B.cnt[g] = 0;
         if (tid == 0) {
             DpLevelDev &Lv = B.levels[m];
