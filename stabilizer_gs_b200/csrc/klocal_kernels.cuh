@@ -392,6 +392,23 @@ SGS_D int sr_branch(const DpTerms &H, int o, int b0, int pos, const SrBranch &Bc
     out[nn].excl |= 1u << (pos - b0);
     return nn + 1;
 }
+// The same branching seen from ONE root-to-leaf path of the include/exclude tree (thread-per-path mode of
+// k_sr_run): `bit` = 1 asks for the include branch of term j, 0 for the exclude branch; a term that does not
+// branch (anticommutes or is already a member) continues on the 0 path only.  Returns false if the path
+// does not exist.  srel[] = the site's term rows relative to o.
+SGS_D bool sr_step(const uint64_t *srel, int j, int bit, SrBranch &b)
+{
+    const uint64_t P = srel[j];
+    bool com = true;
+    for (int i = 0; i < b.r; i++) com &= !anti(b.g[i], P);
+    if (!com || in_rref(b.g, b.r, P)) return bit == 0;
+    if (!bit) { b.excl |= 1u << j; return true; }
+    if (b.r >= kDpRows) return false;
+    signed_add(b.g, b.q, b.r, P, q_plus(P));
+    for (int t = 0; t < j; t++)
+        if (((b.excl >> t) & 1) && in_rref(b.g, b.r, srel[t])) return false;
+    return true;
+}
 // last wave: widen to [max(o,0), m+2), project onto [max(o,0), m+1) — keep the subgroup with no support on
 // site m+1 (position k relative to o_m): Stab::project (cpp/stab.cpp:524-577), canonical with signs
 SGS_D void sr_project(const SrBranch &Bc, int k, DpGroup &G)
@@ -864,7 +881,10 @@ struct SrBufs {
     DpLevelDev *levels;
     char *pool;
     int cap;
+    int waves_only;              // 1: never use the thread-per-path mode (tests, SGS_SR_WAVES=1)
 };
+constexpr int kSrPathBits = 16;             // thread-per-path mode: at most this many terms on the site ...
+constexpr long long kSrPathMax = 1 << 20;   // ... and this many paths (groups << terms); else breadth-first waves
 
 SGS_D void *sr_take(SrCtl *ctl, char *pool, size_t bytes)       // one thread
 {
@@ -879,12 +899,14 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ int part[256];
+    __shared__ uint64_t srel[32];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, wid = tid >> 5, nw = nth >> 5;
     SrCtl *ctl = B.ctl;
     unsigned gen = ctl->gen;
     int err = ctl->err;
     const int k = H.k;
+    if (tid == 0) { ctl->nbr[0] = 0; ctl->nbr[1] = 0; ctl->nbr[2] = 0; ctl->nuniq = 0; }
     grid.sync();
     unsigned long long tprof = gtime();
     int m = m_hi - 1;
@@ -893,40 +915,72 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
         const int o = m - k + 1, b0 = H.boff[m], b1 = H.boff[m + 1];
         if (b1 - b0 > 30) { err = 3; break; }
         if (Ln.count > B.cap) { err = 4; break; }
-        // ---- waves: seed, then one wave per term whose last site is m (branch order is not significant)
+        // ---- branches.  Thread-per-path mode (the usual case: few terms per site): every root-to-leaf path of
+        //      every group's include/exclude tree is tried by one thread, which projects the branch it reaches -
+        //      no barrier between the terms and none before the projection.  ctl->nbr[0] / nuniq are zero here
+        //      (cleared before the loop and, for the next level, after their last read below).
+        const int nt = b1 - b0;
+        const bool paths = !B.waves_only && nt <= kSrPathBits && ((long long)Ln.count << nt) <= kSrPathMax;
         int nbr = Ln.count, cur = 0, w = 0;
-        for (int p = tid; p < nbr; p += nth) sr_seed(Ln.groups[p], p, B.br[0][p]);
-        if (tid == 0) { ctl->nbr[0] = 0; ctl->nbr[1] = 0; ctl->nuniq = 0; }
-        grid.sync();
-        for (int pos = b0; pos < b1; pos++, w++) {
-            int *counter = &ctl->nbr[w % 3];
-            if (tid == 0) ctl->nbr[(w + 1) % 3] = 0;        // next wave's counter; last read two barriers ago
-            const SrBranch *in = B.br[cur];
-            SrBranch *out = B.br[cur ^ 1];
-            for (int bw = tid - lane; bw < nbr; bw += nth) {          // warp-uniform: one allocation per warp
-                const int b = bw + lane;
-                SrBranch tmp[2];
-                const int nn = b < nbr ? sr_branch(H, o, b0, pos, in[b], tmp) : 0;
-                const unsigned m1 = __ballot_sync(0xffffffffu, nn >= 1), m2 = __ballot_sync(0xffffffffu, nn == 2);
-                const int tot = __popc(m1) + __popc(m2);
+        if (paths) {
+            __syncthreads();
+            if ((int)threadIdx.x < nt) srel[threadIdx.x] = rel_row(H.rows + (size_t)(b0 + threadIdx.x) * H.W, H.W, o);
+            __syncthreads();
+            const int npath = Ln.count << nt;
+            for (int bw = tid - lane; bw < npath; bw += nth) {        // warp-uniform: one allocation per warp
+                const int id = bw + lane;
+                bool live = id < npath;
+                SrBranch b;
+                if (live) {
+                    sr_seed(Ln.groups[id >> nt], id >> nt, b);
+                    for (int j = 0; j < nt && live; j++) live = sr_step(srel, j, (id >> j) & 1, b);
+                }
+                const unsigned lm = __ballot_sync(0xffffffffu, live);
                 int base = 0;
-                if (lane == 0 && tot) base = atomicAdd(counter, tot);
+                if (lane == 0 && lm) base = atomicAdd(&ctl->nbr[0], __popc(lm));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                const unsigned lt = (1u << lane) - 1u;
-                const int at = base + __popc(m1 & lt) + __popc(m2 & lt);
-                if (base + tot <= B.cap) for (int i = 0; i < nn; i++) out[at + i] = tmp[i];
+                const int at = base + __popc(lm & ((1u << lane) - 1u));
+                if (live && base + __popc(lm) <= B.cap) { sr_project(b, k, B.flat[at]); B.par[at] = b.par; }
             }
             grid.sync();
-            nbr = *counter;
-            if (nbr > B.cap) break;                          // uniform
-            cur ^= 1;
+            nbr = ctl->nbr[0];
+        } else {
+            // ---- waves: seed, then one wave per term whose last site is m (branch order is not significant)
+            for (int p = tid; p < nbr; p += nth) sr_seed(Ln.groups[p], p, B.br[0][p]);
+            if (tid == 0) { ctl->nbr[0] = 0; ctl->nbr[1] = 0; }
+            grid.sync();
+            for (int pos = b0; pos < b1; pos++, w++) {
+                int *counter = &ctl->nbr[w % 3];
+                if (tid == 0) ctl->nbr[(w + 1) % 3] = 0;        // next wave's counter; last read two barriers ago
+                const SrBranch *in = B.br[cur];
+                SrBranch *out = B.br[cur ^ 1];
+                for (int bw = tid - lane; bw < nbr; bw += nth) {          // warp-uniform: one allocation per warp
+                    const int b = bw + lane;
+                    SrBranch tmp[2];
+                    const int nn = b < nbr ? sr_branch(H, o, b0, pos, in[b], tmp) : 0;
+                    const unsigned m1 = __ballot_sync(0xffffffffu, nn >= 1), m2 = __ballot_sync(0xffffffffu, nn == 2);
+                    const int tot = __popc(m1) + __popc(m2);
+                    int base = 0;
+                    if (lane == 0 && tot) base = atomicAdd(counter, tot);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned lt = (1u << lane) - 1u;
+                    const int at = base + __popc(m1 & lt) + __popc(m2 & lt);
+                    if (base + tot <= B.cap) for (int i = 0; i < nn; i++) out[at + i] = tmp[i];
+                }
+                grid.sync();
+                nbr = *counter;
+                if (nbr > B.cap) break;                          // uniform
+                cur ^= 1;
+            }
         }
         SGS_PROF(ctl, 0);
         if (nbr > B.cap) { err = 4; break; }
         const int total = nbr;
-        // ---- projection of every branch = the children, with their parent
-        for (int c = tid; c < total; c += nth) { sr_project(B.br[cur][c], k, B.flat[c]); B.par[c] = B.br[cur][c].par; }
-        grid.sync();
+        if (!paths) {
+            // ---- projection of every branch = the children, with their parent
+            for (int c = tid; c < total; c += nth) { sr_project(B.br[cur][c], k, B.flat[c]); B.par[c] = B.br[cur][c].par; }
+            grid.sync();
+        }
         SGS_PROF(ctl, 1);
         // ---- distinct groups
         {
@@ -954,6 +1008,7 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
         err = ctl->err_snap;
         if (err) break;
         // ---- groups in key order; a (group, parent) link is counted once
+        if (tid == 0) { ctl->nbr[0] = 0; ctl->nbr[1] = 0; ctl->nbr[2] = 0; ctl->nuniq = 0; }   // for the next level; all read before the last barrier
         {
             DpGroup *groups = const_cast<DpGroup *>(B.levels[m].groups);
             for (int c = tid; c < total; c += nth) {

@@ -257,6 +257,7 @@ static Status alloc_view(KlocalMachine::Impl &K, DdView &D, size_t entries, cuda
 Status KlocalMachine::Impl::alloc_sr(int cap, size_t pool_bytes)
 {
     sr.cap = cap;
+    sr.waves_only = getenv("SGS_SR_WAVES") ? 1 : 0;        // breadth-first waves only (A/B, tests)
     SGS_TRY(take(&sr.br[0], cap)); SGS_TRY(take(&sr.br[1], cap)); SGS_TRY(take(&sr.flat, cap));
     SGS_TRY(take(&sr.par, cap)); SGS_TRY(take(&sr.cnt, (size_t)cap + 1)); SGS_TRY(take(&sr.moff, (size_t)cap + 1)); SGS_TRY(take(&sr.first, cap));
     SGS_TRY(alloc_view(*this, sr.D, cap, st));

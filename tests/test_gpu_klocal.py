@@ -136,6 +136,26 @@ def test_capacity_overflow_is_redone_with_larger_buffers(monkeypatch, env):
     assert sorted(map(key, p['results'])) == sorted(map(key, g['results']))
 
 
+@pytest.mark.parametrize('n,k,per,seed', [(10, 3, 3, 2), (8, 4, 6, 3), (24, 6, 3, 6), (12, 8, 6, 7), (16, 7, 5, 8), (12, 1, 2, 9)])
+def test_right_environment_waves_equal_paths(monkeypatch, n, k, per, seed):
+    """k_sr_run builds a level's branches either with one thread per root-to-leaf path of the include/exclude
+    tree (default when the site has few terms) or as breadth-first waves (SGS_SR_WAVES=1, and automatically for
+    many terms per site): same levels, same search; also with a scratch capacity that overflows first."""
+    S = sgs()
+    text = G.klocal_text(n, k, min(per, 4 ** k - 1), seed)
+    ref = O.klocal(text=text, threads=4)
+    for env in ({}, {'SGS_SR_WAVES': '1'}, {'SGS_SR_CAP': '32'}, {'SGS_SR_WAVES': '1', 'SGS_SR_CAP': '32'}):
+        for name in ('SGS_SR_WAVES', 'SGS_SR_CAP'):
+            monkeypatch.delenv(name, raising=False)
+        for name, v in env.items():
+            monkeypatch.setenv(name, v)
+        r = S.klocal_search(S.HamHandle.from_text(text))
+        assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12), env
+        assert r['generators'] == ref['generators'] and r['term_signs'] == ref['term_signs'], env
+        assert r['sright_counts'] == ref['sright_counts'] and r['states_per_site'] == ref['states_per_site'], env
+        assert r['transitions'] == ref['transitions'], env
+
+
 def test_per_site_api_matches_one_shot():
     """sgs_klocal_create / evolve / nstates / ground_state (the loop of cpp/klocal_sparse.cpp) = sgs_klocal_search"""
     S = sgs()
