@@ -221,6 +221,8 @@ struct DpCtl {
     int cur;                 // which of the two state buffers holds the current states
     unsigned gen;            // generation of the dedup table (monotone over the machine's life)
     int caps, capc, hm_cap, hb_cap, log_cap;
+    int adv_done;            // sites of the advance in flight that are done (hand-over from the cluster-mode kernel)
+    int bailed;              // a cluster-mode kernel met a batch too large for it (sticky; the host then stops trying)
     unsigned long long prof[8];   // ns spent per phase (thread 0's view), for SGS_DP_TRACE
 };
 struct DpStepLog { int m, nin, total, nuniq, hm_off, hb_off; };
@@ -645,6 +647,22 @@ SGS_D int block_scan(const int *v, int *off, int n, int *part /* shared, blockDi
 }
 
 // ------------------------------------------------------------------------------------------------
+// Barrier between the phases of the persistent kernels.  Grid mode: a cooperative launch of one CTA per SM and
+// cooperative_groups grid.sync() (1.5-2 us on B200 whatever the grid size).  Cluster mode (CL): the whole kernel
+// is ONE thread-block cluster and the phases are separated by the hardware cluster barrier (~0.2 us), which pays
+// while a site's batch is small (the DP is latency-bound).  A cluster-mode kernel stops in front of the
+// first site whose batch is too large for its few warps and leaves the rest of the run to the grid-mode kernel
+// enqueued right behind it (`resume`): no host round trip in between.
+template <bool CL>
+struct StepSync {
+    SGS_D void sync() const
+    {
+        if constexpr (CL) cooperative_groups::this_cluster().sync();
+        else cooperative_groups::this_grid().sync();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // k_dp_run: StateMachine::evolve (cpp/state.cpp:483-533) for `nsteps` consecutive sites in one persistent
 // cooperative launch.  Phases of one site, separated by grid barriers:
 //   P0 move every state to the next site (one thread per state) and count its accepted next environments
@@ -672,10 +690,10 @@ struct DpBufs {
     int tstride, slab_stride;
 };
 
-__global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int nsteps)
+template <bool CL>
+__global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int nsteps, int resume)
 {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+    const StepSync<CL> grid;
     __shared__ int part[256];
     __shared__ uint64_t relw[64 * kDpVW];                    // window terms of the current site, relative to o_m
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -686,9 +704,12 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
     unsigned gen = ctl->gen;
     const int caps = ctl->caps, capc = ctl->capc, hm_cap = ctl->hm_cap, hb_cap = ctl->hb_cap, log_cap = ctl->log_cap;
     const int tstride = B.tstride, slab_stride = B.slab_stride, k = H.k;
+    int it = resume ? ctl->adv_done : 0;                     // sites of this advance already done by the kernel in front
+    bool bail = false;
     grid.sync();                                             // everyone has read ctl before anyone writes it
     unsigned long long tprof = gtime();
-    for (int it = 0; it < nsteps && !err; it++) {
+    for (; it < nsteps && !err; it++) {
+        if (CL && nin > 2 * nw) { bail = true; break; }      // too many states for one cluster: grid mode takes over
         const int m = m0 + it, m1 = m + 1;
         const DpLevelDev L = B.levels[m], Ln = B.levels[m1];
         const DpState *inS = B.S[cur];
@@ -740,6 +761,7 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
         const int total = ctl->total;
         err = ctl->err_snap;
         if (err) break;
+        if (CL && total > 2 * nth) { bail = true; break; }   // nothing of this site is committed yet: grid mode redoes it
         // ---- P2: key = valid bits for last site in [m1+1, min(m1+k-1, n)), positions relative to boff[m1]
         {
             const int lo = H.boff[min(m1 + 1, H.n + 1)] - H.boff[m1];
@@ -834,6 +856,8 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
         ctl->nin = nin; ctl->cur = cur; ctl->hm_off = hm_off; ctl->hb_off = hb_off; ctl->step = step;
         ctl->gen = gen + 1;                  // an aborted step may have left claims of generation gen in the table
         ctl->total = 0; ctl->nuniq = nin;
+        ctl->adv_done = it;
+        if (bail) ctl->bailed = 1;
     }
 }
 
@@ -866,6 +890,7 @@ __global__ void k_dp_trace(const DpCtl *ctl, const DpStepLog *log, const DpHistA
 // The list of compatible next groups of a group is a set (py/state.py:523); its order is not significant.
 struct SrCtl {
     int err, err_snap, nuniq, done_m;
+    int bailed;                  // a cluster-mode kernel met a level too large for it (sticky)
     int nbr[3];                  // rotating branch counters of the waves
     unsigned gen;
     unsigned long long pool_used, pool_cap;
@@ -894,10 +919,10 @@ SGS_D void *sr_take(SrCtl *ctl, char *pool, size_t bytes)       // one thread
     return pool + at;
 }
 
-__global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, int m_lo)
+template <bool CL>
+__global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, int m_lo, int resume)
 {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+    const StepSync<CL> grid;
     __shared__ int part[256];
     __shared__ uint64_t srel[32];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -906,10 +931,11 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
     unsigned gen = ctl->gen;
     int err = ctl->err;
     const int k = H.k;
+    int m = (resume ? ctl->done_m : m_hi) - 1;               // levels above were built by the kernel in front
+    bool bail = false;
     if (tid == 0) { ctl->nbr[0] = 0; ctl->nbr[1] = 0; ctl->nbr[2] = 0; ctl->nuniq = 0; }
     grid.sync();
     unsigned long long tprof = gtime();
-    int m = m_hi - 1;
     for (; m >= m_lo && !err; m--) {
         const DpLevelDev Ln = B.levels[m + 1];
         const int o = m - k + 1, b0 = H.boff[m], b1 = H.boff[m + 1];
@@ -922,6 +948,7 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
         const int nt = b1 - b0;
         const bool paths = !B.waves_only && nt <= kSrPathBits && ((long long)Ln.count << nt) <= kSrPathMax;
         int nbr = Ln.count, cur = 0, w = 0;
+        if (CL && (!paths || (Ln.count << nt) > 2 * nth)) { bail = true; break; }    // grid mode takes over from this level
         if (paths) {
             __syncthreads();
             if ((int)threadIdx.x < nt) srel[threadIdx.x] = rel_row(H.rows + (size_t)(b0 + threadIdx.x) * H.W, H.W, o);
@@ -975,6 +1002,7 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
         }
         SGS_PROF(ctl, 0);
         if (nbr > B.cap) { err = 4; break; }
+        if (CL && nbr > 2 * nth) { bail = true; break; }     // nothing of this level is stored yet
         const int total = nbr;
         if (!paths) {
             // ---- projection of every branch = the children, with their parent
@@ -1052,6 +1080,7 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
         if (err) atomicMax(&ctl->err, err);
         ctl->gen = gen + 2;                  // an aborted level may have left claims of generations gen, gen + 1 in the table
         ctl->done_m = m + 1;
+        if (bail) ctl->bailed = 1;
     }
 }
 

@@ -125,6 +125,9 @@ struct KlocalMachine::Impl {
     int trace_cap = 0;
     unsigned launches = 0;
     double dev_seconds = 0.0;
+    int cl_size = 0;               // CTAs of the cluster-mode kernels (0: grid mode only; SGS_DP_CLUSTER)
+    bool cl_dp = false, cl_sr = false;             // still worth trying cluster mode first (cleared once it bailed)
+    Status launch_persistent(const void *grid_fn, const void *cl_fn, bool use_cl, void **args, int *resume);
     Status pending;                // error met inside a const accessor, returned by the next call
 
     ~Impl();
@@ -186,10 +189,33 @@ Status KlocalMachine::Impl::init()
     SGS_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
     int coop = 0, occ_dp = 0, occ_sr = 0;
     SGS_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dp, k_dp_run, 256, 0));
-    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_sr_run, 256, 0));
+    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dp, k_dp_run<false>, 256, 0));
+    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_sr_run<false>, 256, 0));
     if (!coop || occ_dp < 1 || occ_sr < 1) return Status::fail(SGS_ERR_CUDA, "device cannot co-schedule the persistent DP kernels");
     if (const char *v = getenv("SGS_DP_GRID")) if (atoi(v) > 0) nsm = std::min(nsm, atoi(v));     // persistent grid size (experiments)
+    // cluster mode for small batches: one cluster of 16 CTAs (non-portable size; 8 if the device refuses;
+    // SGS_DP_CLUSTER=8|16 picks one, 0 turns cluster mode off)
+    int want = 16;
+    if (const char *v = getenv("SGS_DP_CLUSTER")) want = atoi(v);
+    cl_size = 0;
+    for (int size : {16, 8}) {
+        if (size > want || (want != 16 && want != 8)) continue;
+        bool ok = true;
+        const void *fns[2] = {(const void *)k_dp_run<true>, (const void *)k_sr_run<true>};
+        for (const void *fn : fns) {
+            if (size > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { ok = false; break; }
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3(size); cfg.blockDim = dim3(256); cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess || ncl < 1) { ok = false; break; }
+        }
+        (void)cudaGetLastError();
+        if (ok) { cl_size = size; break; }
+    }
+    cl_dp = cl_sr = cl_size > 0;
     SGS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     SGS_CUDA_TRY(cudaEventCreate(&e0));
     SGS_CUDA_TRY(cudaEventCreate(&e1));
@@ -317,15 +343,37 @@ Status KlocalMachine::Impl::make_top_level(int m)
     return set_level(m, L);
 }
 
-// levels m_hi-1 ... m_lo from level m_hi: one cooperative launch, one synchronisation
+// One run of a persistent kernel pair: while cluster mode is worth trying, the cluster-mode kernel goes first and
+// the grid-mode kernel behind it resumes wherever that one stopped (nothing to do if it finished: an empty
+// cooperative launch).  args[last] is the resume flag.
+Status KlocalMachine::Impl::launch_persistent(const void *grid_fn, const void *cl_fn, bool use_cl, void **args, int *resume)
+{
+    *resume = 0;
+    if (use_cl) {
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cl_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(cl_size); cfg.blockDim = dim3(256); cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+        SGS_CUDA_TRY(cudaLaunchKernelExC(&cfg, cl_fn, args));
+        launches++;
+        *resume = 1;
+    }
+    SGS_CUDA_TRY(cudaLaunchCooperativeKernel(grid_fn, dim3(nsm), dim3(256), args, 0, st));
+    launches++;
+    return Status();
+}
+
+// levels m_hi-1 ... m_lo from level m_hi: one cooperative launch (behind a cluster-mode one), one synchronisation
 Status KlocalMachine::Impl::run_sright(int m_hi, int m_lo)
 {
     for (int attempt = 0;; attempt++) {
-        void *args[] = {&terms, &sr, &m_hi, &m_lo};
-        SGS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_sr_run, dim3(nsm), dim3(256), args, 0, st));
-        launches++;
+        int resume = 0;
+        void *args[] = {&terms, &sr, &m_hi, &m_lo, &resume};
+        SGS_TRY(launch_persistent((const void *)k_sr_run<false>, (const void *)k_sr_run<true>, cl_sr, args, &resume));
         SGS_CUDA_TRY(cudaMemcpyAsync(&hsr, sr.ctl, sizeof(SrCtl), cudaMemcpyDeviceToHost, st));
         SGS_CUDA_TRY(cudaStreamSynchronize(st));
+        if (hsr.bailed) cl_sr = false;
         if (!hsr.err) break;
         if ((hsr.err != 4 && hsr.err != 8) || attempt >= 6) return ctl_error(hsr.err, "right environments");
         // scratch (4) or level pool (8) too small: take bigger ones and redo this run
@@ -389,6 +437,7 @@ Status KlocalMachine::Impl::sync_ctl()
         seg_open = false;
     }
     hctl_valid = true;
+    if (hctl.bailed) cl_dp = false;
     if (hctl.err) return ctl_error(hctl.err, "k-local DP");
     return Status();
 }
@@ -453,10 +502,9 @@ Status KlocalMachine::Impl::advance(int nsteps)
         return Status::fail(SGS_ERR_ARG, "no right-environment level for this site");
     if (!seg_open) { SGS_CUDA_TRY(cudaEventRecord(e0, st)); seg_open = true; }
     hctl_valid = false;
-    int m0 = m_;
-    void *args[] = {&terms, &dp, &m0, &nsteps};
-    SGS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_dp_run, dim3(nsm), dim3(256), args, 0, st));
-    launches++;
+    int m0 = m_, resume = 0;
+    void *args[] = {&terms, &dp, &m0, &nsteps, &resume};
+    SGS_TRY(launch_persistent((const void *)k_dp_run<false>, (const void *)k_dp_run<true>, cl_dp, args, &resume));
     m_ += nsteps;
     return Status();
 }

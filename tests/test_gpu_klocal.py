@@ -156,6 +156,26 @@ def test_right_environment_waves_equal_paths(monkeypatch, n, k, per, seed):
         assert r['transitions'] == ref['transitions'], env
 
 
+@pytest.mark.parametrize('n,k,per,seed', [(10, 3, 3, 2), (8, 4, 6, 3), (24, 6, 3, 6), (16, 7, 5, 8), (40, 4, 6, 1)])
+def test_cluster_mode_equals_grid_mode(monkeypatch, n, k, per, seed):
+    """The persistent kernels run as one thread-block cluster (hardware barrier between the phases) while the
+    batches are small and hand over to the cooperative grid otherwise (SGS_DP_CLUSTER=0: grid only, 8: smaller
+    cluster).  Same levels, states and result in every mode; (40, 4, 6) outgrows the cluster in mid-run."""
+    S = sgs()
+    text = G.klocal_text(n, k, min(per, 4 ** k - 1), seed)
+    ref = O.klocal(text=text, threads=4)
+    for mode in (None, '0', '8'):
+        if mode is None:
+            monkeypatch.delenv('SGS_DP_CLUSTER', raising=False)
+        else:
+            monkeypatch.setenv('SGS_DP_CLUSTER', mode)
+        r = S.klocal_search(S.HamHandle.from_text(text))
+        assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12), mode
+        assert r['generators'] == ref['generators'] and r['term_signs'] == ref['term_signs'], mode
+        assert r['sright_counts'] == ref['sright_counts'] and r['states_per_site'] == ref['states_per_site'], mode
+        assert r['transitions'] == ref['transitions'], mode
+
+
 def test_per_site_api_matches_one_shot():
     """sgs_klocal_create / evolve / nstates / ground_state (the loop of cpp/klocal_sparse.cpp) = sgs_klocal_search"""
     S = sgs()
