@@ -222,7 +222,7 @@ struct DpCtl {
     unsigned gen;            // generation of the dedup table (monotone over the machine's life)
     int caps, capc, hm_cap, hb_cap, log_cap;
     int adv_done;            // sites of the advance in flight that are done (hand-over from the cluster-mode kernel)
-    int bailed;              // a cluster-mode kernel met a batch too large for it (sticky; the host then stops trying)
+    int bailed;              // bit MODE: a small-mode kernel met a batch too large for it (sticky; the host then stops trying that mode)
     unsigned long long prof[8];   // ns spent per phase (thread 0's view), for SGS_DP_TRACE
 };
 struct DpStepLog { int m, nin, total, nuniq, hm_off, hb_off; };
@@ -634,10 +634,17 @@ SGS_D int block_scan(const int *v, int *off, int n, int *part /* shared, blockDi
     for (int i = lo; i < hi; i++) acc += v[i];
     part[tid] = acc;
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {                                          // warp 0: exclusive scan of the partial sums
+        const int np = per > 0 ? (n + per - 1) / per : 0;    // threads that own elements (the others hold 0 and use nothing)
         int run = 0;
-        for (int i = 0; i < nt; i++) { const int t = part[i]; part[i] = run; run += t; }
-        off[n] = run;
+        for (int base = 0; base < np; base += 32) {
+            const int t = base + tid < nt ? part[base + tid] : 0;
+            int inc = t;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += y; }
+            if (base + tid < nt) part[base + tid] = run + inc - t;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (tid == 0) off[n] = run;
     }
     __syncthreads();
     acc = part[tid];
@@ -647,17 +654,26 @@ SGS_D int block_scan(const int *v, int *off, int n, int *part /* shared, blockDi
 }
 
 // ------------------------------------------------------------------------------------------------
-// Barrier between the phases of the persistent kernels.  Grid mode: a cooperative launch of one CTA per SM and
-// cooperative_groups grid.sync() (1.5-2 us on B200 whatever the grid size).  Cluster mode (CL): the whole kernel
-// is ONE thread-block cluster and the phases are separated by the hardware cluster barrier (~0.2 us), which pays
-// while a site's batch is small (the DP is latency-bound).  A cluster-mode kernel stops in front of the
-// first site whose batch is too large for its few warps and leaves the rest of the run to the grid-mode kernel
-// enqueued right behind it (`resume`): no host round trip in between.
-template <bool CL>
+// Barrier between the phases of the persistent kernels, by launch mode:
+//   kGrid    a cooperative launch of one 256-thread CTA per SM, cooperative_groups grid.sync() (1.5-2 us on B200
+//            whatever the grid size) - any batch size;
+//   kCluster the whole kernel is ONE thread-block cluster, phases separated by the hardware cluster barrier;
+//   kBlock   the whole kernel is ONE CTA of 1024 threads, phases separated by __syncthreads(), and every table
+//            of the site stays in that SM's L1.
+// The DP is latency-bound: while a site's batch is small a phase costs a few dependent L2 round
+// trips plus the barrier, so the small modes pay.  A small-mode kernel stops in front of the first site (level)
+// whose batch is too large for its few warps and leaves the rest of the run to the next kernel enqueued right
+// behind it (`resume`): block -> cluster -> grid, no host round trip in between.
+enum { kGrid = 0, kCluster = 1, kBlock = 2 };
+template <int MODE>
 struct StepSync {
+    static constexpr int kThreads = MODE == kBlock ? 1024 : 256;
+    static constexpr int kBailStates = MODE == kBlock ? 1 : 2;     // bail above this many states per warp (the move phase is one warp per state) ...
+    static constexpr int kBailChildren = MODE == kBlock ? 4 : 2;   // ... or children (branches) per thread
     SGS_D void sync() const
     {
-        if constexpr (CL) cooperative_groups::this_cluster().sync();
+        if constexpr (MODE == kCluster) cooperative_groups::this_cluster().sync();
+        else if constexpr (MODE == kBlock) __syncthreads();
         else cooperative_groups::this_grid().sync();
     }
 };
@@ -690,11 +706,13 @@ struct DpBufs {
     int tstride, slab_stride;
 };
 
-template <bool CL>
-__global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int nsteps, int resume)
+template <int MODE>
+__global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms H, DpBufs B, int m0, int nsteps, int resume)
 {
-    const StepSync<CL> grid;
-    __shared__ int part[256];
+    const StepSync<MODE> grid;
+    constexpr bool CL = MODE != kGrid;
+    constexpr int kBailS = StepSync<MODE>::kBailStates, kBailC = StepSync<MODE>::kBailChildren;
+    __shared__ int part[StepSync<MODE>::kThreads];
     __shared__ uint64_t relw[64 * kDpVW];                    // window terms of the current site, relative to o_m
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, wid = tid >> 5, nw = nth >> 5;
@@ -709,7 +727,7 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
     grid.sync();                                             // everyone has read ctl before anyone writes it
     unsigned long long tprof = gtime();
     for (; it < nsteps && !err; it++) {
-        if (CL && nin > 2 * nw) { bail = true; break; }      // too many states for one cluster: grid mode takes over
+        if (CL && nin > kBailS * nw) { bail = true; break; }   // too many states for this mode: the next kernel takes over
         const int m = m0 + it, m1 = m + 1;
         const DpLevelDev L = B.levels[m], Ln = B.levels[m1];
         const DpState *inS = B.S[cur];
@@ -761,7 +779,7 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
         const int total = ctl->total;
         err = ctl->err_snap;
         if (err) break;
-        if (CL && total > 2 * nth) { bail = true; break; }   // nothing of this site is committed yet: grid mode redoes it
+        if (CL && total > kBailC * nth) { bail = true; break; }    // nothing of this site is committed yet: the next kernel redoes it
         // ---- P2: key = valid bits for last site in [m1+1, min(m1+k-1, n)), positions relative to boff[m1]
         {
             const int lo = H.boff[min(m1 + 1, H.n + 1)] - H.boff[m1];
@@ -857,7 +875,7 @@ __global__ void __launch_bounds__(256) k_dp_run(DpTerms H, DpBufs B, int m0, int
         ctl->gen = gen + 1;                  // an aborted step may have left claims of generation gen in the table
         ctl->total = 0; ctl->nuniq = nin;
         ctl->adv_done = it;
-        if (bail) ctl->bailed = 1;
+        if (bail) ctl->bailed |= 1 << MODE;
     }
 }
 
@@ -890,7 +908,7 @@ __global__ void k_dp_trace(const DpCtl *ctl, const DpStepLog *log, const DpHistA
 // The list of compatible next groups of a group is a set (py/state.py:523); its order is not significant.
 struct SrCtl {
     int err, err_snap, nuniq, done_m;
-    int bailed;                  // a cluster-mode kernel met a level too large for it (sticky)
+    int bailed;                  // bit MODE: a small-mode kernel met a level too large for it (sticky)
     int nbr[3];                  // rotating branch counters of the waves
     unsigned gen;
     unsigned long long pool_used, pool_cap;
@@ -919,11 +937,13 @@ SGS_D void *sr_take(SrCtl *ctl, char *pool, size_t bytes)       // one thread
     return pool + at;
 }
 
-template <bool CL>
-__global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, int m_lo, int resume)
+template <int MODE>
+__global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_sr_run(DpTerms H, SrBufs B, int m_hi, int m_lo, int resume)
 {
-    const StepSync<CL> grid;
-    __shared__ int part[256];
+    const StepSync<MODE> grid;
+    constexpr bool CL = MODE != kGrid;
+    constexpr int kBailC = StepSync<MODE>::kBailChildren;
+    __shared__ int part[StepSync<MODE>::kThreads];
     __shared__ uint64_t srel[32];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, wid = tid >> 5, nw = nth >> 5;
@@ -948,7 +968,7 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
         const int nt = b1 - b0;
         const bool paths = !B.waves_only && nt <= kSrPathBits && ((long long)Ln.count << nt) <= kSrPathMax;
         int nbr = Ln.count, cur = 0, w = 0;
-        if (CL && (!paths || (Ln.count << nt) > 2 * nth)) { bail = true; break; }    // grid mode takes over from this level
+        if (CL && (!paths || (Ln.count << nt) > kBailC * nth)) { bail = true; break; }    // the next kernel takes over from this level
         if (paths) {
             __syncthreads();
             if ((int)threadIdx.x < nt) srel[threadIdx.x] = rel_row(H.rows + (size_t)(b0 + threadIdx.x) * H.W, H.W, o);
@@ -1002,7 +1022,7 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
         }
         SGS_PROF(ctl, 0);
         if (nbr > B.cap) { err = 4; break; }
-        if (CL && nbr > 2 * nth) { bail = true; break; }     // nothing of this level is stored yet
+        if (CL && nbr > kBailC * nth) { bail = true; break; } // nothing of this level is stored yet
         const int total = nbr;
         if (!paths) {
             // ---- projection of every branch = the children, with their parent
@@ -1080,7 +1100,7 @@ __global__ void __launch_bounds__(256) k_sr_run(DpTerms H, SrBufs B, int m_hi, i
         if (err) atomicMax(&ctl->err, err);
         ctl->gen = gen + 2;                  // an aborted level may have left claims of generations gen, gen + 1 in the table
         ctl->done_m = m + 1;
-        if (bail) ctl->bailed = 1;
+        if (bail) ctl->bailed |= 1 << MODE;
     }
 }
 

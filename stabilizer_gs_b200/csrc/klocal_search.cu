@@ -125,9 +125,10 @@ struct KlocalMachine::Impl {
     int trace_cap = 0;
     unsigned launches = 0;
     double dev_seconds = 0.0;
-    int cl_size = 0;               // CTAs of the cluster-mode kernels (0: grid mode only; SGS_DP_CLUSTER)
-    bool cl_dp = false, cl_sr = false;             // still worth trying cluster mode first (cleared once it bailed)
-    Status launch_persistent(const void *grid_fn, const void *cl_fn, bool use_cl, void **args, int *resume);
+    int cl_size = 0;               // CTAs of the cluster-mode kernels (0: no cluster mode; SGS_DP_CLUSTER)
+    bool blk_ok = true;            // single-CTA mode available (SGS_DP_BLOCK=0 turns it off)
+    unsigned small_dp = 0, small_sr = 0;           // bit MODE: still worth trying that small mode first (cleared once it bailed)
+    Status launch_persistent(const void *const fns[3], unsigned small, void **args, int *resume);
     Status pending;                // error met inside a const accessor, returned by the next call
 
     ~Impl();
@@ -189,8 +190,8 @@ Status KlocalMachine::Impl::init()
     SGS_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
     int coop = 0, occ_dp = 0, occ_sr = 0;
     SGS_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dp, k_dp_run<false>, 256, 0));
-    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_sr_run<false>, 256, 0));
+    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dp, k_dp_run<kGrid>, 256, 0));
+    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_sr_run<kGrid>, 256, 0));
     if (!coop || occ_dp < 1 || occ_sr < 1) return Status::fail(SGS_ERR_CUDA, "device cannot co-schedule the persistent DP kernels");
     if (const char *v = getenv("SGS_DP_GRID")) if (atoi(v) > 0) nsm = std::min(nsm, atoi(v));     // persistent grid size (experiments)
     // cluster mode for small batches: one cluster of 16 CTAs (non-portable size; 8 if the device refuses;
@@ -201,7 +202,7 @@ Status KlocalMachine::Impl::init()
     for (int size : {16, 8}) {
         if (size > want || (want != 16 && want != 8)) continue;
         bool ok = true;
-        const void *fns[2] = {(const void *)k_dp_run<true>, (const void *)k_sr_run<true>};
+        const void *fns[2] = {(const void *)k_dp_run<kCluster>, (const void *)k_sr_run<kCluster>};
         for (const void *fn : fns) {
             if (size > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { ok = false; break; }
             cudaLaunchConfig_t cfg{};
@@ -215,7 +216,8 @@ Status KlocalMachine::Impl::init()
         (void)cudaGetLastError();
         if (ok) { cl_size = size; break; }
     }
-    cl_dp = cl_sr = cl_size > 0;
+    if (const char *v = getenv("SGS_DP_BLOCK")) blk_ok = atoi(v) != 0;
+    small_dp = small_sr = (cl_size > 0 ? 1u << kCluster : 0u) | (blk_ok ? 1u << kBlock : 0u);
     SGS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     SGS_CUDA_TRY(cudaEventCreate(&e0));
     SGS_CUDA_TRY(cudaEventCreate(&e1));
@@ -343,23 +345,30 @@ Status KlocalMachine::Impl::make_top_level(int m)
     return set_level(m, L);
 }
 
-// One run of a persistent kernel pair: while cluster mode is worth trying, the cluster-mode kernel goes first and
-// the grid-mode kernel behind it resumes wherever that one stopped (nothing to do if it finished: an empty
-// cooperative launch).  args[last] is the resume flag.
-Status KlocalMachine::Impl::launch_persistent(const void *grid_fn, const void *cl_fn, bool use_cl, void **args, int *resume)
+// One run of a persistent kernel chain: the small-mode kernels that are still worth trying go first (one CTA,
+// then one cluster), the grid-mode kernel behind them resumes wherever they stopped (nothing to do if they
+// finished: an empty cooperative launch).  fns[] is indexed by mode; args[last] is the resume flag.
+Status KlocalMachine::Impl::launch_persistent(const void *const fns[3], unsigned small, void **args, int *resume)
 {
     *resume = 0;
-    if (use_cl) {
+    if (small & (1u << kBlock)) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.stream = st;
+        SGS_CUDA_TRY(cudaLaunchKernelExC(&cfg, fns[kBlock], args));
+        launches++;
+        *resume = 1;
+    }
+    if (small & (1u << kCluster)) {
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)cl_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.gridDim = dim3(cl_size); cfg.blockDim = dim3(256); cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
-        SGS_CUDA_TRY(cudaLaunchKernelExC(&cfg, cl_fn, args));
+        SGS_CUDA_TRY(cudaLaunchKernelExC(&cfg, fns[kCluster], args));
         launches++;
         *resume = 1;
     }
-    SGS_CUDA_TRY(cudaLaunchCooperativeKernel(grid_fn, dim3(nsm), dim3(256), args, 0, st));
+    SGS_CUDA_TRY(cudaLaunchCooperativeKernel(fns[kGrid], dim3(nsm), dim3(256), args, 0, st));
     launches++;
     return Status();
 }
@@ -370,10 +379,11 @@ Status KlocalMachine::Impl::run_sright(int m_hi, int m_lo)
     for (int attempt = 0;; attempt++) {
         int resume = 0;
         void *args[] = {&terms, &sr, &m_hi, &m_lo, &resume};
-        SGS_TRY(launch_persistent((const void *)k_sr_run<false>, (const void *)k_sr_run<true>, cl_sr, args, &resume));
+        const void *const fns[3] = {(const void *)k_sr_run<kGrid>, (const void *)k_sr_run<kCluster>, (const void *)k_sr_run<kBlock>};
+        SGS_TRY(launch_persistent(fns, small_sr, args, &resume));
         SGS_CUDA_TRY(cudaMemcpyAsync(&hsr, sr.ctl, sizeof(SrCtl), cudaMemcpyDeviceToHost, st));
         SGS_CUDA_TRY(cudaStreamSynchronize(st));
-        if (hsr.bailed) cl_sr = false;
+        small_sr &= ~(unsigned)hsr.bailed;
         if (!hsr.err) break;
         if ((hsr.err != 4 && hsr.err != 8) || attempt >= 6) return ctl_error(hsr.err, "right environments");
         // scratch (4) or level pool (8) too small: take bigger ones and redo this run
@@ -437,7 +447,7 @@ Status KlocalMachine::Impl::sync_ctl()
         seg_open = false;
     }
     hctl_valid = true;
-    if (hctl.bailed) cl_dp = false;
+    small_dp &= ~(unsigned)hctl.bailed;
     if (hctl.err) return ctl_error(hctl.err, "k-local DP");
     return Status();
 }
@@ -504,7 +514,8 @@ Status KlocalMachine::Impl::advance(int nsteps)
     hctl_valid = false;
     int m0 = m_, resume = 0;
     void *args[] = {&terms, &dp, &m0, &nsteps, &resume};
-    SGS_TRY(launch_persistent((const void *)k_dp_run<false>, (const void *)k_dp_run<true>, cl_dp, args, &resume));
+    const void *const fns[3] = {(const void *)k_dp_run<kGrid>, (const void *)k_dp_run<kCluster>, (const void *)k_dp_run<kBlock>};
+    SGS_TRY(launch_persistent(fns, small_dp, args, &resume));
     m_ += nsteps;
     return Status();
 }

@@ -157,23 +157,25 @@ def test_right_environment_waves_equal_paths(monkeypatch, n, k, per, seed):
 
 
 @pytest.mark.parametrize('n,k,per,seed', [(10, 3, 3, 2), (8, 4, 6, 3), (24, 6, 3, 6), (16, 7, 5, 8), (40, 4, 6, 1)])
-def test_cluster_mode_equals_grid_mode(monkeypatch, n, k, per, seed):
-    """The persistent kernels run as one thread-block cluster (hardware barrier between the phases) while the
-    batches are small and hand over to the cooperative grid otherwise (SGS_DP_CLUSTER=0: grid only, 8: smaller
-    cluster).  Same levels, states and result in every mode; (40, 4, 6) outgrows the cluster in mid-run."""
+def test_small_batch_modes_equal_grid_mode(monkeypatch, n, k, per, seed):
+    """The persistent kernels run as one CTA (__syncthreads between the phases), then as one thread-block cluster
+    (hardware cluster barrier) while the batches are small, and hand over to the cooperative grid otherwise
+    (SGS_DP_BLOCK=0 / SGS_DP_CLUSTER=0 turn a mode off, SGS_DP_CLUSTER=8 is the portable cluster size).  Same
+    levels, states and result in every combination; (40, 4, 6) outgrows both small modes in mid-run."""
     S = sgs()
     text = G.klocal_text(n, k, min(per, 4 ** k - 1), seed)
     ref = O.klocal(text=text, threads=4)
-    for mode in (None, '0', '8'):
-        if mode is None:
-            monkeypatch.delenv('SGS_DP_CLUSTER', raising=False)
-        else:
-            monkeypatch.setenv('SGS_DP_CLUSTER', mode)
+    for env in ({}, {'SGS_DP_BLOCK': '0'}, {'SGS_DP_CLUSTER': '0'}, {'SGS_DP_BLOCK': '0', 'SGS_DP_CLUSTER': '0'},
+                {'SGS_DP_BLOCK': '0', 'SGS_DP_CLUSTER': '8'}):
+        for name in ('SGS_DP_BLOCK', 'SGS_DP_CLUSTER'):
+            monkeypatch.delenv(name, raising=False)
+        for name, v in env.items():
+            monkeypatch.setenv(name, v)
         r = S.klocal_search(S.HamHandle.from_text(text))
-        assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12), mode
-        assert r['generators'] == ref['generators'] and r['term_signs'] == ref['term_signs'], mode
-        assert r['sright_counts'] == ref['sright_counts'] and r['states_per_site'] == ref['states_per_site'], mode
-        assert r['transitions'] == ref['transitions'], mode
+        assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12), env
+        assert r['generators'] == ref['generators'] and r['term_signs'] == ref['term_signs'], env
+        assert r['sright_counts'] == ref['sright_counts'] and r['states_per_site'] == ref['states_per_site'], env
+        assert r['transitions'] == ref['transitions'], env
 
 
 def test_per_site_api_matches_one_shot():
