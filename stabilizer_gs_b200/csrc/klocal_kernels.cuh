@@ -241,16 +241,22 @@ struct DpMoved {
     int r, sright, dead, nadd;
 };
 
+// per-warp shared-memory staging of the move phase (tables of up to kMoveTab entries, i.e. k <= 4)
+constexpr int kMoveTab = 16;
+struct MoveStage { double E[2 * kMoveTab]; DpBack B[2 * kMoveTab]; DpState st; DpGroup sr; };
+static_assert(sizeof(DpState) % 8 == 0 && sizeof(DpGroup) % 8 == 0 && sizeof(DpState) / 8 <= 32 && sizeof(DpGroup) / 8 <= 32, "one lane per word");
+
 // State::move_to_next + project_to(k-1) (cpp/state.cpp:382-413, :460-466) for one state, by one warp.
-SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const double *inE, int tstride,
-                        const DpGroup *level, DpMoved &mv, double *E, double *tE, DpBack *B, DpBack *tB, DpHistAdd *hist, int *err, int lane,
-                        const uint64_t *relw /* shared: rows of the terms from position boff[m] on, relative to o_m */)
+// Returns the rank of the moved state (-1: dead) and its valid set to every lane; st / sr may live in shared
+// memory, E/tE/B/tB (the 2^rank table, its back-pointers and scratch of the same size) too.
+SGS_D int dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const double *inE, int tstride,
+                       const DpGroup &sr, DpMoved &mv, double *E, double *tE, DpBack *B, DpBack *tB, DpHistAdd *hist, int *err, int lane,
+                       const uint64_t *relw /* shared: rows of the terms from position boff[m] on, relative to o_m */, uint64_t *valid)
 {
     const int k = H.k, o = m - k + 1;
     uint64_t g[kDpRows + 1];
     int r = st.r;
     for (int i = 0; i < r; i++) g[i] = st.g[i];
-    uint64_t valid[kDpVW];
     for (int i = 0; i < kDpVW; i++) valid[i] = st.valid[i];
     for (int e = lane; e < (1 << r); e += 32) {
         E[e] = inE[(size_t)s * tstride + e];
@@ -258,7 +264,6 @@ SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const
         B[e] = b;
     }
     __syncwarp();
-    const DpGroup &sr = level[st.sright];
     if (lane == 0) { mv.sright = st.sright; mv.dead = 0; mv.nadd = 0; mv.r = 0; hist->nadd = 0; }
 
     // stab_tmp = <stab, Sright> (cpp/state.cpp:384-390), bits only
@@ -270,9 +275,9 @@ SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const
     for (int pos = b0; pos < b1; pos++) {
         const uint64_t P = relw[pos - b0];
         if (ech_reduce(tmp, P) != 0) continue;
-        if (!in_rref(sr.g, sr.r, P)) { if (lane == 0) mv.dead = 1; return; }          // cpp/state.cpp:397-399
+        if (!in_rref(sr.g, sr.r, P)) { if (lane == 0) mv.dead = 1; return -1; }       // cpp/state.cpp:397-399
         if (in_rref(g, r, P)) continue;
-        if (r + 1 > kDpTab || r + 1 > kDpRows || nadd >= kDpMaxAdd) { if (lane == 0) { atomicMax(err, 1); mv.dead = 1; } return; }
+        if (r + 1 > kDpTab || r + 1 > kDpRows || nadd >= kDpMaxAdd) { if (lane == 0) { atomicMax(err, 1); mv.dead = 1; } return -1; }
         group_add(g, r, P, E, B, tE, tB, nadd, lane);                  // State::add, cpp/state.cpp:367-380
         if (lane == 0) hist->added[nadd] = (uint16_t)pos;
         nadd++;
@@ -298,7 +303,7 @@ SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const
     // valid bits relative to boff[m+1]; bucket m+k+1 (never filtered so far) enters as all-valid
     vshift_right(valid, b1 - b0);
     const int lo = H.boff[min(m + k + 1, H.n + 1)] - b1, hi = H.boff[min(m + k + 2, H.n + 1)] - b1;
-    if (hi > 64 * kDpVW) { if (lane == 0) { atomicMax(err, 2); mv.dead = 1; } return; }
+    if (hi > 64 * kDpVW) { if (lane == 0) { atomicMax(err, 2); mv.dead = 1; } return -1; }
     vset_range(valid, lo, hi);
     if (lane == 0) {
         for (int i = 0; i < r; i++) mv.g[i] = g[i] >> 2;                // origin o_{m+1}
@@ -306,6 +311,7 @@ SGS_D void dp_move_warp(const DpTerms &H, int m, int s, const DpState &st, const
         mv.r = r;
         for (int i = 0; i < kDpVW; i++) mv.valid[i] = valid[i];
     }
+    return r;
 }
 
 // span of the valid terms with last site in [m+1, min(m+k+1, n)) truncated to [max(m-k+2,0), m+2):
@@ -713,6 +719,7 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
     constexpr bool CL = MODE != kGrid;
     constexpr int kBailS = StepSync<MODE>::kBailStates, kBailC = StepSync<MODE>::kBailChildren;
     __shared__ int part[StepSync<MODE>::kThreads];
+    __shared__ MoveStage stage[StepSync<MODE>::kThreads / 32];
     __shared__ uint64_t relw[64 * kDpVW];                    // window terms of the current site, relative to o_m
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, wid = tid >> 5, nw = nth >> 5;
@@ -746,18 +753,31 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
             __syncthreads();
         }
         for (int s = wid; s < nin; s += nw) {
-            double *E = B.slabE + (size_t)s * 2 * slab_stride;
-            DpBack *Bk = B.slabB + (size_t)s * 2 * slab_stride;
+            // the state, its right environment and (while the tables are small) the sign table with its scratch
+            // are staged in shared memory: the serial group algebra below never waits for L2
+            MoveStage &ms = stage[threadIdx.x >> 5];
+            __syncwarp();
+            if (lane < (int)(sizeof(DpState) / 8)) ((uint64_t *)&ms.st)[lane] = ((const uint64_t *)&inS[s])[lane];
+            __syncwarp();
+            if (lane < (int)(sizeof(DpGroup) / 8)) ((uint64_t *)&ms.sr)[lane] = ((const uint64_t *)&L.groups[ms.st.sright])[lane];
+            __syncwarp();
+            const bool staged = tstride <= kMoveTab;
+            double *gE = B.slabE + (size_t)s * 2 * slab_stride;
+            DpBack *gB = B.slabB + (size_t)s * 2 * slab_stride;
+            double *E = staged ? ms.E : gE, *tE = staged ? ms.E + kMoveTab : gE + slab_stride;
+            DpBack *Bk = staged ? ms.B : gB, *tBk = staged ? ms.B + kMoveTab : gB + slab_stride;
             DpMoved &mv = B.moved[s];
-            dp_move_warp(H, m, s, inS[s], inE, tstride, L.groups, mv, E, E + slab_stride, Bk, Bk + slab_stride, B.hm + hm_off + s,
-                         &ctl->err, lane, relw);
+            uint64_t valid[kDpVW];
+            const int mr = dp_move_warp(H, m, s, ms.st, inE, tstride, ms.sr, mv, E, tE, Bk, tBk, B.hm + hm_off + s, &ctl->err, lane, relw, valid);
             __syncwarp();
             int cnt = 0;
-            if (!mv.dead) {
+            if (mr >= 0) {
+                if (staged) for (int e = lane; e < (1 << mr); e += 32) { gE[e] = E[e]; gB[e] = Bk[e]; }
                 Ech e;
-                dp_valid_span(H, m, mv.valid, e, relw);
+                dp_valid_span(H, m, valid, e, relw);
                 if (lane == 0) B.span[s] = e;
-                const int j0 = L.map_off[mv.sright], j1 = L.map_off[mv.sright + 1];
+                const int sright = ms.st.sright;
+                const int j0 = L.map_off[sright], j1 = L.map_off[sright + 1];
                 for (int j = j0 + lane; j < j1; j += 32) cnt += dp_accepts(e, Ln.groups[L.map_idx[j]]);
                 for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
             }
