@@ -8,11 +8,14 @@
 //
 // Design (not a port): every object a DP step touches lives on at most 2k sites, so all rows are ONE u64
 // relative to the step's origin o_m = m - k + 1 (site s at bits 2(s-o), 2(s-o)+1).  The DP is latency-bound, so
-// the whole of it runs in two persistent cooperative kernels (k_sr_run: right environments of every site,
-// k_dp_run: any number of consecutive site steps) whose phases are separated by grid barriers and whose batch
-// sizes live in a device control block — no host round trip and no kernel boundary inside the site loop.
+// the whole of it runs in two persistent kernels (k_sr_run: right environments of every site, k_dp_run: any
+// number of consecutive site steps) whose phases are separated by barriers and whose batch sizes live in a
+// device control block — no host round trip and no kernel boundary inside the site loop.  Each kernel has
+// three launch modes (StepSync: one CTA / one thread-block cluster / cooperative grid) chained on the stream,
+// the small ones handing over on the device when a batch outgrows them.
 // One warp owns one state (generator rows replicated per lane, the 2^rank sign table and its back-pointers
-// split across the lanes, in a per-state global slab); one thread owns one right-environment branch.
+// split across the lanes, in shared memory or a per-state global slab); one thread owns one right-environment
+// branch (one root-to-leaf path of the include/exclude tree).
 // Instead of the reference's per-entry history arrays (2n ints per table entry, cpp/stab.cpp:752-759) every
 // table entry keeps one back-pointer (parent state, parent entry, signs of the generators added at this site)
 // in a history pool; the generator list is recovered by a device traceback at the end.
@@ -34,6 +37,7 @@ constexpr int kDpTab = 10;         // max rank with a materialised 2^rank table
 constexpr int kDpVW = 4;           // valid-term bitset words (terms in k+2 consecutive buckets <= 256)
 constexpr int kDpMaxAdd = 16;      // generators added at one site
 constexpr int kDpMaxSr = 2 * kDpRows;
+static_assert(kDpMaxSr <= 32, "one lane per echelon row");
 
 struct DpTerms {                   // Hamiltonian in paulis_list order
     int n, k, T, W;
@@ -93,21 +97,21 @@ SGS_D void mul1(uint64_t &a, int &qa, uint64_t b, int qb)
 // membership of v in the span of RREF rows g[0..r) (bits only)
 SGS_D bool in_rref(const uint64_t *g, int r, uint64_t v)
 {
-    for (int i = 0; i < r; i++) if ((v >> ctz64(g[i])) & 1) v ^= g[i];
+    for (int i = 0; i < r; i++) if (v & (g[i] & (0 - g[i]))) v ^= g[i];      // pivot = lowest set bit
     return v == 0;
 }
 
 // echelon basis (arbitrary order, each row clear at earlier pivots) — bits only
-struct Ech { uint64_t b[kDpMaxSr]; int n; };
+struct Ech { uint64_t b[kDpMaxSr]; uint64_t p[kDpMaxSr]; int n; };     // p[i] = lowest set bit of b[i] (its pivot)
 SGS_D uint64_t ech_reduce(const Ech &e, uint64_t v)
 {
-    for (int i = 0; i < e.n; i++) if ((v >> ctz64(e.b[i])) & 1) v ^= e.b[i];
+    for (int i = 0; i < e.n; i++) if (v & e.p[i]) v ^= e.b[i];
     return v;
 }
 SGS_D void ech_add(Ech &e, uint64_t v)
 {
     v = ech_reduce(e, v);
-    if (v && e.n < kDpMaxSr) e.b[e.n++] = v;
+    if (v && e.n < kDpMaxSr) { e.b[e.n] = v; e.p[e.n] = v & (0 - v); e.n++; }
 }
 
 // multiword right shift of the valid bitset by s bits, shifting in zeros
@@ -238,6 +242,7 @@ struct DpLevelDev {          // type_Sright (cpp/state.hpp:49-51) of one site: g
 struct DpMoved {
     uint64_t g[kDpRows];
     uint64_t valid[kDpVW];
+    uint64_t accm;           // bit i: the i-th compatible next environment (map order) accepts the state (if there are <= 64)
     int r, sright, dead, nadd;
 };
 
@@ -775,11 +780,18 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
                 if (staged) for (int e = lane; e < (1 << mr); e += 32) { gE[e] = E[e]; gB[e] = Bk[e]; }
                 Ech e;
                 dp_valid_span(H, m, valid, e, relw);
-                if (lane == 0) B.span[s] = e;
+                if (lane < e.n) { B.span[s].b[lane] = e.b[lane]; B.span[s].p[lane] = e.p[lane]; }   // e is the same in every lane; kDpMaxSr = 32
+                if (lane == 0) B.span[s].n = e.n;
                 const int sright = ms.st.sright;
                 const int j0 = L.map_off[sright], j1 = L.map_off[sright + 1];
-                for (int j = j0 + lane; j < j1; j += 32) cnt += dp_accepts(e, Ln.groups[L.map_idx[j]]);
-                for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                uint64_t accm = 0;
+                for (int base = j0; base < j1; base += 32) {
+                    const int j = base + lane;
+                    const unsigned am = __ballot_sync(0xffffffffu, j < j1 && dp_accepts(e, Ln.groups[L.map_idx[j]]));
+                    cnt += __popc(am);
+                    if (base - j0 < 64) accm |= (uint64_t)am << (base - j0);
+                }
+                if (lane == 0) mv.accm = accm;                         // P2 re-evaluates only beyond 64 candidates
             }
             if (lane == 0) B.nacc[s] = cnt;
         }
@@ -810,13 +822,16 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
                 const Ech &e = B.span[s];
                 uint64_t kv[kDpVW];
                 for (int i = 0; i < kDpVW; i++) kv[i] = 0;
-                for (int b = lo; b < hi; b++) if (vget(mv.valid, b)) kv[b >> 6] |= 1ULL << (b & 63);
+                for (int i = 0; i < kDpVW; i++) {                      // the valid bits [lo, hi)
+                    const int a = max(lo - 64 * i, 0), z = min(hi - 64 * i, 64);
+                    if (a < z) kv[i] = mv.valid[i] & ((z >= 64 ? ~0ULL : (1ULL << z) - 1ULL) & ~((1ULL << a) - 1ULL));
+                }
                 int c = B.off[s];
                 const int j0 = L.map_off[mv.sright], j1 = L.map_off[mv.sright + 1];
                 for (int base = j0; base < j1; base += 32) {          // children in (parent, map) order
                     const int j = base + lane;
                     const int nx = j < j1 ? L.map_idx[j] : 0;
-                    const bool acc = j < j1 && dp_accepts(e, Ln.groups[nx]);
+                    const bool acc = j < j1 && (j - j0 < 64 ? (bool)((mv.accm >> (j - j0)) & 1) : dp_accepts(e, Ln.groups[nx]));
                     const unsigned am = __ballot_sync(0xffffffffu, acc);
                     if (acc) {
                         const int cc = c + __popc(am & ((1u << lane) - 1u));
