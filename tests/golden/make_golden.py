@@ -275,6 +275,17 @@ INSTANCES = {
     'klocal_9_2_2_4': ('text', lambda: G.klocal_text(9, 2, 2, 4), ('sparse', 'klocal')),
     'klocal_64_4_3_0': ('text', lambda: G.klocal_text(64, 4, 3, 0), ('klocal',)),
     'periodic_example': ('file', os.path.join(REF, 'example/hamiltonian_periodic.txt'), ('periodic',)),
+    # more unit cells for the periodic path (the reference ships one example only); run with cmax=10, c=2
+    'periodic_tfim_1_2': ('text', lambda: "1 2\n -1.0 ZZ 0 1\n -0.5 X 0\n", ('periodic', 10, 2)),
+    'periodic_cell2_2_3': ('text', lambda: "2 3\n -1.0 XZX 0 1 2\n 0.7 YY 1 2\n -0.3 ZZ 0 1\n", ('periodic', 10, 2)),
+    'periodic_frustrated_1_3': ('text', lambda: "1 3\n 1.0 XZX 0 1 2\n -1.0 YY 1 2\n", ('periodic', 10, 2)),
+    # second batch of random instances (other seeds, k = 5, deeper sparse trees)
+    'sparse_7_24_3': ('text', lambda: G.sparse_text(7, 24, 3), ('sparse',)),
+    'sparse_5_20_9': ('text', lambda: G.sparse_text(5, 20, 9), ('sparse',)),
+    'sparse_9_26_2': ('text', lambda: G.sparse_text(9, 26, 2), ('sparse',)),
+    'klocal_12_5_2_7': ('text', lambda: G.klocal_text(12, 5, 2, 7), ('klocal',)),
+    'klocal_14_3_4_9': ('text', lambda: G.klocal_text(14, 3, 4, 9), ('klocal',)),
+    'klocal_11_2_3_6': ('text', lambda: G.klocal_text(11, 2, 3, 6), ('klocal',)),   # 233 240 sparse leaves: too slow for the Python sparse search
 }
 
 
@@ -297,7 +308,7 @@ def main():
                 f.write(text)
             rec = dict(name=name, file=name + '.txt')
             if 'periodic' in runs:
-                rec['periodic'] = run_periodic(path)
+                rec['periodic'] = run_periodic(path, *runs[1:])
             else:
                 H = Hamiltonian.from_file(path)
                 rec.update(n=H.n, k=H.k, nterms=len(H.original_paulis))

@@ -78,12 +78,19 @@ def test_config3_golden_md5():
     assert max(r['states_per_site']) == 113 and r['transitions'] == 2850
 
 
-def test_periodic_matches_python_reference():
-    g = json.load(open(os.path.join(GOLDEN, 'periodic_example.json')))['periodic']
-    r = O.periodic(os.path.join(GOLDEN, 'periodic_example.txt'), cmax=g['cmax'], c=g['c'])
+PERIODIC = sorted(f for f in glob.glob(os.path.join(GOLDEN, '*.json')) if 'periodic' in json.load(open(f)))
+
+
+@pytest.mark.parametrize('path', PERIODIC, ids=lambda p: os.path.basename(p)[:-5])
+def test_periodic_matches_python_reference(path):
+    """py/klocal_periodic.py on the reference's example and on three more unit cells (fixtures written by the
+    unmodified Python reference, tests/golden/make_golden.py)"""
+    rec = json.load(open(path))
+    g = rec['periodic']
+    r = O.periodic(os.path.join(GOLDEN, rec['file']), cmax=g['cmax'], c=g['c'])
     assert (r['l'], r['k'], r['n'], r['nterms']) == (g['l'], g['k'], g['n'], g['nterms'])
     assert r['sright_log'] == g['sright_log']
     assert r['fixed_point_sizes'] == g['fixed_point_sizes']
-    key = lambda o: (o['energy'], o['begin'], o['end'], o['generators'])
+    key = lambda o: (round(o['energy'], 9), o['begin'], o['end'], o['generators'])
     assert sorted(map(key, r['results'])) == sorted(map(key, g['results']))
     assert min(o['energy'] for o in r['results']) / g['c'] == pytest.approx(g['min_energy_per_period'])
