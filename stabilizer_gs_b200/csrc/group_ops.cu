@@ -21,46 +21,58 @@ namespace {
 constexpr int kMaxRows = 128;
 
 // K1: Stab::canonicalize (cpp/stab.cpp:437-449): RREF with pivot = lowest set bit, rows sorted by pivot,
-// signs carried by phase-tracked products (Pauli::dot, cpp/stab.cpp:320-330).  One thread: m <= 128.
+// signs carried by phase-tracked products (Pauli::dot, cpp/stab.cpp:320-330).  One warp, m <= 128; the rows of a
+// stabilizer group commute, so products may be taken in any order.  Rows enter one by one into a fully reduced
+// basis (no row has a bit at another row's pivot): which basis rows multiply into the newcomer is therefore
+// decided by the newcomer's own bits, the lanes multiply their share of them and a butterfly combines the
+// partial products; clearing the new pivot from the basis is one row per lane.
 template <int W>
 __global__ void k_canonicalize(int m, uint64_t *rows, int8_t *signs, int *rank)
 {
     __shared__ uint64_t C[kMaxRows * W];
-    __shared__ int q[kMaxRows], piv[kMaxRows];
-    if (threadIdx.x != 0) return;
+    __shared__ int q[kMaxRows], piv[kMaxRows], dst[kMaxRows];
+    const int lane = threadIdx.x;
     int r = 0;
     for (int i = 0; i < m; i++) {
         uint64_t v[W];
         for (int k = 0; k < W; k++) v[k] = rows[(size_t)i * W + k];
         int qv = row_plus_phase<W>(v);
         if (signs[i] < 0) qv = (qv + 2) & 3;
-        for (int b = 0; b < r; b++)
-            if (row_bit<W>(v, piv[b])) row_mul<W>(v, qv, C + b * W, q[b]);
-        if (row_is_zero<W>(v)) continue;
-        const int pv = row_lowbit<W>(v);
-        for (int b = 0; b < r; b++)
-            if (row_bit<W>(C + b * W, pv)) row_mul<W>(C + b * W, q[b], v, qv);
-        for (int k = 0; k < W; k++) C[r * W + k] = v[k];
-        q[r] = qv; piv[r] = pv; r++;
-    }
-    for (int i = 1; i < r; i++) {
-        uint64_t v[W];
-        for (int k = 0; k < W; k++) v[k] = C[i * W + k];
-        const int qv = q[i], pv = piv[i];
-        int j = i - 1;
-        while (j >= 0 && piv[j] > pv) {
-            for (int k = 0; k < W; k++) C[(j + 1) * W + k] = C[j * W + k];
-            q[j + 1] = q[j]; piv[j + 1] = piv[j];
-            j--;
+        uint64_t acc[W];
+        int qa = 0;
+        for (int k = 0; k < W; k++) acc[k] = 0;
+        for (int b = lane; b < r; b += 32)
+            if (row_bit<W>(v, piv[b])) row_mul<W>(acc, qa, C + b * W, q[b]);
+        for (int o = 16; o; o >>= 1) {
+            uint64_t oth[W];
+            for (int k = 0; k < W; k++) oth[k] = __shfl_xor_sync(0xffffffffu, acc[k], o);
+            const int qo = __shfl_xor_sync(0xffffffffu, qa, o);
+            row_mul<W>(acc, qa, oth, qo);
         }
-        for (int k = 0; k < W; k++) C[(j + 1) * W + k] = v[k];
-        q[j + 1] = qv; piv[j + 1] = pv;
+        row_mul<W>(v, qv, acc, qa);
+        if (row_is_zero<W>(v)) continue;                       // uniform: every lane holds the same v
+        const int pv = row_lowbit<W>(v);
+        for (int b = lane; b < r; b += 32)
+            if (row_bit<W>(C + b * W, pv)) row_mul<W>(C + b * W, q[b], v, qv);
+        if (lane == 0) {
+            for (int k = 0; k < W; k++) C[r * W + k] = v[k];
+            q[r] = qv; piv[r] = pv;
+        }
+        r++;
+        __syncwarp();
     }
-    for (int i = 0; i < r; i++) {
-        for (int k = 0; k < W; k++) rows[(size_t)i * W + k] = C[i * W + k];
-        signs[i] = (int8_t)row_sign<W>(C + i * W, q[i]);
+    // rows in pivot order: position = number of smaller pivots (pivots are distinct)
+    for (int b = lane; b < r; b += 32) {
+        int c = 0;
+        for (int j = 0; j < r; j++) c += piv[j] < piv[b];
+        dst[b] = c;
     }
-    *rank = r;
+    __syncwarp();
+    for (int b = lane; b < r; b += 32) {
+        for (int k = 0; k < W; k++) rows[(size_t)dst[b] * W + k] = C[b * W + k];
+        signs[dst[b]] = (int8_t)row_sign<W>(C + b * W, q[b]);
+    }
+    if (lane == 0) *rank = r;
 }
 
 // K2: Stab::energy / decompose (cpp/stab.cpp:493-505,579-587) for a batch; the group is canonical.

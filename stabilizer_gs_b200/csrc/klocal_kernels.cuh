@@ -726,6 +726,10 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
     __shared__ int part[StepSync<MODE>::kThreads];
     __shared__ MoveStage stage[StepSync<MODE>::kThreads / 32];
     __shared__ uint64_t relw[64 * kDpVW];                    // window terms of the current site, relative to o_m
+    // block mode: the de-duplication table of a small site lives in shared memory (see k_sr_run)
+    constexpr int kSmemSlots = MODE == kBlock ? 512 : 1;
+    __shared__ DdSlot stab[kSmemSlots];
+    if (MODE == kBlock) for (int i = threadIdx.x; i < kSmemSlots; i += blockDim.x) stab[i] = DdSlot{~0ULL, ~0ULL, ~0ULL};   // as the global table: all-ones = no generation
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, wid = tid >> 5, nw = nth >> 5;
     DpCtl *ctl = B.ctl;
@@ -812,6 +816,8 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
         err = ctl->err_snap;
         if (err) break;
         if (CL && total > kBailC * nth) { bail = true; break; }    // nothing of this site is committed yet: the next kernel redoes it
+        DdView D = B.D;
+        if (MODE == kBlock && 2 * total <= kSmemSlots) { D.tab = stab; D.mask = kSmemSlots - 1; }
         // ---- P2: key = valid bits for last site in [m1+1, min(m1+k-1, n)), positions relative to boff[m1]
         {
             const int lo = H.boff[min(m1 + 1, H.n + 1)] - H.boff[m1];
@@ -854,31 +860,31 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
             const int hi = H.boff[min(max(m1 + k - 1, m1 + 1), H.n)] - H.boff[m1];
             const int vlo = min(lo, 63);
             const PrefixSpec ps{32 - __clz(max(Ln.count, 1)), 2 * (k + 1), vlo, max(min(hi, 64) - vlo, 0)};
-            for (int c = tid; c < total; c += nth) dd_insert(B.D, gen, B.keys, c, ps);
+            for (int c = tid; c < total; c += nth) dd_insert(D, gen, B.keys, c, ps);
         }
         grid.sync();
         SGS_PROF(ctl, 3);
         // ---- P4
-        for (int c = tid; c < total; c += nth) dd_lead(B.D, c, &ctl->nuniq);
+        for (int c = tid; c < total; c += nth) dd_lead(D, c, &ctl->nuniq);
         grid.sync();
         SGS_PROF(ctl, 4);
         const int nuniq = ctl->nuniq;
         if (nuniq > caps) { err = 5; break; }
         if ((long long)hb_off + (long long)nuniq * tstride > hb_cap) { err = 7; break; }
         // ---- P5
-        dd_rank_tiles(B.D, B.keys, nuniq, wid, nw, lane);
+        dd_rank_tiles(D, B.keys, nuniq, wid, nw, lane);
         grid.sync();
         SGS_PROF(ctl, 5);
         // ---- P6: exact ties are won by the later child (merge_gs keeps the newcomer unless the incumbent is
         //      strictly lower, cpp/stab.cpp:832); valid bits outside the key come from the first child
         //      (State::merge_gs copies state1, cpp/state.cpp:415-419)
         for (int p = wid; p < nuniq; p += nw) {
-            const int c = B.D.lidx[p], dst = B.D.rank[c], r = B.keys[c].r;
-            const int head = (int)(unsigned)B.D.tab[B.D.owner[c]].head;
+            const int c = D.lidx[p], dst = D.rank[c], r = B.keys[c].r;
+            const int head = (int)(unsigned)D.tab[D.owner[c]].head;
             for (int e = lane; e < (1 << r); e += 32) {
                 double best = 0.0;
                 int bj = -1, bp = 0;
-                for (int j = head; j >= 0; j = B.D.next[j]) {
+                for (int j = head; j >= 0; j = D.next[j]) {
                     const int pj = B.parent[j];
                     const double v = B.slabE[(size_t)pj * 2 * slab_stride + e];
                     if (bj < 0 || v < best || (v == best && j > bj)) { best = v; bj = j; bp = pj; }
@@ -919,10 +925,17 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
 __global__ void k_dp_trace(const DpCtl *ctl, const DpStepLog *log, const DpHistAdd *hm, const DpBack *hb, int tstride, int floor_step,
                            int state, int entry, int *out_pos, int *out_sign, int *out_n, int cap)
 {
+    // the step log of the newest kTraceStage steps is staged by the whole block: the walk itself is a pointer
+    // chase (back-pointer -> what its parent added), one thread
+    constexpr int kTraceStage = 256;
+    __shared__ DpStepLog slog[kTraceStage];
+    const int nst = ctl->step, lo = max(floor_step, nst - kTraceStage);
+    for (int t = lo + (int)threadIdx.x; t < nst; t += blockDim.x) slog[t - lo] = log[t];
+    __syncthreads();
     if (threadIdx.x || blockIdx.x) return;
     int n = 0, s = state, e = entry;
-    for (int t = ctl->step - 1; t >= floor_step; t--) {
-        const DpStepLog &L = log[t];
+    for (int t = nst - 1; t >= floor_step; t--) {
+        const DpStepLog L = t >= lo ? slog[t - lo] : log[t];
         const DpBack b = hb[(size_t)L.hb_off + (size_t)s * tstride + e];
         if (b.state < 0) break;
         const DpHistAdd &h = hm[L.hm_off + b.state];
@@ -980,6 +993,11 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_sr_run(DpTerms 
     constexpr int kBailC = StepSync<MODE>::kBailChildren;
     __shared__ int part[StepSync<MODE>::kThreads];
     __shared__ uint64_t srel[32];
+    // block mode: the de-duplication table of a small level lives in shared memory (generic-address atomics on
+    // it stay inside the SM instead of three dependent L2 round trips per entry); same generation-tag scheme
+    constexpr int kSmemSlots = MODE == kBlock ? 1024 : 1;
+    __shared__ DdSlot stab[kSmemSlots];
+    if (MODE == kBlock) for (int i = threadIdx.x; i < kSmemSlots; i += blockDim.x) stab[i] = DdSlot{~0ULL, ~0ULL, ~0ULL};   // as the global table: all-ones = no generation
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, wid = tid >> 5, nw = nth >> 5;
     SrCtl *ctl = B.ctl;
@@ -1059,6 +1077,8 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_sr_run(DpTerms 
         if (nbr > B.cap) { err = 4; break; }
         if (CL && nbr > kBailC * nth) { bail = true; break; } // nothing of this level is stored yet
         const int total = nbr;
+        DdView D = B.D;
+        if (MODE == kBlock && 2 * total <= kSmemSlots) { D.tab = stab; D.mask = kSmemSlots - 1; }
         if (!paths) {
             // ---- projection of every branch = the children, with their parent
             for (int c = tid; c < total; c += nth) { sr_project(B.br[cur][c], k, B.flat[c]); B.par[c] = B.br[cur][c].par; }
@@ -1068,16 +1088,16 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_sr_run(DpTerms 
         // ---- distinct groups
         {
             const PrefixSpec ps{0, 2 * (k + 1), 0, 0};
-            for (int c = tid; c < total; c += nth) dd_insert(B.D, gen, B.flat, c, ps);
+            for (int c = tid; c < total; c += nth) dd_insert(D, gen, B.flat, c, ps);
         }
         grid.sync();
         SGS_PROF(ctl, 2);
-        for (int c = tid; c < total; c += nth) dd_lead(B.D, c, &ctl->nuniq);
+        for (int c = tid; c < total; c += nth) dd_lead(D, c, &ctl->nuniq);
         grid.sync();
         SGS_PROF(ctl, 3);
         const int nuniq = ctl->nuniq;
         // ---- key order; level storage; clear the per-group counters
-        dd_rank_tiles(B.D, B.flat, nuniq, wid, nw, lane);
+        dd_rank_tiles(D, B.flat, nuniq, wid, nw, lane);
         for (int g = tid; g <= nuniq; g += nth) B.cnt[g] = 0;
         if (tid == 0) {
             DpLevelDev &Lv = B.levels[m];
@@ -1095,9 +1115,9 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_sr_run(DpTerms 
         {
             DpGroup *groups = const_cast<DpGroup *>(B.levels[m].groups);
             for (int c = tid; c < total; c += nth) {
-                const int ld = B.D.leader[c], g = B.D.rank[ld];
+                const int ld = D.leader[c], g = D.rank[ld];
                 if (ld == c) groups[g] = B.flat[c];
-                const bool first = dd_pair_first(B.D, gen + 1, B.D.leader, B.par, c);
+                const bool first = dd_pair_first(D, gen + 1, D.leader, B.par, c);
                 B.first[c] = first;
                 if (first) atomicAdd(&B.cnt[g], 1);
             }
@@ -1124,7 +1144,7 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_sr_run(DpTerms 
         {
             int *map_idx = const_cast<int *>(B.levels[m].map_idx);
             for (int c = tid; c < total; c += nth)
-                if (B.first[c]) map_idx[atomicAdd(&B.cnt[B.D.rank[B.D.leader[c]]], 1)] = B.par[c];
+                if (B.first[c]) map_idx[atomicAdd(&B.cnt[D.rank[D.leader[c]]], 1)] = B.par[c];
         }
         grid.sync();
         SGS_PROF(ctl, 7);

@@ -533,7 +533,7 @@ Status KlocalMachine::Impl::traceback(int state, int entry, std::vector<std::pai
 {
     SGS_TRY(sync_ctl());
     int *d_pos = d_trace, *d_sign = d_trace + trace_cap, *d_n = d_trace + 2 * trace_cap;
-    k_dp_trace<<<1, 1, 0, st>>>(dp.ctl, dp.log, dp.hm, dp.hb, tstride, 0, state, entry, d_pos, d_sign, d_n, trace_cap);
+    k_dp_trace<<<1, 128, 0, st>>>(dp.ctl, dp.log, dp.hm, dp.hb, tstride, 0, state, entry, d_pos, d_sign, d_n, trace_cap);
     launches++;
     int nn = 0;
     SGS_CUDA_TRY(cudaMemcpyAsync(&nn, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
