@@ -342,7 +342,7 @@ SGS_D int key_cmp(const DpKey &a, const DpKey &b)
 {
     if (a.r != b.r) return a.r < b.r ? -1 : 1;
     if (a.sright != b.sright) return a.sright < b.sright ? -1 : 1;
-    for (int i = 0; i < kDpRows; i++) if (a.g[i] != b.g[i]) return a.g[i] < b.g[i] ? -1 : 1;
+    for (int i = 0; i < a.r; i++) if (a.g[i] != b.g[i]) return a.g[i] < b.g[i] ? -1 : 1;     // rows >= r are zero in every key
     for (int i = 0; i < kDpVW; i++) if (a.v[i] != b.v[i]) return a.v[i] < b.v[i] ? -1 : 1;
     return 0;
 }
@@ -350,8 +350,8 @@ SGS_D int key_cmp(const DpKey &a, const DpKey &b)
 SGS_D int key_cmp(const DpGroup &a, const DpGroup &b)
 {
     if (a.r != b.r) return a.r < b.r ? -1 : 1;
-    for (int i = 0; i < kDpRows; i++) if (a.g[i] != b.g[i]) return a.g[i] < b.g[i] ? -1 : 1;
-    for (int i = 0; i < kDpRows; i++) if (a.neg[i] != b.neg[i]) return a.neg[i] < b.neg[i] ? -1 : 1;
+    for (int i = 0; i < a.r; i++) if (a.g[i] != b.g[i]) return a.g[i] < b.g[i] ? -1 : 1;     // rows and signs >= r are zero in every group
+    for (int i = 0; i < a.r; i++) if (a.neg[i] != b.neg[i]) return a.neg[i] < b.neg[i] ? -1 : 1;
     return 0;
 }
 
