@@ -878,27 +878,31 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
         // ---- P6: exact ties are won by the later child (merge_gs keeps the newcomer unless the incumbent is
         //      strictly lower, cpp/stab.cpp:832); valid bits outside the key come from the first child
         //      (State::merge_gs copies state1, cpp/state.cpp:415-419)
-        for (int p = wid; p < nuniq; p += nw) {
-            const int c = D.lidx[p], dst = D.rank[c], r = B.keys[c].r;
-            const int head = (int)(unsigned)D.tab[D.owner[c]].head;
-            for (int e = lane; e < (1 << r); e += 32) {
-                double best = 0.0;
-                int bj = -1, bp = 0;
-                for (int j = head; j >= 0; j = D.next[j]) {
-                    const int pj = B.parent[j];
-                    const double v = B.slabE[(size_t)pj * 2 * slab_stride + e];
-                    if (bj < 0 || v < best || (v == best && j > bj)) { best = v; bj = j; bp = pj; }
+        //      A key is merged by a group of 8, 16 or 32 lanes (the table has at most tstride entries), so a warp
+        //      merges up to four keys at once; the merged state is written one word per lane.
+        {
+            const int gl = tstride >= 32 ? 32 : (tstride <= 8 ? 8 : 16), per = 32 / gl, sub = lane / gl, sl = lane % gl;
+            for (int p = wid * per + sub; p < nuniq; p += nw * per) {
+                const int c = D.lidx[p], dst = D.rank[c], r = B.keys[c].r;
+                const int head = (int)(unsigned)D.tab[D.owner[c]].head;
+                for (int e = sl; e < (1 << r); e += gl) {
+                    double best = 0.0;
+                    int bj = -1, bp = 0;
+                    for (int j = head; j >= 0; j = D.next[j]) {
+                        const int pj = B.parent[j];
+                        const double v = B.slabE[(size_t)pj * 2 * slab_stride + e];
+                        if (bj < 0 || v < best || (v == best && j > bj)) { best = v; bj = j; bp = pj; }
+                    }
+                    outE[(size_t)dst * tstride + e] = best;
+                    B.hb[(size_t)hb_off + (size_t)dst * tstride + e] = B.slabB[(size_t)bp * 2 * slab_stride + e];
                 }
-                outE[(size_t)dst * tstride + e] = best;
-                B.hb[(size_t)hb_off + (size_t)dst * tstride + e] = B.slabB[(size_t)bp * 2 * slab_stride + e];
-            }
-            if (lane == 0) {
                 DpState &S = outS[dst];
                 const int pp = B.parent[c];
-                for (int i = 0; i < kDpRows; i++) S.g[i] = B.keys[c].g[i];
-                for (int i = 0; i < kDpVW; i++) S.valid[i] = B.moved[pp].valid[i];
-                S.r = r;
-                S.sright = B.keys[c].sright;
+                for (int i = sl; i < kDpRows + kDpVW + 1; i += gl) {
+                    if (i < kDpRows) S.g[i] = B.keys[c].g[i];
+                    else if (i < kDpRows + kDpVW) S.valid[i - kDpRows] = B.moved[pp].valid[i - kDpRows];
+                    else { S.r = r; S.sright = B.keys[c].sright; }
+                }
             }
         }
         if (tid == 0) {
