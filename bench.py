@@ -42,15 +42,59 @@ def survey_ops(rank_hist, T, n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md).  The timed region of the default
+    run is ~0.1 s, too short for `nvidia-smi -lms` to start up, so the samples come from NVML directly (a thread
+    polling every 5 ms; the search itself runs inside a ctypes call that releases the GIL); nvidia-smi is the
+    fallback when the NVML binding is missing."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap',
+               0x80: 'hw_power_brake_slowdown'}
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
+        self.sm, self.mx, self.reasons, self.how = [], None, set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = device
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            if vis and all(t.strip().isdigit() for t in vis.split(',')) and device < len(vis.split(',')):
+                idx = int(vis.split(',')[device])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _sample_nvml(self):
+        nv = self._nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+        bits = int(get(self._h))
+        for b, nm in self.REASONS.items():
+            if bits & b:
+                self.reasons.add(nm)
+
+    def _poll(self):
+        while not self._stop.is_set():
+            try:
+                self._sample_nvml()
+            except Exception:
+                break
+            self._stop.wait(0.005)
 
     def start(self):
+        if self._nv is not None:
+            self.how = 'nvml thread, 5 ms'
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
         try:
+            self.how = 'nvidia-smi -lms 100'
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.device}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
@@ -62,6 +106,16 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
+        if self._thread is not None:
+            try:
+                self._sample_nvml()           # the loop has just ended: the clocks are still the loaded ones
+            except Exception:
+                pass
+            self._stop.set()
+            self._thread.join(timeout=1)
+            return dict(sm_mhz=statistics.median(self.sm) if self.sm else None, sm_max_mhz=self.mx,
+                        reasons=sorted(self.reasons - {'hw_power_brake_slowdown'} | ({'hw_slowdown'} if 'hw_power_brake_slowdown' in self.reasons else set())),
+                        samples=len(self.sm), how=self.how)
         if self.proc:
             self.proc.terminate()
             try:
@@ -77,7 +131,7 @@ class ClockSampler:
                 if len(r) > 5 + i and r[5 + i].lower().startswith('active'):
                     reasons.add(nm)
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), how=self.how)
 
 
 def run_reference(args, rank, world):
