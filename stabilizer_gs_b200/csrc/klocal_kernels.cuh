@@ -979,7 +979,7 @@ struct SrBufs {
     int waves_only;              // 1: never use the thread-per-path mode (tests, SGS_SR_WAVES=1)
 };
 constexpr int kSrPathBits = 16;             // thread-per-path mode: at most this many terms on the site ...
-constexpr long long kSrPathMax = 1 << 20;   // ... and this many paths (groups << terms); else breadth-first waves
+constexpr long long kSrPathMax = 1 << 17;   // ... and this many paths (groups << terms: a few rounds of the grid); else breadth-first waves
 
 SGS_D void *sr_take(SrCtl *ctl, char *pool, size_t bytes)       // one thread
 {

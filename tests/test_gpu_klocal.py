@@ -183,6 +183,20 @@ def test_small_batch_modes_equal_grid_mode(monkeypatch, n, k, per, seed):
         assert r['transitions'] == ref['transitions'], env
 
 
+@pytest.mark.parametrize('n,k,per,seed', [(8, 3, 18, 1), (9, 3, 20, 3), (7, 2, 12, 2)])
+def test_many_terms_per_site_vs_oracle(n, k, per, seed):
+    """18-20 terms share a last site: more than the thread-per-path mode of k_sr_run takes (16), so the levels
+    are built by breadth-first waves without being asked to, next to path-mode levels at the chain's ends."""
+    S = sgs()
+    text = G.klocal_text(n, k, min(per, 4 ** k - 1), seed)
+    ref = O.klocal(text=text, threads=4)
+    r = S.klocal_search(S.HamHandle.from_text(text))
+    assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12)
+    assert r['generators'] == ref['generators'] and r['term_signs'] == ref['term_signs']
+    assert r['sright_counts'] == ref['sright_counts'] and r['states_per_site'] == ref['states_per_site']
+    assert r['transitions'] == ref['transitions']
+
+
 def test_per_site_api_matches_one_shot():
     """sgs_klocal_create / evolve / nstates / ground_state (the loop of cpp/klocal_sparse.cpp) = sgs_klocal_search"""
     S = sgs()
