@@ -87,10 +87,10 @@ SGS_D uint64_t rel_row(const uint64_t *row, int W, int o)
 
 SGS_D int q_plus(uint64_t r) { return (4 - (popc64(r & (r >> 1) & kEven) & 3)) & 3; }
 SGS_D int q_sign(uint64_t r, int q) { return ((q + popc64(r & (r >> 1) & kEven)) & 3) == 0 ? 1 : -1; }
-SGS_D bool anti(uint64_t a, uint64_t b) { return popc64(a & swapzx(b)) & 1; }
+SGS_D bool anti(uint64_t a, uint64_t b) { return parity64(a & swapzx(b)); }
 SGS_D void mul1(uint64_t &a, int &qa, uint64_t b, int qb)
 {
-    qa = (qa + qb + 2 * popc64((a >> 1) & b & kEven)) & 3;
+    qa = (qa + qb + 2 * parity64((a >> 1) & b & kEven)) & 3;
     a ^= b;
 }
 
