@@ -289,10 +289,10 @@ def main():
                              call='sgs_ham_from_arrays + sgs_sparse_search (host buffers in, host result out)'),
                     gpu_launches=launches,
                     roofline=dict(bound='int_alu', achieved=achieved / 1e12, peak=peak / 1e12, unit='Tops/s (32-bit LOP3/IADD/POPC)',
-                                  frac=achieved / peak, traffic=(86.1e6 if args.workload == 'config4' else None),
+                                  frac=achieved / peak, traffic=(77.4e6 if args.workload == 'config4' else None),
                                   note='achieved = SURVEY §8(d) ALGORITHMIC ops of a from-scratch evaluation of every candidate '
                                        '(2*T*m*W32 + m^2*W32/2 each) / k_dfs time; the kernel evaluates candidates incrementally so frac > 1 '
-                                       'is expected — executed work (ncu, profiles/): 34 warp-instructions per candidate, alu pipe 61 %, issue slots 60 % of peak; peak = LOP3 issue rate measured '
+                                       'is expected — executed work (ncu, profiles/): 36 warp-instructions per candidate, alu pipe 60 %, issue slots 69 % of peak; peak = LOP3 issue rate measured '
                                        'in this run (sgs_measure_int_peaks); traffic = dram read+write bytes of one k_dfs launch from the ncu --set full capture '
                                        '(profiles/r01_k_dfs_ncu_full_summary.csv): 0.1 % of DRAM peak, the tables are KBs and L2-resident by design',
                                   popc_peak=peaks['popc_ops_per_s'] / 1e12, implied_sm_mhz=peaks['sm_mhz'],
