@@ -47,3 +47,17 @@ def test_id_courier_and_max_over_ranks_gloo_world2(tmp_path):
     for p, (o, e) in zip(ps, outs):
         assert p.returncode == 0, e[-2000:]
         assert 'ok' in o
+
+
+def test_clock_sampler_without_a_gpu_reports_no_samples():
+    """bench.py samples the SM clock through NVML (thread) or nvidia-smi; with neither it must not raise and must
+    say that it saw nothing (the bench line then carries clocks with samples = 0)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    s = mod.ClockSampler(0)
+    s.start()
+    out = s.stop()
+    assert set(out) >= {'sm_mhz', 'sm_max_mhz', 'reasons', 'samples'}
+    assert out['samples'] == 0 or out['sm_mhz'] is not None
