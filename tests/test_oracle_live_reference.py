@@ -1,0 +1,56 @@
+"""Live differential test: the CPU oracle against the UNMODIFIED Python reference on fresh random instances.
+
+Runs only where the reference is present (/root/reference, i.e. the build container); on the GPU box it is skipped
+— there the committed fixtures under tests/golden/ (written by the same functions) are the pin.  The instances are
+tiny because the reference evaluates ~25 sparse leaves or ~50 DP transitions per second."""
+import importlib.util
+import os
+import tempfile
+
+import pytest
+
+import gen_hamiltonians as G
+import oracle_py as O
+from conftest import GOLDEN
+
+REF = '/root/reference/py'
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason='the Python reference is not on this machine')
+
+
+@pytest.fixture(scope='module')
+def mg():
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(GOLDEN, 'make_golden.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _ref_ham(mg, text):
+    with tempfile.NamedTemporaryFile('w', suffix='.txt', delete=False) as f:
+        f.write(text)
+    try:
+        return mg.Hamiltonian.from_file(f.name)
+    finally:
+        os.unlink(f.name)
+
+
+@pytest.mark.parametrize('n,T,seed', [(3, 7, 101), (4, 9, 102), (5, 10, 103), (4, 12, 104), (6, 9, 105)])
+def test_sparse_fresh_instances(mg, n, T, seed):
+    text = G.sparse_text(n, T, seed)
+    ref = mg.run_sparse(_ref_ham(mg, text), 'cpp')
+    r = O.sparse(text=text)
+    assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12)
+    assert r['generators'] == ref['generators'] and r['term_signs'] == ref['term_signs']
+    assert r['candidates'] == ref['candidates'] == ref['distinct_groups']
+    assert {str(k): v for k, v in r['rank_hist'].items()} == ref['ranks']
+
+
+@pytest.mark.parametrize('n,k,per,seed', [(6, 2, 2, 111), (7, 3, 2, 112), (6, 3, 3, 113), (8, 2, 3, 114)])
+def test_klocal_fresh_instances(mg, n, k, per, seed):
+    text = G.klocal_text(n, k, per, seed)
+    ref = mg.run_klocal(_ref_ham(mg, text))
+    r = O.klocal(text=text, threads=2)
+    assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12)
+    assert r['generators'] == ref['generators'] and r['term_signs'] == ref['term_signs']
+    assert r['sright_counts'] == [ref['sright_counts'][str(m)] for m in range(n + 1)]
+    assert r['states_per_site'] == ref['states_per_site'] and r['transitions'] == ref['transitions']
