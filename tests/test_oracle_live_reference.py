@@ -54,3 +54,16 @@ def test_klocal_fresh_instances(mg, n, k, per, seed):
     assert r['generators'] == ref['generators'] and r['term_signs'] == ref['term_signs']
     assert r['sright_counts'] == [ref['sright_counts'][str(m)] for m in range(n + 1)]
     assert r['states_per_site'] == ref['states_per_site'] and r['transitions'] == ref['transitions']
+
+
+@pytest.mark.parametrize('cell', ["1 2\n 0.7 XY 0 1\n -0.4 Z 0\n 0.2 X 0\n", "2 2\n -1.0 ZZ 0 1\n 0.6 XX 1 2\n -0.25 Y 1\n",
+                                  "1 3\n -0.9 ZXZ 0 1 2\n 0.35 XX 0 1\n"])
+def test_periodic_fresh_cells(mg, cell, tmp_path):
+    p = tmp_path / 'cell.txt'
+    p.write_text(cell)
+    ref = mg.run_periodic(str(p), 10, 2)
+    r = O.periodic(str(p), cmax=10, c=2)
+    assert (r['l'], r['k'], r['n'], r['nterms']) == (ref['l'], ref['k'], ref['n'], ref['nterms'])
+    assert r['sright_log'] == ref['sright_log'] and r['fixed_point_sizes'] == ref['fixed_point_sizes']
+    key = lambda o: (round(o['energy'], 9), o['begin'], o['end'], o['generators'])
+    assert sorted(map(key, r['results'])) == sorted(map(key, ref['results']))
