@@ -112,7 +112,8 @@ def test_periodic_matches_python_reference(path):
 
 def test_periodic_vs_oracle_other_cells(tmp_path):
     S = sgs()
-    cases = ["1 2\n -1.0 ZZ 0 1\n -0.5 X 0\n", "2 3\n -1.0 XZX 0 1 2\n 0.7 YY 1 2\n -0.3 ZZ 0 1\n", "1 3\n 1.0 XZX 0 1 2\n -1.0 YY 1 2\n"]
+    cases = ["1 2\n -1.0 ZZ 0 1\n -0.5 X 0\n", "2 3\n -1.0 XZX 0 1 2\n 0.7 YY 1 2\n -0.3 ZZ 0 1\n", "1 3\n 1.0 XZX 0 1 2\n -1.0 YY 1 2\n",
+             "1 2\n 0.7 XY 0 1\n -0.4 Z 0\n 0.2 X 0\n", "2 2\n -1.0 ZZ 0 1\n 0.6 XX 1 2\n -0.25 Y 1\n", "1 3\n -0.9 ZXZ 0 1 2\n 0.35 XX 0 1\n"]
     for i, text in enumerate(cases):
         p = tmp_path / f'per{i}.txt'
         p.write_text(text)
