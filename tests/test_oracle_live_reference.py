@@ -67,3 +67,22 @@ def test_periodic_fresh_cells(mg, cell, tmp_path):
     assert r['sright_log'] == ref['sright_log'] and r['fixed_point_sizes'] == ref['fixed_point_sizes']
     key = lambda o: (round(o['energy'], 9), o['begin'], o['end'], o['generators'])
     assert sorted(map(key, r['results'])) == sorted(map(key, ref['results']))
+
+
+@pytest.mark.parametrize('n,k,per,seed', [(7, 3, 2, 121), (9, 2, 3, 122), (6, 4, 4, 123)])
+def test_parser_order_matches_reference(mg, n, k, per, seed):
+    """Hamiltonian::from_file / paulis_list (cpp/state.cpp:58-96, py/state.py:34-49): term windows and the
+    (last site, file order) ordering of the product's parser against the reference's own objects."""
+    import stabilizer_gs_b200 as S
+    text = G.klocal_text(n, k, per, seed)
+    Hr = _ref_ham(mg, text)
+    H = S.HamHandle.from_text(text)
+    assert (H.n, H.k, H.nterms) == (Hr.n, Hr.k, len(Hr.original_paulis))
+    ws = [float(w) for _, w in Hr.original_paulis]
+    assert len(set(ws)) == len(ws)
+    buckets = Hr.paulis.values() if isinstance(Hr.paulis, dict) else Hr.paulis
+    expect = [ws.index(float(w)) for bucket in buckets for _, w in bucket]
+    assert H.order() == expect
+    rows, w, b, e = H.terms()
+    for i, (P, wi) in enumerate(Hr.original_paulis):
+        assert w[i] == pytest.approx(float(wi)) and (b[i], e[i]) == (P.begin, P.end)
