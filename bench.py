@@ -13,8 +13,16 @@ Total work is fixed as N grows → "scaling": "strong".
 value  = candidates / (max over ranks of the CUDA-event time of the search kernels), term tables resident
 e2e    = the same through the public one-shot C-ABI call with HOST buffers (sgs_ham_from_arrays +
          sgs_sparse_search: device allocation, upload, search, result download inside the timed region)
+roofline.frac = EXECUTED integer-ALU-pipe utilisation of the dominant kernel (k_dfs): ALU-pipe warp instructions
+         per launch (ncu counters of this build and workload, profiles/r02_k_dfs_counters.json) x 32 lanes / the
+         kernel's live CUDA-event time / (N x the LOP3 issue peak measured in this run).  The SURVEY §8(d)
+         ALGORITHMIC figure (a from-scratch evaluation of every candidate) is kept as algorithmic_over_peak: the
+         kernel is incremental, so that one exceeds 1.
+config5 = one complete n=40/T=1000 search (BASELINE configs[4], the north-star target) per run, same process,
+         so that the 1/2/4/8-GPU scaling runs carry the curve of that workload too (--no-config5 skips it).
 --impl reference times the CPU implementation (the oracle port of the reference's FullState::evolve,
-since cpp/ needs Eigen + Boost which are not in the image) on a bounded sample of the same instance.
+since cpp/ needs Eigen + Boost which are not in the image) on a uniform sample of the same instance: the
+complete walk of every stride-th depth-2 subtree (hashed), all host threads.
 """
 import argparse
 import ctypes
@@ -134,22 +142,40 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm), how=self.how)
 
 
+# The complete oracle walk of config 4 costs ~2.0e3 core-seconds (measured: 251 s on 8 cores,
+# tests/golden/oracle_sparse_24_300_0.json); a sample walks 1/stride of its depth-2 subtrees completely.
+CPU_CORE_SECONDS_FULL = 2000.0
+
+
+def cpu_stride(cores, seconds):
+    return max(2, int(round(CPU_CORE_SECONDS_FULL / (max(seconds, 1.0) * max(cores, 1)))))
+
+
+def cpu_sample_note(stride):
+    return (f'uniform sample: complete walk of every {stride}-th (hashed) depth-2 subtree of the same n={N_QUBITS}/T={N_TERMS} '
+            'instance + the top of the tree (oracle/sparse.c = restatement of FullState::evolve, OpenMP tasks, '
+            'per-thread accumulators); cpp/ of the reference needs Eigen+Boost (absent) and its sources do not '
+            'travel to the GPU box')
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of FullState::evolve (cpp/state.cpp:636-687) with all host threads, each
-    step a bounded sample (wall-time limited) of the same n=24/T=300 search."""
+    step a uniform sample of the same n=24/T=300 search (every stride-th depth-2 subtree, walked completely;
+    step i takes the i-th residue class)."""
     if rank != 0:
         return
     import gen_hamiltonians as G
     import oracle_py as O
     text = G.sparse_text(N_QUBITS, N_TERMS, SEED)
     cores = os.cpu_count() or 1
-    # each step is a wall-time-bounded sample; the whole run stays within ~2 minutes whatever K is
-    sample_s = float(os.environ.get('SGS_BENCH_SAMPLE_S', str(max(1.0, min(8.0, 100.0 / max(args.steps, 1))))))
+    # the whole run stays within ~2 minutes whatever K is
+    per_step = float(os.environ.get('SGS_BENCH_SAMPLE_S', str(max(2.0, min(15.0, 100.0 / max(args.steps, 1))))))
+    stride = cpu_stride(cores, per_step)
     for _ in range(min(args.warmup, 1)):
-        O.sparse_sample(text=text, threads=cores, seconds=1.0)
+        O.sparse_stride(text=text, threads=cores, stride=stride * 8, offset=1)
     cand, secs = 0, 0.0
-    for _ in range(args.steps):
-        r = O.sparse_sample(text=text, threads=cores, seconds=sample_s)
+    for i in range(args.steps):
+        r = O.sparse_stride(text=text, threads=cores, stride=stride, offset=i % stride)
         cand += r['candidates']
         secs += r['seconds']
     value = cand / secs
@@ -157,11 +183,49 @@ def run_reference(args, rank, world):
                 steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * secs / args.steps, higher_is_better=True,
                 scaling='strong', vs_baseline=None, dtype='u64 bit algebra + f64 energies', data='synthetic',
                 impl='reference', config=dict(workload=WORKLOAD),
-                cpu_baseline=dict(value=value, unit='candidates/s', cores=cores, kind='port',
-                                  sample=f'{sample_s:.0f} s wall-time-bounded include-first walk of the same instance per step '
-                                         '(oracle/sparse.c, OpenMP tasks); cpp/ of the reference needs Eigen+Boost, absent here'),
+                cpu_baseline=dict(value=value, unit='candidates/s', cores=cores, kind='port', sample=cpu_sample_note(stride)),
                 e2e=dict(value=value, unit='candidates/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
+
+
+def load_counters(workload):
+    """ncu counters of one k_dfs launch of this build (scripts/ncu_counters.py writes them from the committed
+    --set full capture): executed ALU-pipe / total warp instructions, thread instructions, DRAM bytes."""
+    path = os.path.join(ROOT, 'profiles', 'r02_k_dfs_counters.json')
+    try:
+        return json.load(open(path)).get(workload), 'profiles/r02_k_dfs_counters.json'
+    except (OSError, ValueError):
+        return None, None
+
+
+def roofline_block(workload, hot_s_per_step, world, peaks, rank_hist, T, n):
+    """executed-instruction roofline of k_dfs: see the module docstring"""
+    peak = peaks['lop3_ops_per_s'] * world
+    ops = survey_ops(rank_hist, T, n)
+    ctr, src = load_counters(workload)
+    blk = dict(bound='int_alu', unit='Tops/s (32-bit integer-pipe lane-ops: LOP3/IADD/SHF/ISETP...)', peak=peak / 1e12,
+               peak_source=f'LOP3 issue rate measured in this run on one GPU (sgs_measure_int_peaks) x {world} GPU(s)',
+               popc_peak=peaks['popc_ops_per_s'] * world / 1e12, implied_sm_mhz=peaks['sm_mhz'],
+               hot_kernel='k_dfs', hot_kernel_ms=1e3 * hot_s_per_step,
+               algorithmic_over_peak=ops / hot_s_per_step / peak,
+               algorithmic_note='SURVEY §8(d) from-scratch ops of every candidate (2*T*m*W32 + m^2*W32/2) / k_dfs time / peak; '
+                                'the kernel evaluates candidates incrementally, so this exceeds 1 and is not a utilisation')
+    if ctr:
+        # all shards together execute the same instructions as one (the tree is partitioned, the top is KBs)
+        alu_lane_ops = ctr['inst_executed_pipe_alu'] * 32.0
+        achieved = alu_lane_ops / hot_s_per_step
+        blk.update(achieved=achieved / 1e12, frac=achieved / peak,
+                   frac_lane_weighted=achieved / peak * ctr['thread_inst_executed'] / (32.0 * ctr['inst_executed']),
+                   issue_slot_frac=ctr['inst_executed'] / hot_s_per_step / (peak / 32.0 * 2.0),
+                   traffic=ctr.get('dram_bytes'), source=src, counters=ctr,
+                   note='achieved = executed ALU-pipe warp instructions of one k_dfs launch (ncu, this build and workload) x 32 '
+                        'lanes / live CUDA-event time of the kernel; frac = achieved / peak = the ALU-pipe utilisation; '
+                        'traffic = dram read+write bytes of the same launch (the tables are KBs and L2-resident: the bound is '
+                        'the integer pipe, not HBM)')
+    else:
+        blk.update(achieved=None, frac=None, traffic=None, source=None,
+                   note='no ncu counters committed for this workload: utilisation not reported')
+    return blk
 
 
 def main():
@@ -171,7 +235,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='config4', choices=['config4', 'config5'],
-                    help='config4 = n=24/T=300 (default, the bench line); config5 = n=40/T=1000 (28 s per step on one B200: use --steps 1)')
+                    help='config4 = n=24/T=300 (default, the bench line); config5 = n=40/T=1000 (~20 s per step on one B200: use --steps 1)')
+    ap.add_argument('--no-config5', action='store_true', help='skip the one-step config5 block of the default run')
     args = ap.parse_args()
     if args.workload == 'config5':
         global N_QUBITS, N_TERMS, WORKLOAD
@@ -268,36 +333,51 @@ def main():
     barrier()
     e2e_s = allmax(time.perf_counter() - t0)
 
+    # ---- config5 block: ONE complete n=40/T=1000 search on the same N GPUs (device-timed, max over ranks) ----
+    c5 = None
+    if args.workload == 'config4' and not args.no_config5 and not os.environ.get('SGS_BENCH_NO_CONFIG5'):
+        text5 = G.sparse_text(40, 1000, SEED)
+        ham5 = S.HamHandle.from_text(text5)
+        plan5 = S.SparsePlan(ham5, device=device, rank=rank, world=world, nccl_id=nccl_id)
+        barrier()
+        t5 = time.perf_counter()
+        r5 = plan5.run()
+        barrier()
+        wall5 = allmax(time.perf_counter() - t5)
+        dev5 = allmax(r5['seconds_device'])
+        hot5 = allmax(r5['seconds_hot_kernel'])
+        plan5.close()
+        if rank == 0:
+            c5 = dict(workload=f'sparse random Pauli Hamiltonian n=40 T=1000 seed={SEED} (BASELINE configs[4]), full enumeration',
+                      steps=1, warmup=0, n_gpus=world, candidates=r5['candidates'], seconds=dev5, wall_seconds=wall5,
+                      candidates_per_s=r5['candidates'] / dev5, energy=r5['energy'], rank=r5['m'],
+                      k_dfs_seconds=hot5, gpu_launches=r5['kernel_launches'],
+                      roofline=roofline_block('config5', hot5, world, peaks, r5['rank_hist'], 1000, 40),
+                      note='one search, first (adaptive, host-synchronised) run of its plan; timed with CUDA events, max over ranks')
+
     if rank == 0:
         cand = res['candidates']
         hist = res['rank_hist']
-        ops = survey_ops(hist, T, N_QUBITS)
         h2d = T * W * 8 + T * 8 * 2 + T * 4
         d2h = res['m'] * W * 8 + res['m'] + T + 8 + 8 * 65
-        peak = peaks['lop3_ops_per_s']
-        achieved = ops / (hot_s / args.steps)
         line = dict(metric='stabilizer candidates evaluated/sec', value=cand / (dev_s / args.steps), unit='candidates/s',
                     n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=1e3 * dev_s / args.steps,
                     higher_is_better=True, scaling='strong', vs_baseline=None,
                     dtype='u64 bit algebra + f64 energies', data='synthetic',
-                    config=dict(workload=WORKLOAD, candidates_per_step=cand, parallelism=f'shard{world}',
+                    config=dict(workload=WORKLOAD),
+                    detail=dict(candidates_per_step=cand, parallelism=f'shard{world}',
                                 l2='flushed between steps (512 MB memset); inputs are L2-resident by design (KBs)',
-                                energy=res['energy'], rank=res['m'], wall_ms_per_step=1e3 * wall / args.steps),
+                                energy=res['energy'], rank=res['m'], wall_ms_per_step=1e3 * wall / args.steps,
+                                rank_hist={str(k): v for k, v in hist.items()}, walk_paths=res.get('walk_paths')),
                     time_to_ground_state_ms=1e3 * e2e_s / e2e_steps,
                     e2e=dict(value=cand_e / (e2e_s / e2e_steps), unit='candidates/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=1e3 * e2e_s / e2e_steps, steps=e2e_steps,
                              call='sgs_ham_from_arrays + sgs_sparse_search (host buffers in, host result out)'),
                     gpu_launches=launches,
-                    roofline=dict(bound='int_alu', achieved=achieved / 1e12, peak=peak / 1e12, unit='Tops/s (32-bit LOP3/IADD/POPC)',
-                                  frac=achieved / peak, traffic=(77.4e6 if args.workload == 'config4' else None),
-                                  note='achieved = SURVEY §8(d) ALGORITHMIC ops of a from-scratch evaluation of every candidate '
-                                       '(2*T*m*W32 + m^2*W32/2 each) / k_dfs time; the kernel evaluates candidates incrementally so frac > 1 '
-                                       'is expected — executed work (ncu, profiles/): 36 warp-instructions per candidate, alu pipe 60 %, issue slots 69 % of peak; peak = LOP3 issue rate measured '
-                                       'in this run (sgs_measure_int_peaks); traffic = dram read+write bytes of one k_dfs launch from the ncu --set full capture '
-                                       '(profiles/r01_k_dfs_ncu_full_summary.csv): 0.1 % of DRAM peak, the tables are KBs and L2-resident by design',
-                                  popc_peak=peaks['popc_ops_per_s'] / 1e12, implied_sm_mhz=peaks['sm_mhz'],
-                                  hot_kernel='k_dfs', hot_kernel_ms=1e3 * hot_s / args.steps),
+                    roofline=roofline_block(args.workload, hot_s / args.steps, world, peaks, hist, T, N_QUBITS),
                     clocks=clocks)
+        if c5:
+            line['config5'] = c5
         # the time-to-exact-ground-state half of BASELINE's metric, on the DP configs (rank 0, N=1 only; GPU
         # wall time of the one-shot calls, parse + upload + search + result)
         if world == 1:
@@ -327,10 +407,10 @@ def main():
         if world == 1:
             import oracle_py as O
             cores = os.cpu_count() or 1
-            r = O.sparse_sample(text=text, threads=cores, seconds=12.0)
+            stride = cpu_stride(cores, 15.0) if args.workload == 'config4' else 4096
+            r = O.sparse_stride(text=text, threads=cores, stride=stride, offset=0)
             line['cpu_baseline'] = dict(value=r['candidates'] / r['seconds'], unit='candidates/s', cores=cores, kind='port',
-                                        sample=f'12 s wall-time-bounded include-first walk of the same n={N_QUBITS}/T={N_TERMS} instance '
-                                               '(oracle/sparse.c = restatement of FullState::evolve, OpenMP tasks)')
+                                        sample=cpu_sample_note(stride), sample_candidates=r['candidates'], sample_seconds=r['seconds'])
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -107,7 +107,12 @@ typedef struct {
     double seconds_device;       /* CUDA-event time of the search kernels (max over local GPUs) */
     double seconds_hot_kernel;   /* CUDA-event time of the dominant kernel                     */
     uint32_t kernel_launches;    /* launches of this library's kernels during the call         */
-    int reserved[7];
+    /* sparse search diagnostics (the parity tests assert that every path of the walk was exercised):
+     * [0] certified frames walked with 32-bit clique masks, [1] with 64-bit masks, [2] multi-word independence
+     * proven on the folded 64-bit image, [3] decided by the full-width elimination, [4] dependent residues
+     * certified by the clique test, [5] frames not certified, [6] warp-cooperative child frames (level A);
+     * saturating; summed over shards when a communicator combines them */
+    uint32_t walk_paths[7];
 } sgs_result;
 void sgs_result_free(sgs_result *r);     /* frees the buffers inside *r (not r itself)        */
 

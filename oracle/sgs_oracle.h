@@ -75,6 +75,8 @@ void ores_free(ores *r);
 ores *oracle_sparse(const oham *H, int threads);
 /* same walk, stopped after max_leaves leaves or `seconds` (bench.py's bounded CPU sample) */
 ores *oracle_sparse_sample(const oham *H, int threads, uint64_t max_leaves, double seconds);
+/* uniform sample: walks, completely, the subtrees below every stride-th (hashed) pair of first two included terms */
+ores *oracle_sparse_stride(const oham *H, int threads, int stride, int offset);
 /* k-local DP: StateMachine (cpp/state.cpp:445-550) + generate_Sright_all (:218-238) */
 ores *oracle_klocal(const oham *H, int threads);
 

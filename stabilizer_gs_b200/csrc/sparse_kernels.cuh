@@ -57,6 +57,7 @@ struct BestRec {
 struct SparseStats {
     unsigned long long hist[kMaxG + 1];   // candidates per rank
     unsigned long long slow_nodes;        // candidates evaluated by k_general
+    unsigned long long paths[8];          // which code paths of the walk ran (kPath*; summed over shards like hist)
     unsigned int error;                   // SGS_ERR_* (positive) set by a kernel
     unsigned int pad;
     unsigned long long dbg[8];            // SGS_TRACE diagnostics of the walk (see k_dfs)
@@ -78,6 +79,18 @@ struct SparseDev {
 };
 
 enum { kErrOverflow = 8, kErrLimit = 6 };
+constexpr int kStatsSummed = kMaxG + 2 + 8;   // leading u64 words of SparseStats that add up over shards (hist, slow_nodes, paths)
+// SparseStats::paths — diagnostics the parity tests assert on (sgs_result.walk_paths)
+enum {
+    kPathWalk32 = 0,     // certified frames walked with 32-bit clique masks (<= 32 candidates)
+    kPathWalk64 = 1,     // certified frames walked with 64-bit clique masks
+    kPathFoldOk = 2,     // multi-word rows: independence proven on the folded 64-bit image
+    kPathFoldFull = 3,   // multi-word rows: the image was dependent, the full-width elimination decided
+    kPathDepCert = 4,    // dependent residues, certified because no dependency is a clique
+    kPathNoCert = 5,     // frames level B could not certify (commuting dependency / > kMaxDep dependencies)
+    kPathLevelA = 6,     // warp-cooperative child frames pushed below a root
+    kPathSplit = 7       // roots whose children were handed to a next k_dfs round
+};
 
 SGS_D unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // order-preserving encoding of a double into an unsigned key (atomicMin on the key = min on the double)
@@ -300,6 +313,10 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
         const int m = rec[0];
         const unsigned flags = rec[1];
         const uint16_t *g = rec + 2;
+        if (m > kMaxG || 2 + m > D.S) {           // a record no queue slot can hold: a corrupted or over-deep node
+            if (lane == 0) atomicMax(&D.stats->error, (unsigned)kErrLimit);
+            continue;
+        }
         const bool mine = nshards <= 1 || (int)(tuple_hash(g, m) % (unsigned)nshards) == shard;
         if (own_only && !mine) continue;          // parent-sharded level: the owner evaluates and expands it
 
@@ -465,6 +482,10 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
             }
             const unsigned vb = __ballot_sync(0xffffffffu, valid);
             if (vb == 0) continue;
+            if (m >= kMaxG || 2 + m + 1 > D.S) {          // a child of rank m + 1 fits no record (rank limit): report, never write
+                if (lane == 0) atomicMax(&D.stats->error, (unsigned)kErrLimit);
+                break;
+            }
             if (out == nullptr) { if (lane == 0) atomicAdd(out_count, (unsigned)__popc(vb)); continue; }
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(out_count, (unsigned)__popc(vb));
@@ -557,6 +578,7 @@ __host__ __device__ inline size_t dfs_smem_bytes(int cap)
     b += (size_t)kMaxG * 2 * 2;        // path, best tuple
     b += 64;                           // basis pivots
     b += 64 * 8 + 8;                   // suffix sums of the candidate weights (branch-and-bound mode), 8-byte aligned
+    b += 8 * 4;                        // code-path counters
     return (b + 15) & ~(size_t)15;
 }
 
@@ -741,7 +763,7 @@ SGS_D float expected_cliques(int n, int e)
 //  instruction cache)
 template <int W, bool PRUNE>
 __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, int n, int nlow, int depth,
-                  uint32_t *hc, double &bw, uint64_t &bm, int lane, float split_cliques, double *SW, double need)
+                  uint32_t *hc, double &bw, uint64_t &bm, int lane, float split_cliques, double *SW, double need, uint32_t *pc)
 {
     // 1. independence of ALL n residues (lower-index entries included: a dependency through one of them would
     //    make a later child non-canonical).  Own rows: entries lane and lane + 32; step u broadcasts the
@@ -768,6 +790,7 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         }
         const bool dep = rows_dependent_1w(p0, p1, n, lane);
         proven = !dep;
+        if (lane == 0) pc[dep ? kPathFoldFull : kPathFoldOk]++;
     }
     if (W == 1) {
         dependent = rows_dependent_1w(e0[0], e1[0], n, lane);
@@ -863,7 +886,7 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
                 cmb1 ^= cmu;
             }
         }
-        if (fail) return 0;
+        if (fail) { if (lane == 0) pc[kPathNoCert]++; return 0; }
 #pragma unroll 1
         for (int gcode = 1; gcode < (1 << ndep); gcode++) {
             uint64_t S = 0;
@@ -871,8 +894,9 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
             for (int k = 0; k < kMaxDep; k++) if ((gcode >> k) & 1) S ^= deps[k];
             const bool in0 = (S >> lane) & 1, in1 = (S >> (lane + 32)) & 1;
             const bool bad = (in0 && (S & ~adj0 & ~(1ULL << lane)) != 0) || (in1 && (S & ~adj1 & ~(1ULL << (lane + 32))) != 0);
-            if (!__any_sync(0xffffffffu, bad)) return 0;          // a commuting dependency: not certified
+            if (!__any_sync(0xffffffffu, bad)) { if (lane == 0) pc[kPathNoCert]++; return 0; }   // a commuting dependency: not certified
         }
+        if (lane == 0) pc[kPathDepCert]++;
     }
     // 2. commutation graph of the candidates only (list positions nlow..n-1; vertex = position - nlow): lane
     //    owns vertices lane and lane + 32, keeps the higher-numbered neighbours (cliques grow upward)
@@ -911,6 +935,7 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
             if (expected_cliques(ncand, e) > split_cliques) return 2;
         }
         if (lane < ncand) AD32[lane] = up32;
+        if (lane == 0) pc[kPathWalk32]++;
         __syncwarp();
         uint32_t bm32 = 0;
         lb_walk<uint32_t, PRUNE>(AD32, WA + nlow, ncand, depth, hc, bw, bm32, a32 & ((1u << lane) - 1u), 0u, lane, SW, need);
@@ -940,6 +965,7 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         }
         AD[lane] = up0;
         if (lane + 32 < ncand) AD[lane + 32] = up1;
+        if (lane == 0) pc[kPathWalk64]++;
         __syncwarp();
         uint64_t bmr = 0;
         lb_walk<uint64_t, PRUNE>(AD, WA + nlow, ncand, depth, hc, bw, bmr, a0 & ((1ULL << lane) - 1ULL), a1 & ((1ULL << (lane + 32)) - 1ULL), lane, SW,
@@ -1022,7 +1048,9 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     uint16_t *bestG = (uint16_t *)p;    p += (size_t)kMaxG * 2;
     uint8_t *pivB = (uint8_t *)p;       p += 64;
     p = smem_raw + (((size_t)(p - smem_raw) + 7) & ~(size_t)7);
-    double *SW = (double *)p;           // [64] suffix sums of the candidate weights (branch-and-bound mode)
+    double *SW = (double *)p;           p += 64 * 8;   // [64] suffix sums of the candidate weights (branch-and-bound mode)
+    uint32_t *pc = (uint32_t *)p;       // [8] code-path counters (kPath*)
+    if (lane < 8) pc[lane] = 0;
 
     const unsigned gw = blockIdx.x * wpb + warp;
     BestRec *myrec = D.wbest + gw;
@@ -1055,7 +1083,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         double bw = -1.0;
         uint64_t bm = 0;
         // a clique of weight w gives the energy Ef - w: it reaches the incumbent iff w >= Ef - thr
-        const int rc = level_b<W, PRUNE>(R + lb * W, WA + lb, AD, AD32, n, nlow, depth, hc, bw, bm, lane, split, SW, Ef - thr);
+        const int rc = level_b<W, PRUNE>(R + lb * W, WA + lb, AD, AD32, n, nlow, depth, hc, bw, bm, lane, split, SW, Ef - thr, pc);
         if (rc != 1) return rc;
         // does any lane's best clique reach the incumbent?
         const bool cand = bm != 0 && (Ef - bw) <= bestE;
@@ -1100,7 +1128,10 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         const uint16_t *rec = items + (size_t)(perm ? perm[it] : it) * D.S;
         const int m0 = rec[0];
         const unsigned flags = rec[1];
-        if (nshards > 1 && (int)(tuple_hash(rec + 2, m0) % (unsigned)nshards) != shard) continue;
+        // a subtree root belongs to the shard of its PARENT (hash of the tuple without its last generator): the same
+        // partition whether the last expansion level was replicated (first, adaptive run of a plan) or expanded by
+        // the parent's owner only (recorded launch sequence)
+        if (nshards > 1 && (int)(tuple_hash(rec + 2, m0 > 0 ? m0 - 1 : 0) % (unsigned)nshards) != shard) continue;
         __syncwarp();
         for (int i = lane; i < m0; i += 32) path[i] = rec[2 + i];
         __syncwarp();
@@ -1197,6 +1228,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             if (lane == 0) slot = atomicAdd(retry_count, (unsigned)(a - q0));
             slot = __shfl_sync(0xffffffffu, slot, 0);
             if (slot + (unsigned)(a - q0) <= retry_cap) {
+                if (lane == 0) pc[kPathSplit]++;
                 for (int j = q0 + lane; j < a; j += 32) {
                     uint16_t *o = retry_out + (size_t)(slot + (unsigned)(j - q0)) * D.S;
                     o[0] = (uint16_t)(m0 + 1);
@@ -1314,6 +1346,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             if (lane == 0) {
                 hist[depth + 2] += (uint32_t)(nal - nlow);
                 fbase[fd] = base; fa[fd] = a; fq[fd] = q; fE[fd] = E;
+                pc[kPathLevelA]++;
             }
             __syncwarp();
             fd++;
@@ -1336,6 +1369,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     __syncwarp();
     for (int i = lane; i <= kMaxG; i += 32)
         if (hist[i]) atomicAdd(&D.stats->hist[i], (unsigned long long)hist[i]);
+    if (lane < 8 && pc[lane]) atomicAdd(&D.stats->paths[lane], (unsigned long long)pc[lane]);
 }
 
 // ------------------------------------------------------------------------------------------------

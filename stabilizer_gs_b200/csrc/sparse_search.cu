@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -219,7 +220,7 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
     want(&c.order, Tn);
     want(&c.wbest, c.nwbest);
     want(&c.allbest, std::max(nshards, 1));
-    want(&c.hist_sum, kMaxG + 2);
+    want(&c.hist_sum, kStatsSummed);
     want(&c.qA, (size_t)qcap * S);
     want(&c.qB, (size_t)qcap * S);
     want(&c.slow, (size_t)slow_cap * S);
@@ -509,6 +510,7 @@ void SparsePlan::Impl::fill_stats(const SparseStats &tot, sgs_result *out)
         out->sum_2m += (double)tot.hist[i] * std::ldexp(1.0, i);
     }
     out->slow_nodes = tot.slow_nodes;
+    for (int i = 0; i < 7; i++) out->walk_paths[i] = (uint32_t)std::min<unsigned long long>(tot.paths[i], 0xffffffffull);
 }
 
 // result of a shard (rank of a world without communicator) that owns no candidate: energy +inf, no generator
@@ -581,7 +583,7 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         for (auto &c : devs) { sendb.push_back(c.gbest); recvb.push_back(c.allbest); sumb.push_back(c.stats); sts.push_back(c.stream); }
         Status s = nccl->all_gather_bytes(sendb, recvb, sizeof(BestRec), sts);
         if (!s.ok()) return s;
-        s = nccl->all_reduce_sum_u64(sumb, kMaxG + 2, sts);          // hist[0..kMaxG] and slow_nodes are contiguous u64
+        s = nccl->all_reduce_sum_u64(sumb, kStatsSummed, sts);          // hist[0..kMaxG], slow_nodes and paths[] are contiguous u64
         if (!s.ok()) return s;
         for (auto &c : devs) {
             SGS_CUDA_TRY(cudaSetDevice(c.device));
@@ -668,8 +670,10 @@ Status SparsePlan::Impl::run(sgs_result *out)
     memset(out, 0, sizeof(*out));
     if (rp.ok) {
         Status s = W == 1 ? run_replay<1>(out) : (W == 2 ? run_replay<2>(out) : run_replay<4>(out));
-        if (s.ok() || rp.ok) return s;
-        sgs_result_free(out);          // replay diverged: redo adaptively
+        // A diverged replay is redone adaptively only when this process is alone: with a communicator the other
+        // ranks have left their collectives behind, so a second pair here would hang or mismatch — report it.
+        if (s.ok() || rp.ok || nccl) return s;
+        sgs_result_free(out);
         memset(out, 0, sizeof(*out));
     }
     auto local = [&](DevCtx &c) {
@@ -697,15 +701,16 @@ Status SparsePlan::Impl::run(sgs_result *out)
         // then the same deterministic argmin on every GPU
         for (auto &c : devs) {
             cudaSetDevice(c.device);
-            cudaMemcpyAsync(c.hist_sum, c.hstats.hist, sizeof(unsigned long long) * (kMaxG + 1), cudaMemcpyHostToDevice, c.stream);
-            cudaMemcpyAsync(c.hist_sum + kMaxG + 1, &c.hstats.slow_nodes, sizeof(unsigned long long), cudaMemcpyHostToDevice, c.stream);
+            static_assert(offsetof(SparseStats, hist) == 0 && offsetof(SparseStats, error) == sizeof(unsigned long long) * kStatsSummed,
+                          "the summed counters lead SparseStats");
+            cudaMemcpyAsync(c.hist_sum, &c.hstats, sizeof(unsigned long long) * kStatsSummed, cudaMemcpyHostToDevice, c.stream);
         }
         std::vector<void *> sendb, recvb, sumb;
         std::vector<cudaStream_t> sts;
         for (auto &c : devs) { sendb.push_back(c.gbest); recvb.push_back(c.allbest); sumb.push_back(c.hist_sum); sts.push_back(c.stream); }
         Status s = nccl->all_gather_bytes(sendb, recvb, sizeof(BestRec), sts);
         if (!s.ok()) return s;
-        s = nccl->all_reduce_sum_u64(sumb, kMaxG + 2, sts);
+        s = nccl->all_reduce_sum_u64(sumb, kStatsSummed, sts);
         if (!s.ok()) return s;
         for (auto &c : devs) {
             cudaSetDevice(c.device);
@@ -714,12 +719,11 @@ Status SparsePlan::Impl::run(sgs_result *out)
         }
         DevCtx &c0 = devs[0];
         cudaSetDevice(c0.device);
-        unsigned long long hsum[kMaxG + 2];
+        unsigned long long hsum[kStatsSummed];
         SGS_CUDA_TRY(cudaMemcpyAsync(&best, c0.gbest, sizeof(BestRec), cudaMemcpyDeviceToHost, c0.stream));
         SGS_CUDA_TRY(cudaMemcpyAsync(hsum, c0.hist_sum, sizeof(hsum), cudaMemcpyDeviceToHost, c0.stream));
         for (auto &c : devs) { cudaSetDevice(c.device); SGS_CUDA_TRY(cudaStreamSynchronize(c.stream)); }
-        memcpy(tot.hist, hsum, sizeof(unsigned long long) * (kMaxG + 1));
-        tot.slow_nodes = hsum[kMaxG + 1];
+        memcpy(&tot, hsum, sizeof(hsum));
     } else {
         for (size_t i = 1; i < devs.size(); i++) {      // only reachable with world > 1 && nccl_id == NULL per process: no merge
             const BestRec &b = devs[i].hbest;

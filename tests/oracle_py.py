@@ -76,6 +76,8 @@ def lib():
         L.oracle_sparse.argtypes = [C.POINTER(OHam), C.c_int]
         L.oracle_sparse_sample.restype = C.POINTER(ORes)
         L.oracle_sparse_sample.argtypes = [C.POINTER(OHam), C.c_int, C.c_uint64, C.c_double]
+        L.oracle_sparse_stride.restype = C.POINTER(ORes)
+        L.oracle_sparse_stride.argtypes = [C.POINTER(OHam), C.c_int, C.c_int, C.c_int]
         L.oracle_klocal.restype = C.POINTER(ORes)
         L.oracle_klocal.argtypes = [C.POINTER(OHam), C.c_int]
         L.ores_free.argtypes = [C.POINTER(ORes)]
@@ -157,6 +159,17 @@ def sparse_sample(text=None, path=None, threads=1, max_leaves=0, seconds=0.0):
     """bounded sample of the sparse walk: returns candidates visited and seconds"""
     H = _load(text, path)
     r = lib().oracle_sparse_sample(H, threads, max_leaves, seconds)
+    try:
+        return _res(H, r, False)
+    finally:
+        lib().ores_free(r)
+        lib().oham_free(H)
+
+
+def sparse_stride(text=None, path=None, threads=1, stride=16, offset=0):
+    """uniform sample: complete walk of every stride-th depth-2 subtree; returns candidates visited and seconds"""
+    H = _load(text, path)
+    r = lib().oracle_sparse_stride(H, threads, stride, offset)
     try:
         return _res(H, r, False)
     finally:

@@ -1,0 +1,267 @@
+"""GPU parity tests where the benchmark actually runs: mid-size and full-size random instances on which the
+certified clique walk (level B of k_dfs) does almost all the work, compared with the CPU oracle — candidates,
+full rank histogram, energy, generators, term signs — at several prefix depths, on virtual shards (first run of a
+plan = adaptive launch sequence, second run = recorded sequence), with the hand-off rounds and with branch and
+bound.  The goldens tests/golden/oracle_sparse_*.json were written by tests/golden/make_golden_oracle.py
+(oracle/sparse.c = restatement of FullState::evolve, cpp/state.cpp:636-687, itself pinned to the Python reference);
+two further instances are compared with the oracle run live on the box's host cores.
+
+Reference to match: cpp/state.cpp:636-687 (FullState::evolve), cpp/stab.cpp:314-318 (commute),
+:437-449 (canonicalize), :493-511 (decompose/include).
+"""
+import glob
+import json
+import os
+
+import pytest
+
+import gen_hamiltonians as G
+import oracle_py as O
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+ORACLE_GOLDEN = sorted(f for f in glob.glob(os.path.join(GOLDEN, 'oracle_sparse_*.json')) if '24_300_0' not in f)
+CONFIG4 = os.path.join(GOLDEN, 'oracle_sparse_24_300_0.json')
+
+# accumulated over the tests of this module; asserted at the end (test_every_walk_path_was_exercised)
+PATHS = {'w1': [0] * 7, 'w2': [0] * 7}
+NAMES = ['walk32', 'walk64', 'fold_ok', 'fold_full', 'dep_certified', 'not_certified', 'level_a']
+
+
+def sgs():
+    import stabilizer_gs_b200 as S
+    return S
+
+
+def _name(p):
+    return os.path.basename(p)[:-5]
+
+
+def _load(path):
+    g = json.load(open(path))
+    text = G.sparse_text(g['n'], g['nterms'], g['seed'])
+    ref = dict(g['sparse'])
+    ref['rank_hist'] = {int(k): v for k, v in ref.pop('ranks').items()}
+    return g, text, ref
+
+
+def _note(g_n, r):
+    acc = PATHS['w1' if g_n <= 32 else 'w2']
+    for i in range(7):
+        acc[i] += r['walk_paths'][i]
+
+
+def check_same(r, ref):
+    assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10, abs=1e-12)
+    assert r['generators'] == ref['generators']
+    assert r['term_signs'] == ref['term_signs']
+    assert r['candidates'] == ref['candidates']
+    assert {k: v for k, v in r['rank_hist'].items() if v} == {k: v for k, v in ref['rank_hist'].items() if v}
+
+
+@pytest.mark.parametrize('depth', [0, 1, 2])
+@pytest.mark.parametrize('path', ORACLE_GOLDEN, ids=_name)
+def test_midsize_vs_oracle_golden(path, depth):
+    S = sgs()
+    g, text, ref = _load(path)
+    r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=depth)
+    check_same(r, ref)
+    assert r['sum_2m'] == ref['sum_2m']
+    _note(g['n'], r)
+
+
+@pytest.mark.parametrize('n,T,seed', [(28, 150, 11), (40, 160, 12)])
+def test_midsize_vs_live_oracle(n, T, seed):
+    """the same comparison against the oracle run now (not a stored vector)"""
+    S = sgs()
+    text = G.sparse_text(n, T, seed)
+    ref = O.sparse(text=text, threads=os.cpu_count() or 1)
+    for depth in (0, 1):
+        r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=depth)
+        check_same(r, ref)
+        _note(n, r)
+
+
+def _merge(parts):
+    hist = {}
+    for p in parts:
+        for k, v in p['rank_hist'].items():
+            hist[k] = hist.get(k, 0) + v
+    return sum(p['candidates'] for p in parts), {k: v for k, v in hist.items() if v}, min(parts, key=lambda p: p['energy'])
+
+
+@pytest.mark.parametrize('split', [False, True], ids=['one_round', 'hand_off_rounds'])
+@pytest.mark.parametrize('world', [2, 8])
+@pytest.mark.parametrize('path', ORACLE_GOLDEN, ids=_name)
+def test_midsize_virtual_shards(monkeypatch, path, world, split):
+    """every rank of a world without communicator returns its shard: the shards partition the oracle's tree (counts
+    per rank add up to the oracle's histogram) and the best shard holds the oracle's answer — for the first run of a
+    plan (adaptive, host-synchronised) and the second (recorded launch sequence), which must own the SAME roots."""
+    S = sgs()
+    g, text, ref = _load(path)
+    if split:
+        monkeypatch.setenv('SGS_SPLIT', '1')
+    else:
+        monkeypatch.setenv('SGS_NOSPLIT', '1')
+    H = S.HamHandle.from_text(text)
+    first, second = [], []
+    for r in range(world):
+        plan = S.SparsePlan(H, rank=r, world=world)
+        first.append(plan.run())
+        second.append(plan.run())
+        plan.close()
+    for a, b in zip(first, second):      # same partition in both launch sequences
+        assert a['candidates'] == b['candidates'] and a['rank_hist'] == b['rank_hist']
+        assert a['energy'] == b['energy'] and a['generators'] == b['generators']
+    for parts in (first, second, first[:world // 2] + second[world // 2:]):
+        cand, hist, best = _merge(parts)
+        assert cand == ref['candidates'] and hist == ref['rank_hist']
+        assert best['energy'] == pytest.approx(ref['energy'], rel=1e-10) and best['generators'] == ref['generators']
+        assert best['term_signs'] == ref['term_signs']
+    _note(g['n'], first[0])
+
+
+@pytest.mark.parametrize('path', ORACLE_GOLDEN, ids=_name)
+def test_midsize_branch_and_bound(path):
+    S = sgs()
+    g, text, ref = _load(path)
+    H = S.HamHandle.from_text(text)
+    for depth in (0, 1):
+        r = S.sparse_search(H, prune=1, expand_depth=depth)
+        assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10)
+        assert r['generators'] == ref['generators'] and r['term_signs'] == ref['term_signs']
+        assert r['candidates'] <= ref['candidates']
+    parts = [S.sparse_search(H, prune=1, rank=k, world=4) for k in range(4)]
+    best = min(parts, key=lambda p: p['energy'])
+    assert best['energy'] == pytest.approx(ref['energy'], rel=1e-10) and best['generators'] == ref['generators']
+
+
+def _with_dependent_triples(n, T, seed):
+    """a random instance plus a few XX / YY / ZZ triples (XX*YY = -ZZ): sporadic groups with dependent terms, which
+    only some shards meet — the case where one rank's first run needs the exact kernel and another's does not"""
+    lines = G.sparse_text(n, T, seed).splitlines()
+    extra = []
+    for a, b, w in ((0, 1, 0.61), (3, 7, -0.43), (n - 2, n - 1, 0.37)):
+        extra += [f" {w:.10f} XX {a} {b}", f" {-w * 0.7:.10f} YY {a} {b}", f" {w * 0.9:.10f} ZZ {a} {b}"]
+    return '\n'.join([lines[0]] + lines[1:T // 2] + extra + lines[T // 2:]) + '\n'
+
+
+@pytest.mark.parametrize('world', [2, 5])
+def test_plan_reuse_across_ranks_with_sporadic_dependent_terms(world):
+    """the recorded launch sequence of one rank and the adaptive sequence of another must split the
+    tree the same way, whatever each rank's first run met."""
+    S = sgs()
+    text = _with_dependent_triples(16, 60, 4)
+    ref = O.sparse(text=text, threads=4)
+    H = S.HamHandle.from_text(text)
+    one = S.sparse_search(H)
+    check_same(one, ref)
+    runs = [[], [], []]
+    for r in range(world):
+        plan = S.SparsePlan(H, rank=r, world=world)
+        for k in range(3):
+            runs[k].append(plan.run())
+        plan.close()
+    for r in range(world):
+        assert runs[0][r]['candidates'] == runs[1][r]['candidates'] == runs[2][r]['candidates']
+    # any mixture of first and later runs across the ranks is a partition of the tree
+    for pick in ([0] * world, [1] * world, [i % 2 for i in range(world)], [(i + 1) % 3 for i in range(world)]):
+        parts = [runs[pick[r]][r] for r in range(world)]
+        cand, hist, best = _merge(parts)
+        assert cand == ref['candidates'] and hist == {k: v for k, v in ref['rank_hist'].items() if v}
+        assert best['energy'] == pytest.approx(ref['energy'], rel=1e-10) and best['generators'] == ref['generators']
+
+
+def test_rank_limit_is_reported_not_overrun():
+    """more than 64 independent commuting terms (a 70-site ZZ chain) must end with SGS_ERR_LIMIT,
+    never with records written past their slot."""
+    S = sgs()
+    n = 70
+    text = f"{n} 2\n" + ''.join(f" {-1.0 - 0.01 * i:.4f} ZZ {i} {i + 1}\n" for i in range(n - 1))
+    H = S.HamHandle.from_text(text)
+    for kw in (dict(prune=1), dict(prune=1, expand_depth=1)):
+        with pytest.raises(S.SgsError) as e:
+            S.sparse_search(H, **kw)
+        assert e.value.code in (-6, -8)          # SGS_ERR_LIMIT (or a queue overflow on the way there)
+    # the device is still healthy afterwards
+    r = S.sparse_search(S.HamHandle.from_text(G.sparse_text(8, 20, 1)))
+    assert r['candidates'] > 0
+
+
+@pytest.mark.skipif(not os.path.exists(CONFIG4), reason='config-4 oracle golden not generated')
+def test_config4_vs_oracle_golden():
+    """BASELINE configs[3] — the benchmark's workload — against the oracle's complete walk (81 206 511 leaves)"""
+    S = sgs()
+    g, text, ref = _load(CONFIG4)
+    assert ref['candidates'] == 81206511
+    H = S.HamHandle.from_text(text)
+    plan = S.SparsePlan(H)
+    for _ in range(2):                       # adaptive run, then the recorded launch sequence the bench times
+        r = plan.run()
+        check_same(r, ref)
+        assert r['sum_2m'] == ref['sum_2m']
+    plan.close()
+    _note(24, r)
+    r = S.sparse_search(H, expand_depth=2)
+    check_same(r, ref)
+    r = S.sparse_search(H, prune=1)
+    assert r['energy'] == pytest.approx(ref['energy'], rel=1e-10) and r['generators'] == ref['generators']
+    assert r['term_signs'] == ref['term_signs']
+    parts = [S.sparse_search(H, rank=k, world=8) for k in range(8)]
+    cand, hist, best = _merge(parts)
+    assert cand == ref['candidates'] and hist == ref['rank_hist'] and best['generators'] == ref['generators']
+
+
+def _invariants(S, text, r):
+    H = S.HamHandle.from_text(text)
+    rows, w, b, e = H.terms()
+    assert r['energy'] == pytest.approx(sum(wi * si for wi, si in zip(w, r['term_signs'])), rel=1e-10)
+    code = {'I': 0, 'Z': 1, 'X': 2, 'Y': 3}
+    gb = [sum(code[ch] << (2 * j) for j, ch in enumerate(s[1:])) for s in r['generators']]
+    ev = int('01' * 128, 2)
+    sw = lambda x: ((x >> 1) & ev) | ((x & ev) << 1)
+    for i in range(len(gb)):
+        for j in range(i):
+            assert bin(gb[i] & sw(gb[j])).count('1') % 2 == 0          # generators commute
+    piv = [(x & -x).bit_length() - 1 for x in gb]
+    assert piv == sorted(piv) and len(set(piv)) == len(piv)          # RREF order
+    for i, p in enumerate(piv):
+        assert all(not (x >> p) & 1 for j, x in enumerate(gb) if j != i)
+    # every in-group term sign is reproduced by the canonical generators (Stab::energy)
+    from stabilizer_gs_b200.pauli import Pauli
+    from stabilizer_gs_b200.stab import StabilizerGroup
+    n = H.n
+    gens = Pauli.from_packed([[((x >> (64 * k)) & (2 ** 64 - 1)) for k in range((2 * n + 63) // 64)] for x in gb],
+                             [1 if s[0] == '+' else -1 for s in r['generators']], n)
+    st = StabilizerGroup(gens, canonicalized=True)
+    terms = Pauli.from_packed(rows, [1] * len(rows), n)
+    assert [int(v) for v in st.get_energy(terms)] == r['term_signs']
+
+
+def test_config5_full_size():
+    """BASELINE configs[4], the north-star target (n=40, T=1000, W=2; ~20 s on one B200): the candidate count is the
+    one every earlier build and every shard count has produced, E = sum w*sign, the generators are canonical,
+    commute and reproduce the term signs, and branch and bound returns the same ground state."""
+    S = sgs()
+    text = G.sparse_text(40, 1000, 0)
+    H = S.HamHandle.from_text(text)
+    r = S.sparse_search(H)
+    assert r['candidates'] == 265058149351
+    assert r['energy'] == pytest.approx(-10.5788174847, abs=1e-9) and r['m'] == 13
+    _invariants(S, text, r)
+    _note(40, r)
+    p = S.sparse_search(H, prune=1)
+    assert p['energy'] == r['energy'] and p['generators'] == r['generators'] and p['term_signs'] == r['term_signs']
+    assert p['candidates'] < r['candidates']
+
+
+def test_every_walk_path_was_exercised():
+    """(runs last in this module) the comparisons above went through both clique-walk mask widths, the folded-image
+    certificate of multi-word rows and the warp-cooperative level A"""
+    w1, w2 = PATHS['w1'], PATHS['w2']
+    print('walk paths W=1:', dict(zip(NAMES, w1)), ' W=2:', dict(zip(NAMES, w2)))
+    assert w1[0] > 0 and w1[1] > 0, 'W=1: both mask widths of lb_walk'
+    assert w2[0] > 0 and w2[1] > 0, 'W=2: both mask widths of lb_walk'
+    assert w2[2] > 0, 'W=2: folded-image certificate'
+    assert w1[6] > 0 and w2[6] > 0, 'level-A descent below a root'
