@@ -27,7 +27,13 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.avg.per_cycle_active',
         'sm__cycles_elapsed.max', 'sm__cycles_active.avg', 'smsp__cycles_active.avg', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
-        'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
+        'sm__warps_active.avg.per_cycle_active', 'smsp__thread_inst_executed_pred_on_per_inst_executed.ratio',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio', 'sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_cbu.sum.pct_of_peak_sustained_active', 'l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct',
+        'l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_local_op_st.sum', 'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
         'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio', 'smsp__average_warp_latency_issue_stalled_wait.ratio',
         'smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio', 'smsp__average_warp_latency_issue_stalled_no_instruction.ratio',
         'smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio', 'smsp__average_warp_latency_issue_stalled_not_selected.ratio',
@@ -81,8 +87,14 @@ def main():
             gpu_time_ms=num('gpu__time_duration.sum'),
             inst_executed=num('smsp__inst_executed.sum'),
             thread_inst_executed=num('smsp__inst_executed.sum') * num('smsp__thread_inst_executed_per_inst_executed.ratio'),
-            inst_executed_pipe_alu=num('smsp__inst_executed_pipe_alu.sum'), inst_executed_pipe_xu=num('smsp__inst_executed_pipe_xu.sum'),
-            inst_executed_pipe_lsu=num('smsp__inst_executed_pipe_lsu.sum'),
+            # ALU-pipe warp instructions of the launch: ncu reports the pipe as % of its peak (64 lanes = 2 warp
+            # instructions per cycle and SM) over the active cycles
+            sm_cycles_active_avg=num('sm__cycles_active.avg'), sm_count=148,
+            inst_executed_pipe_alu=num('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active') / 100.0 * 2.0
+            * num('sm__cycles_active.avg') * 148,
+            xu_pct_of_peak_ncu=num('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'),
+            lsu_pct_of_peak_ncu=num('sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active'),
+            warps_active_per_sm=num('sm__warps_active.avg.per_cycle_active'),
             alu_pct_of_peak_ncu=num('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active'),
             issue_active_pct_ncu=num('smsp__issue_active.avg.pct_of_peak_sustained_active'),
             dram_bytes=num('dram__bytes_read.sum') + num('dram__bytes_write.sum'),

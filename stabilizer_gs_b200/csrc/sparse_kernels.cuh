@@ -309,6 +309,7 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
     __syncwarp();
 
     for (unsigned node = gw; node < nin; node += nw) {
+        if (*(volatile unsigned int *)&D.stats->error) break;      // a limit was hit somewhere: the search is void, stop early
         const uint16_t *rec = in + (size_t)node * D.S;
         const int m = rec[0];
         const unsigned flags = rec[1];
@@ -563,21 +564,29 @@ __global__ void k_class_scatter(const uint16_t *__restrict__ items, unsigned n, 
 
 // ------------------------------------------------------------------------------------------------
 // k_dfs: the hot kernel.
+// Shared memory of one warp.  The arena is what bounds the occupancy of the hot kernel, so everything that is not
+// a list entry is kept small: the root's echelon basis and the level-B commutation matrix share one region (the
+// basis is dead once the root's residues are written), the warp-cooperative level A keeps at most kMaxFramesA
+// frames (a deeper chain of uncertifiable lists goes to the exact kernel), the suffix sums exist only in the
+// branch-and-bound build.
+constexpr int kMaxFramesA = 24;
 template <int W>
-__host__ __device__ inline size_t dfs_smem_bytes(int cap)
+__host__ __device__ inline size_t dfs_scratch_bytes() { return (size_t)(32 * W * 8 > 64 * 8 + 32 * 4 ? 32 * W * 8 : 64 * 8 + 32 * 4); }
+template <int W>
+__host__ __device__ inline size_t dfs_smem_bytes(int cap, bool prune)
 {
     size_t b = 0;
     b += (size_t)cap * W * 8;          // residues
     b += (size_t)cap * 8;              // |w| of each list entry
-    b += (size_t)32 * W * 8;           // basis (subtree-root setup)
-    b += (size_t)64 * 8 + 32 * 4;      // level-B commutation bit-matrix (64-bit and 32-bit forms)
-    b += (size_t)kMaxFrames * 8;       // frame E
-    b += (size_t)kMaxFrames * 4 * 3;   // frame base, a, q
+    b += dfs_scratch_bytes<W>();       // root basis, later the level-B commutation bit-matrix (64-bit or 32-bit form)
+    b += (size_t)kMaxFramesA * 8;      // frame E
+    b += (size_t)kMaxFramesA * 4 * 3;  // frame base, a, q
     b += (size_t)(kMaxG + 1) * 4 + 4;  // hist
     b += (size_t)cap * 2;              // term indices
     b += (size_t)kMaxG * 2 * 2;        // path, best tuple
     b += 64;                           // basis pivots
-    b += 64 * 8 + 8;                   // suffix sums of the candidate weights (branch-and-bound mode), 8-byte aligned
+    b += 8;                            // alignment slack
+    if (prune) b += 64 * 8;            // suffix sums of the candidate weights (branch-and-bound mode)
     b += 8 * 4;                        // code-path counters
     return (b + 15) & ~(size_t)15;
 }
@@ -631,98 +640,183 @@ SGS_D int ctz_mask(uint64_t v) { return __ffsll((long long)v) - 1; }
 SGS_D int popc_mask(uint32_t v) { return __popc(v); }
 SGS_D int popc_mask(uint64_t v) { return __popcll(v); }
 
-// lane-private walk over the cliques of the candidates (vertices 0..ncand-1 = list positions nlow..n-1,
-// ADm[v] = neighbours of v with a higher index).  Work is dealt by the SECOND vertex: lane l (and l + 32)
-// walks every clique {f, l, ...} over its lower neighbours f (dn = bitmask of them) — far better balanced
-// than dealing by the lowest vertex — plus the singleton {l}.  Counts candidates per rank in hc[], keeps the
-// heaviest maximal clique; within a lane the first found wins ties (= lexicographic order, a longer tuple
-// before its prefix); lanes are ordered afterwards by (first vertex, second vertex).
+// is clique A (a bit mask over the list positions) before clique B in the include-first leaf order?  The sorted
+// vertex sequences agree below the lowest differing bit; the clique that HAS that bit continues with a smaller
+// vertex, or continues where the other has ended ("end of tuple" sorts last): it comes first.
+template <typename M>
+SGS_D bool clique_before(M A, M B) { const M x = A ^ B; return (A & (x & ((M)0 - x))) != 0; }
+
+// Walk over the cliques of the candidates (vertices 0..ncand-1 = list positions nlow..n-1, ADm[v] = neighbours of v
+// with a higher index).  Work is dealt by the SECOND vertex: a work item (l, dn) is "every clique {f, l, ...} with f
+// in dn, a set of lower neighbours of l" — far better balanced than dealing by the lowest vertex — plus, for the
+// item's owner, the singleton {l}.  A lane has up to two items.  Counts candidates per rank in hc[], keeps the
+// heaviest clique; ties go to the clique that comes first in the leaf order (clique_before), so neither the deal
+// nor the order of the walk matters.
+//
+// The loop is WARP-CONVERGED: all 32 lanes run the same iteration (at most one pop, then one vertex) until the
+// last lane has finished; the branches inside are short and rejoin before the vote.  (Left to themselves the lanes
+// drift apart through the pop / leaf / push branches and the walk issues with 3-6 active lanes per instruction:
+// ncu, profiles/r02_k_dfs_config4_ncu_source_top_before.csv.)  The two innermost frames live in registers
+// (c0/w0/m0: frame d, c1/w1/m1: frame d - 1), the local-memory stack holds frames 0..d-2: a push stores the old
+// parent, a pop reloads the new parent one pop ahead of its use.  A frame whose last vertex is being expanded is
+// not kept (rest == 0: nothing to come back to), so a pop always lands on a frame with work — except frame 0.
 // PRUNE (branch and bound): SW[v] = sum of the weights of the vertices >= v; a branch whose best conceivable
 // weight (current + every vertex from its lowest remaining candidate on) stays below `need` is not entered.
 template <typename M, bool PRUNE>
-SGS_D void lb_walk(const M *ADm, const double *WAc, int ncand, int depth, uint32_t *hc, double &bw, M &bm, M dn0, M dn1, int lane,
+SGS_D void lb_walk(const M *ADm, const double *WAc, int depth, uint32_t *hc, double &bw, M &bm, int la, M dna, bool owna, int lb, M dnb,
                    const double *SW, double need)
 {
     M cand[kMaxLB], cm[kMaxLB];
     double ws[kMaxLB];
+    int item = 0, d = 0;
+    M c0 = 0, m0 = 0, c1 = 0, m1 = 0, upl = 0;
+    double w0 = 0.0, w1 = 0.0;
+    bool alive = true;
 #pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        const int l = pass == 0 ? lane : lane + 32;
-        if (l >= ncand) break;
-        M dn = pass == 0 ? dn0 : dn1;
-        const M upl = ADm[l];
-        const double wl = WAc[l];
-        hc[depth + 1] += 1;
-        hc[depth + 2] += popc_mask(dn);
-        // one flat loop: frame 0 deals the lower neighbours f (its children are upl & AD[f]), deeper frames are
-        // the usual "candidates & AD[v]" — the same instruction path for every lane whatever its depth
-        if constexpr (sizeof(M) == 4) {
-            // The two innermost frames live in registers (c0/w0/m0: frame d, c1/w1/m1: frame d - 1), the local-memory
-            // stack holds frames 0..d-2: an iteration that neither pushes nor pops touches no memory, a push stores the
-            // old parent and a pop reloads the new parent one pop ahead of its use (the loop is latency-bound).
-            int d = 0;
-            M c0 = dn, m0 = (M)1 << l, c1 = 0, m1 = 0;
-            double w0 = wl, w1 = 0.0;
-            for (;;) {
-                if (c0 == 0) {
-                    if (d == 0) break;
-                    d--;
-                    c0 = c1; w0 = w1; m0 = m1;
-                    if (d >= 1) { c1 = cand[d - 1]; w1 = ws[d - 1]; m1 = cm[d - 1]; }
-                    continue;
-                }
-                const M cc = c0;
-                const int v = ctz_mask(cc);
-                c0 = cc & (cc - 1);
-                const M nc = (d == 0 ? upl : cc) & ADm[v];
-                const double nw = w0 + WAc[v];
-                if (nc == 0) {
-                    if (nw > bw) { bw = nw; bm = m0 | ((M)1 << v); }
-                } else if (PRUNE && nw + SW[ctz_mask(nc)] < need) {
-                    // nothing below can reach the incumbent; the clique itself cannot either (it is lighter still)
-                } else {
-                    hc[depth + 3 + d] += popc_mask(nc);
-                    if (d >= 1) { cand[d - 1] = c1; ws[d - 1] = w1; cm[d - 1] = m1; }
-                    c1 = c0; w1 = w0; m1 = m0;
-                    d++;
-                    c0 = nc; w0 = nw; m0 = m1 | ((M)1 << v);
-                }
-            }
-        } else {
-            // 64-bit masks (more than 32 candidates): the register-cached frames cost more in spills than they save
-            // (measured: +2 % at n=40/T=500), the whole stack stays in local memory
-            int d = 0;
-            cand[0] = dn; ws[0] = wl; cm[0] = (M)1 << l;
-            while (d >= 0) {
-                const M cc = cand[d];
-                if (cc == 0) { d--; continue; }
-                const int v = ctz_mask(cc);
-                cand[d] = cc & (cc - 1);
-                const M nc = (d == 0 ? upl : cc) & ADm[v];
-                const double nw = ws[d] + WAc[v];
-                if (nc == 0) {
-                    if (nw > bw) { bw = nw; bm = cm[d] | ((M)1 << v); }
-                } else if (PRUNE && nw + SW[ctz_mask(nc)] < need) {
-                    // nothing below can reach the incumbent; the clique itself cannot either (it is lighter still)
-                } else {
-                    hc[depth + 3 + d] += popc_mask(nc);
-                    cm[d + 1] = cm[d] | ((M)1 << v);
-                    d++;
-                    cand[d] = nc; ws[d] = nw;
+    while (__any_sync(0xffffffffu, alive)) {
+        if (c0 == 0) {
+            if (d > 0) {
+                d--;
+                c0 = c1; w0 = w1; m0 = m1;
+                if (d >= 1) { c1 = cand[d - 1]; w1 = ws[d - 1]; m1 = cm[d - 1]; }
+            } else if (alive) {
+                // next work item of this lane (at most two per call: rare, may diverge)
+                const int l = item == 0 ? la : lb;
+                if (item >= 2 || l < 0) alive = false;
+                else {
+                    const M dn = item == 0 ? dna : dnb;
+                    const bool own = item == 0 ? owna : true;
+                    item++;
+                    upl = ADm[l];
+                    w0 = WAc[l];
+                    m0 = (M)1 << l;
+                    c0 = dn;
+                    hc[depth + 2] += popc_mask(dn);
+                    if (own) {
+                        hc[depth + 1] += 1;
+                        if (w0 > bw || (w0 == bw && clique_before(m0, bm))) { bw = w0; bm = m0; }
+                    }
                 }
             }
         }
-        if (upl == 0 && wl > bw) { bw = wl; bm = (M)1 << l; }      // the singleton comes after every {f, l, ...}
+        if (c0 != 0) {
+            const int v = ctz_mask(c0);
+            const M rest = c0 & (c0 - 1);
+            const M nc = (d == 0 ? upl : rest) & ADm[v];
+            const double nw = w0 + WAc[v];
+            if (nc == 0) {
+                if (nw >= bw) {
+                    const M cur = m0 | ((M)1 << v);
+                    if (nw > bw || clique_before(cur, bm)) { bw = nw; bm = cur; }
+                }
+                c0 = rest;
+            } else if (PRUNE && nw + SW[ctz_mask(nc)] < need) {
+                c0 = rest;       // nothing below can reach the incumbent; the clique itself cannot either (it is lighter still)
+            } else {
+                hc[depth + 2 + popc_mask(m0)] += popc_mask(nc);
+                if (rest != 0 || d == 0) {
+                    if (d >= 1) { cand[d - 1] = c1; ws[d - 1] = w1; cm[d - 1] = m1; }
+                    c1 = rest; w1 = w0; m1 = m0;
+                    d++;
+                }
+                c0 = nc; w0 = nw; m0 |= (M)1 << v;
+            }
+        }
     }
 }
 
-// Are the n one-word rows (row i in p0 of lane i, row i + 32 in p1 of lane i) linearly DEPENDENT?  Forward
-// elimination across the lanes, two pivots per step so that the shuffle -> lowest bit -> test -> XOR chains of
-// consecutive pivots overlap (the loop is latency-bound).
-SGS_D bool rows_dependent_1w(uint64_t p0, uint64_t p1, int n, int lane)
+// The walk for frames with at most 32 candidates and at most kMaxEdges edges (almost all of them): work items are
+// the EDGES (f, l) of the candidates' commutation graph — "every clique whose two lowest vertices are f < l" — listed
+// in shared memory (EL[e] = l | f << 8, l ascending: heavy items first) and dealt DYNAMICALLY: whenever lanes are
+// idle at the top of an iteration they take the next items off the list, numbered by a ballot (the list cursor is a
+// warp-uniform register: no atomics).  An edge's subtree holds 3-4 cliques on average, so the lanes stay level where
+// a deal by vertex leaves three quarters of them idle (measured: 7 of 32 lanes busy per iteration).
+// Same warp-converged iteration as lb_walk: at most one pop, then one vertex.  The member mask needs no stack: the
+// members above l are added in increasing order and all lie below the lowest remaining candidate of the frame a pop
+// returns to, except the vertex that frame had just expanded — the highest of them.  Candidates per rank are counted
+// in byte fields of a register (clique sizes 3-6; larger ones go straight to hc[]) and flushed every 255 iterations.
+constexpr int kMaxEdges = 256;
+template <bool PRUNE>
+SGS_D void lb_walk_edges(const uint32_t *ADm, const double *WAc, const uint16_t *EL, int nedges, int depth, uint32_t *hc, double &bw,
+                         uint32_t &bm, uint32_t ltmask, const double *SW, double need)
+{
+    uint32_t cand[32];
+    double ws[32];
+    int d = 0, next = 0, iter = 0;
+    uint32_t c0 = 0, m0 = 0, c1 = 0, cnt = 0;
+    double w0 = 0.0, w1 = 0.0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < 4; k++) hc[depth + 3 + k] += (cnt >> (8 * k)) & 255u;
+        cnt = 0;
+    };
+#pragma unroll 1
+    for (;;) {
+        const bool idle = c0 == 0 && d == 0;
+        const unsigned nb = __ballot_sync(0xffffffffu, idle);
+        if (nb) {
+            if (next >= nedges) { if (nb == 0xffffffffu) break; }
+            else {
+                const int e = next + __popc(nb & ltmask);
+                next += __popc(nb);
+                if (idle && e < nedges) {
+                    const unsigned it = EL[e];
+                    const int l = it & 255, f = it >> 8;
+                    c0 = ADm[l] & ADm[f];
+                    w0 = WAc[l] + WAc[f];
+                    m0 = (1u << l) | (1u << f);
+                    if (c0 == 0 && w0 >= bw && (w0 > bw || clique_before(m0, bm))) { bw = w0; bm = m0; }
+                }
+            }
+        }
+        if (c0 == 0 && d > 0) {
+            // pop: the frame below has candidates left (a frame is only kept with rest != 0)
+            d--;
+            c0 = c1; w0 = w1;
+            m0 &= (c0 & (0u - c0)) - 1u;                      // members below the frame's lowest remaining candidate ...
+            m0 &= ~(0x80000000u >> __clz((int)m0));            // ... minus the highest: the vertex expanded last
+            if (d >= 1) { c1 = cand[d - 1]; w1 = ws[d - 1]; }
+        }
+        if (c0 != 0) {
+            const int v = __ffs((int)c0) - 1;
+            const uint32_t rest = c0 & (c0 - 1);
+            const uint32_t nc = rest & ADm[v];
+            const double nw = w0 + WAc[v];
+            const int sz = __popc(m0);                         // the new clique has sz + 1 vertices
+            if (sz <= 5) cnt += 1u << (8 * (sz - 2));
+            else hc[depth + sz + 1] += 1;
+            if (nc == 0) {
+                if (nw >= bw) {
+                    const uint32_t cur = m0 | (1u << v);
+                    if (nw > bw || clique_before(cur, bm)) { bw = nw; bm = cur; }
+                }
+                c0 = rest;
+            } else if (PRUNE && nw + SW[__ffs((int)nc) - 1] < need) {
+                c0 = rest;       // nothing below can reach the incumbent; the clique itself cannot either (it is lighter still)
+            } else {
+                if (rest != 0) {
+                    if (d >= 1) { cand[d - 1] = c1; ws[d - 1] = w1; }
+                    c1 = rest; w1 = w0;
+                    d++;
+                }
+                c0 = nc; w0 = nw; m0 |= 1u << v;
+            }
+        }
+        if (++iter == 255) { flush(); iter = 0; }
+    }
+    flush();
+}
+
+// The certificate of level B on one-word rows (row i in p0 of lane i, row i + 32 in p1 of lane i): are the CANDIDATE
+// rows (positions nlow..n-1) linearly dependent, or does a LOWER row (positions 0..nlow-1) lie in their span?
+// Forward elimination across the lanes with the candidates as the only pivots — the lower rows are reduced along
+// and must stay non-zero — two pivots per step so that the shuffle -> lowest bit -> test -> XOR chains of
+// consecutive pivots overlap (the loop is latency-bound).  Half the pivots of an elimination of all n rows.
+SGS_D bool rows_dependent_1w(uint64_t p0, uint64_t p1, int n, int nlow, int lane)
 {
     const bool two = n > 32;
-    int u = 0;
+    const bool low0 = lane < nlow, low1 = lane + 32 < nlow;
+    int u = nlow;
 #pragma unroll 1
     for (; u + 1 < n; u += 2) {
         const uint64_t c0 = __shfl_sync(0xffffffffu, u < 32 ? p0 : p1, u & 31);
@@ -732,17 +826,23 @@ SGS_D bool rows_dependent_1w(uint64_t p0, uint64_t p1, int n, int lane)
         if (c1 & l0) c1 ^= c0;
         if (c1 == 0) return true;
         const uint64_t l1 = c1 & (0 - c1);
-        if (lane > u + 1) {
+        if (lane > u + 1 || low0) {
             if (p0 & l0) p0 ^= c0;
             if (p0 & l1) p0 ^= c1;
         }
-        if (two && lane + 32 > u + 1) {
+        if (two && (lane + 32 > u + 1 || low1)) {
             if (p1 & l0) p1 ^= c0;
             if (p1 & l1) p1 ^= c1;
         }
     }
-    if (u < n) return __shfl_sync(0xffffffffu, u < 32 ? p0 : p1, u & 31) == 0;
-    return false;
+    if (u < n) {
+        const uint64_t c0 = __shfl_sync(0xffffffffu, u < 32 ? p0 : p1, u & 31);
+        if (c0 == 0) return true;
+        const uint64_t l0 = c0 & (0 - c0);
+        if (low0 && (p0 & l0)) p0 ^= c0;
+        if (low1 && (p1 & l0)) p1 ^= c0;
+    }
+    return __any_sync(0xffffffffu, (low0 && p0 == 0) || (low1 && p1 == 0));
 }
 
 // expected number of cliques of a graph with n vertices and e edges (edge density p): sum_k C(n,k) p^(k(k-1)/2)
@@ -765,9 +865,14 @@ template <int W, bool PRUNE>
 __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, int n, int nlow, int depth,
                   uint32_t *hc, double &bw, uint64_t &bm, int lane, float split_cliques, double *SW, double need, uint32_t *pc)
 {
-    // 1. independence of ALL n residues (lower-index entries included: a dependency through one of them would
-    //    make a later child non-canonical).  Own rows: entries lane and lane + 32; step u broadcasts the
-    //    (already reduced) copy of entry u and clears its lowest set bit from the later rows.
+    // 1. the certificate: the residues of the CANDIDATES (positions nlow..n-1) are linearly independent and no
+    //    lower-index entry lies in their span.  Then, for every clique K of candidates, the group <G, K> has rank
+    //    |K| more, holds no alive term besides K (such a term's residue would lie in span(K)) and every step of
+    //    its canonical generating sequence is valid (a lower-index term in the coset of a new generator would lie
+    //    in the span of K as well).  Dependencies among the lower entries themselves are irrelevant: they can
+    //    never become generators below this frame.  Own rows: entries lane and lane + 32; step u broadcasts the
+    //    (already reduced) copy of candidate u and clears its lowest set bit from the later candidates and from
+    //    the lower rows.
     const bool two = n > 32;
     uint64_t e0[W], e1[W];
 #pragma unroll
@@ -788,35 +893,43 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
             p0 ^= (e0[k] << rot) | (e0[k] >> (64 - rot));
             p1 ^= (e1[k] << rot) | (e1[k] >> (64 - rot));
         }
-        const bool dep = rows_dependent_1w(p0, p1, n, lane);
+        const bool dep = rows_dependent_1w(p0, p1, n, nlow, lane);
         proven = !dep;
         if (lane == 0) pc[dep ? kPathFoldFull : kPathFoldOk]++;
     }
     if (W == 1) {
-        dependent = rows_dependent_1w(e0[0], e1[0], n, lane);
+        dependent = rows_dependent_1w(e0[0], e1[0], n, nlow, lane);
         proven = true;
     }
+    if (!proven) {          // full-width elimination, same scheme (multi-word rows whose folded image was inconclusive)
 #pragma unroll 1
-    for (int u = 0; u < n && !proven; u++) {
-        uint64_t cu[W], lm[W];
-        bool nz = false;
+        for (int u = nlow; u < n; u++) {
+            uint64_t cu[W], lm[W];
+            bool nz = false;
 #pragma unroll
-        for (int k = 0; k < W; k++) {
-            cu[k] = __shfl_sync(0xffffffffu, u < 32 ? e0[k] : e1[k], u & 31);
-            lm[k] = nz ? 0 : (cu[k] & (0 - cu[k]));
-            nz |= cu[k] != 0;
+            for (int k = 0; k < W; k++) {
+                cu[k] = __shfl_sync(0xffffffffu, u < 32 ? e0[k] : e1[k], u & 31);
+                lm[k] = nz ? 0 : (cu[k] & (0 - cu[k]));
+                nz |= cu[k] != 0;
+            }
+            if (!nz) { dependent = true; break; }
+            uint64_t h0 = 0, h1 = 0;
+#pragma unroll
+            for (int k = 0; k < W; k++) { h0 |= e0[k] & lm[k]; h1 |= e1[k] & lm[k]; }
+            if ((lane > u || lane < nlow) && h0) {
+#pragma unroll
+                for (int k = 0; k < W; k++) e0[k] ^= cu[k];
+            }
+            if (two && (lane + 32 > u || lane + 32 < nlow) && h1) {
+#pragma unroll
+                for (int k = 0; k < W; k++) e1[k] ^= cu[k];
+            }
         }
-        if (!nz) { dependent = true; break; }
-        uint64_t h0 = 0, h1 = 0;
+        if (!dependent) {
+            uint64_t z0 = 0, z1 = 0;
 #pragma unroll
-        for (int k = 0; k < W; k++) { h0 |= e0[k] & lm[k]; h1 |= e1[k] & lm[k]; }
-        if (lane > u && h0) {
-#pragma unroll
-            for (int k = 0; k < W; k++) e0[k] ^= cu[k];
-        }
-        if (two && lane + 32 > u && h1) {
-#pragma unroll
-            for (int k = 0; k < W; k++) e1[k] ^= cu[k];
+            for (int k = 0; k < W; k++) { z0 |= e0[k]; z1 |= e1[k]; }
+            dependent = __any_sync(0xffffffffu, (lane < nlow && z0 == 0) || (lane + 32 < nlow && z1 == 0));
         }
     }
     uint64_t adj0 = 0, adj1 = 0;
@@ -936,9 +1049,40 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         }
         if (lane < ncand) AD32[lane] = up32;
         if (lane == 0) pc[kPathWalk32]++;
+        // edge list (aliases the 64-bit matrix, unused here): lane l lists its lower neighbours
+        const uint32_t dnl = lane < ncand ? (a32 & ((1u << lane) - 1u)) : 0u;
+        int eoff = __popc(dnl);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, eoff, o);
+            if (lane >= o) eoff += y;
+        }
+        const int nedges = __shfl_sync(0xffffffffu, eoff, 31);
+        if (nedges <= kMaxEdges) {
+            uint16_t *EL = (uint16_t *)AD;
+            eoff -= __popc(dnl);
+            for (uint32_t x = dnl; x; x &= x - 1) EL[eoff++] = (uint16_t)(lane | ((__ffs((int)x) - 1) << 8));
+            __syncwarp();
+            // singletons and pairs are counted here; a singleton is the best clique only if its vertex is isolated
+            if (lane == 0) { hc[depth + 1] += (uint32_t)ncand; hc[depth + 2] += (uint32_t)nedges; }
+            uint32_t bm32 = 0;
+            if (lane < ncand) { bw = WA[nlow + lane]; bm32 = 1u << lane; }
+            lb_walk_edges<PRUNE>(AD32, WA + nlow, EL, nedges, depth, hc, bw, bm32, (1u << lane) - 1u, SW, need);
+            bm = (uint64_t)bm32 << nlow;
+            __syncwarp();
+            return 1;
+        }
         __syncwarp();
+        // (more than kMaxEdges edges) deal by vertex: l = lane mod p (p = the power of two >= ncand); with k = 32 / p > 1 the lower neighbours of
+        // l are striped over k lanes (f mod k == s), so that short lists still use the whole warp
+        int lg = 0;
+        while ((1 << lg) < ncand) lg++;
+        const int k = 32 >> lg, l = lane & ((1 << lg) - 1), st = lane >> lg;
+        const uint32_t al = __shfl_sync(0xffffffffu, a32, l);
+        const uint32_t stripe = (k == 1 ? 0xffffffffu : k == 2 ? 0x55555555u : k == 4 ? 0x11111111u : k == 8 ? 0x01010101u : k == 16 ? 0x00010001u : 1u) << st;
+        const bool has = l < ncand;
         uint32_t bm32 = 0;
-        lb_walk<uint32_t, PRUNE>(AD32, WA + nlow, ncand, depth, hc, bw, bm32, a32 & ((1u << lane) - 1u), 0u, lane, SW, need);
+        lb_walk<uint32_t, PRUNE>(AD32, WA + nlow, depth, hc, bw, bm32, has ? l : -1, has ? (al & ((1u << l) - 1u) & stripe) : 0u, st == 0, -1, 0u, SW, need);
         bm = (uint64_t)bm32 << nlow;
     } else {
         uint64_t sc0[W], sc1[W];
@@ -968,8 +1112,8 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         if (lane == 0) pc[kPathWalk64]++;
         __syncwarp();
         uint64_t bmr = 0;
-        lb_walk<uint64_t, PRUNE>(AD, WA + nlow, ncand, depth, hc, bw, bmr, a0 & ((1ULL << lane) - 1ULL), a1 & ((1ULL << (lane + 32)) - 1ULL), lane, SW,
-                                 need);
+        lb_walk<uint64_t, PRUNE>(AD, WA + nlow, depth, hc, bw, bmr, lane, a0 & ((1ULL << lane) - 1ULL), true, lane + 32 < ncand ? lane + 32 : -1,
+                                 a1 & ((1ULL << (lane + 32)) - 1ULL), SW, need);
         bm = bmr << nlow;
     }
     __syncwarp();
@@ -986,26 +1130,18 @@ __device__ __noinline__ bool best_update(double Eval, int len, double bestE, int
     return true;
 }
 
-// cold tail of a level-B walk whose best clique reaches the incumbent: warp argmax of (weight, then lowest first
-// vertex, then lowest second vertex; a singleton last), the clique's terms appended to path[depth..).  Returns the
-// clique size and its weight.
+// cold tail of a level-B walk whose best clique reaches the incumbent: warp argmax of (weight, then the clique that
+// comes first in the leaf order), the clique's terms appended to path[depth..).  Returns the clique size and weight.
 __device__ __noinline__ int level_b_pick(double bw, uint64_t bm, const uint16_t *TTlb, uint16_t *path, int depth, int lane, double *wout)
 {
     double w = bm ? bw : -1.0;
-    int key = 1 << 20;
-    if (bm) {
-        const uint64_t rest = bm & (bm - 1);
-        key = ctz64(bm) * 128 + (rest ? ctz64(rest) : 127);
-    }
-    int src = lane;
+    uint64_t mask = bm;
 #pragma unroll 1
     for (int d = 16; d > 0; d >>= 1) {
         const double ow = __shfl_xor_sync(0xffffffffu, w, d);
-        const int ok = __shfl_xor_sync(0xffffffffu, key, d);
-        const int os = __shfl_xor_sync(0xffffffffu, src, d);
-        if (ow > w || (ow == w && ok < key)) { w = ow; key = ok; src = os; }
+        const uint64_t om = __shfl_xor_sync(0xffffffffu, mask, d);
+        if (ow > w || (ow == w && om != mask && clique_before(om, mask))) { w = ow; mask = om; }
     }
-    const uint64_t mask = __shfl_sync(0xffffffffu, bm, src);
     if (lane == 0) {
         uint64_t mm = mask;
         int l2 = depth;
@@ -1016,8 +1152,18 @@ __device__ __noinline__ int level_b_pick(double bw, uint64_t bm, const uint16_t 
     return popc64(mask);
 }
 
+// launch geometry: blocks of kDfsWpb warps (the warps of a block share nothing: small blocks only make the shared-
+// memory granularity finer); kDfsMinBlocks caps the registers (65536 / (32 * kDfsWpb * kDfsMinBlocks) per thread)
+#ifndef SGS_DFS_WPB
+#define SGS_DFS_WPB 4
+#endif
+#ifndef SGS_DFS_MINB
+#define SGS_DFS_MINB 6
+#endif
+constexpr int kDfsWpb = SGS_DFS_WPB, kDfsMinBlocks = SGS_DFS_MINB;
+
 template <int W, bool SPLIT, bool PRUNE>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(32 * kDfsWpb, kDfsMinBlocks)
 k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned int *item_counter,
       int shard, int nshards, int cap, int smem_per_warp, const unsigned int *nitems_dev, const unsigned int *__restrict__ perm,
       uint16_t *retry_out_, unsigned int *retry_count, unsigned retry_cap, const unsigned int *valid_end)
@@ -1035,20 +1181,22 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     unsigned char *p = smem_raw + (size_t)warp * smem_per_warp;
     uint64_t *R = (uint64_t *)p;        p += (size_t)cap * W * 8;
     double *WA = (double *)p;           p += (size_t)cap * 8;
-    uint64_t *B = (uint64_t *)p;        p += (size_t)32 * W * 8;
-    uint64_t *AD = (uint64_t *)p;       p += (size_t)64 * 8;
-    uint32_t *AD32 = (uint32_t *)p;     p += (size_t)32 * 4;
-    double *fE = (double *)p;           p += (size_t)kMaxFrames * 8;
-    int *fbase = (int *)p;              p += (size_t)kMaxFrames * 4;
-    int *fa = (int *)p;                 p += (size_t)kMaxFrames * 4;
-    int *fq = (int *)p;                 p += (size_t)kMaxFrames * 4;
+    uint64_t *B = (uint64_t *)p;        // root basis; dead once the root's residues are written, then:
+    uint64_t *AD = (uint64_t *)p;       // level-B commutation bit-matrix, 64-bit form
+    uint32_t *AD32 = (uint32_t *)(p + 64 * 8);   // ... and 32-bit form
+    p += dfs_scratch_bytes<W>();
+    double *fE = (double *)p;           p += (size_t)kMaxFramesA * 8;
+    int *fbase = (int *)p;              p += (size_t)kMaxFramesA * 4;
+    int *fa = (int *)p;                 p += (size_t)kMaxFramesA * 4;
+    int *fq = (int *)p;                 p += (size_t)kMaxFramesA * 4;
     uint32_t *hist = (uint32_t *)p;     p += (size_t)(kMaxG + 1) * 4 + 4;
     uint16_t *TT = (uint16_t *)p;       p += (size_t)cap * 2;
     uint16_t *path = (uint16_t *)p;     p += (size_t)kMaxG * 2;
     uint16_t *bestG = (uint16_t *)p;    p += (size_t)kMaxG * 2;
     uint8_t *pivB = (uint8_t *)p;       p += 64;
     p = smem_raw + (((size_t)(p - smem_raw) + 7) & ~(size_t)7);
-    double *SW = (double *)p;           p += 64 * 8;   // [64] suffix sums of the candidate weights (branch-and-bound mode)
+    double *SW = (double *)p;           // [64] suffix sums of the candidate weights (branch-and-bound build only)
+    if (PRUNE) p += 64 * 8;
     uint32_t *pc = (uint32_t *)p;       // [8] code-path counters (kPath*)
     if (lane < 8) pc[lane] = 0;
 
@@ -1124,6 +1272,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             troot = tn; tfail = false; tinfo = 0;
         }
         if (it >= nitems) break;
+        if (*(volatile unsigned int *)&D.stats->error) break;      // a limit was hit somewhere: the search is void, stop early
         if (PRUNE) thr = fmin(prune_threshold(bestE), prune_threshold(dec_double(*(volatile unsigned long long *)D.inc)));
         const uint16_t *rec = items + (size_t)(perm ? perm[it] : it) * D.S;
         const int m0 = rec[0];
@@ -1254,6 +1403,8 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                 continue;
             }
             const int jq = q++;
+            // (the warp-cooperative descent is where an over-deep instance spends its time: poll the error flag)
+            if ((jq & 7) == 0 && *(volatile unsigned int *)&D.stats->error) break;
             uint64_t rj[W], sw[W];
 #pragma unroll
             for (int k = 0; k < W; k++) { rj[k] = R[(base + jq) * W + k]; sw[k] = swapzx(rj[k]); }
@@ -1294,7 +1445,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             }
             if (lane == 0) path[depth] = TT[base + jq];
             const int cb = base + a;
-            if (cb + nal > cap || depth + 1 >= kMaxG) {     // out of list space: the exact kernel takes over
+            if (cb + nal > cap || depth + 1 >= kMaxG || fd + 1 >= kMaxFramesA) {     // out of list / frame space: the exact kernel takes over
                 __syncwarp();
                 try_best(Ec, depth + 1);
                 push_slow(D, path, depth + 1, kFlagExpandOnly, lane);

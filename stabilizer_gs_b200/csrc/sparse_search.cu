@@ -142,6 +142,43 @@ Status SparsePlan::Impl::init()
     if (n > 2 * 64) return Status::fail(SGS_ERR_LIMIT, "sparse search supports n <= 128");
     if (T > 65535) return Status::fail(SGS_ERR_LIMIT, "sparse search supports at most 65535 terms");
     if (T > 8192) return Status::fail(SGS_ERR_LIMIT, "sparse search supports at most 8192 terms (shared-memory lists)");
+    {
+        // Input check for the rank limit (kMaxG generators per group).  A greedy pass collects terms that commute
+        // pairwise and are linearly independent; if it gathers more than kMaxG, groups of a higher rank exist, the
+        // tree has more than 2^kMaxG leaves and the search could neither finish nor represent its answer: refuse
+        // now.  (Instances that pass may still meet the limit during the search; the kernels then stop with the
+        // same error instead of writing a record that does not fit.)
+        std::vector<PackedRow> chosen, basis;
+        auto anticommute = [](const PackedRow &a, const PackedRow &b) {
+            uint64_t acc = 0;
+            for (int k = 0; k < kMaxWords; k++) {
+                const uint64_t sw = ((b.w[k] >> 1) & 0x5555555555555555ULL) | ((b.w[k] & 0x5555555555555555ULL) << 1);
+                acc ^= a.w[k] & sw;
+            }
+            return __builtin_popcountll(acc) & 1;
+        };
+        for (int p = 0; p < T && (int)chosen.size() <= kMaxG; p++) {
+            const PackedRow &t = H.terms[H.order[p]];
+            bool ok = true;
+            for (const PackedRow &c : chosen) if (anticommute(t, c)) { ok = false; break; }
+            if (!ok) continue;
+            PackedRow r = t;
+            for (const PackedRow &b : basis) {          // basis rows are reduced: each has a pivot no other row has
+                int pw = 0;
+                while (pw < kMaxWords && b.w[pw] == 0) pw++;
+                const uint64_t pb = b.w[pw] & (0 - b.w[pw]);
+                if (r.w[pw] & pb) for (int k = 0; k < kMaxWords; k++) r.w[k] ^= b.w[k];
+            }
+            bool zero = true;
+            for (int k = 0; k < kMaxWords; k++) zero = zero && r.w[k] == 0;
+            if (zero) continue;
+            chosen.push_back(t);
+            basis.push_back(r);
+        }
+        if ((int)chosen.size() > kMaxG)
+            return Status::fail(SGS_ERR_LIMIT, "sparse search: the Hamiltonian has more than 64 independent pairwise-commuting terms "
+                                               "(groups of rank > 64; the search space exceeds 2^64 groups)");
+    }
     W = (2 * n + 63) / 64;
     if (W == 3) W = 4;
     TW = (T + 63) / 64;
@@ -387,6 +424,7 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         if (hs.error) return Status::fail(hs.error == kErrOverflow ? SGS_ERR_OVERFLOW : SGS_ERR_LIMIT,
                                           "sparse search: device limit hit while expanding the tree (queue overflow or rank/table limit)");
         ratio = std::max(1.0, (double)hcnt[0] / (double)count);
+        if (D.trace) fprintf(stderr, "sparse shard %d: level %d -> %u nodes\n", c.shard, depth + 1, hcnt[0]);
         count = hcnt[0];
         level_counts.push_back(count);
         std::swap(cur, nxt);
@@ -397,11 +435,16 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
     if (count > 0) {
         // list arena per warp: a root holds about `ratio` alive terms (the measured mean number of
         // children of the last expanded level) and the levels below it halve; 6x leaves room for spread
-        int cap = 128;
-        while (cap < 6.0 * ratio && cap < 2048) cap <<= 1;
+        // list arena per warp: a root holds a ~ ratio * depth / 2 alive terms (ratio = measured mean number of
+        // children of the last expanded level; binomial spread), the lists of the levels below it halve:
+        // 2.2 x (mean + 4 sigma), in steps of 32 entries.  A root that needs more goes to the exact kernel.
+        const double a_est = std::max(8.0, ratio * std::max(depth, 1) / 2.0);
+        int cap = (int)(2.2 * (a_est + 4.0 * std::sqrt(a_est)));
+        if (const char *v = getenv("SGS_DFS_CAP")) if (atoi(v) > 0) cap = atoi(v);
+        cap = std::min(2048, std::max(96, (cap + 31) & ~31));
         dfs_cap = cap;
-        const size_t dfs_pw = dfs_smem_bytes<W_>(dfs_cap);
-        int dfs_wpb = 8;
+        const size_t dfs_pw = dfs_smem_bytes<W_>(dfs_cap, opts.prune != 0);
+        int dfs_wpb = kDfsWpb;
         while (dfs_wpb > 1 && dfs_pw * dfs_wpb > 200 * 1024) dfs_wpb >>= 1;
         int dfs_occ = 1 << 30;
         {
@@ -448,6 +491,7 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         if (hs.error) return Status::fail(hs.error == kErrOverflow ? SGS_ERR_OVERFLOW : SGS_ERR_LIMIT,
                                           "sparse search: device limit hit (work-stack overflow, or a group whose sign table exceeds the limit)");
         const unsigned sc = hcnt[2];
+        if (D.trace) fprintf(stderr, "sparse shard %d: work stack %u nodes\n", c.shard, sc);
         if (sc == 0) break;
         c.had_slow = true;
         const unsigned take = std::min(sc, chunk);
