@@ -76,6 +76,7 @@ struct SparseDev {
     unsigned int slow_cap;
     int trace;                   // SGS_TRACE: per-root timing diagnostics into stats->dbg
     unsigned long long *inc;     // branch-and-bound mode: best energy found so far on this device (order-encoded double)
+    float split_cliques;         // multi-shard runs: expected cliques from which a root hands its children to the next k_dfs round
 };
 
 enum { kErrOverflow = 8, kErrLimit = 6 };
@@ -168,31 +169,42 @@ __device__ __noinline__ void push_slow(const SparseDev &D, const uint16_t *g, in
 
 // alive terms of the group generated by g[0..m): bitset AND of adjacency rows, compacted into tt[]
 // (ascending term index).  Returns the count, or -1 if it exceeds cap.
+// The AND is taken per 64-bit word (one lane per word), the expansion of the result into indices per SLICE of
+// 16 bits (up to 8 words = 512 terms per round) or 32 bits (16 words = 1024 terms per round), one slice per lane:
+// a list holds about T / 2^m entries, so a word has a dozen set bits but a slice one or two — the serial
+// "lowest bit, clear it, store" loop is as long as the fullest slice, not the fullest word.
 SGS_D int alive_list(const SparseDev &D, const uint16_t *g, int m, uint16_t *tt, int cap, int lane)
 {
     int total = 0;
-    for (int w0 = 0; w0 < D.TW; w0 += 32) {
-        int w = w0 + lane;
+    const bool narrow = D.TW <= 8;                       // 16-bit slices: 4 per word
+    const int wpr = narrow ? 8 : 16;                     // words per round
+    for (int w0 = 0; w0 < D.TW; w0 += wpr) {
+        const int w = w0 + lane;
         uint64_t a = 0;
-        if (w < D.TW) {
+        if (lane < wpr && w < D.TW) {
             a = ~0ULL;
-            int rem = D.T - w * 64;
+            const int rem = D.T - w * 64;
             if (rem < 64) a = (1ULL << rem) - 1;
             for (int i = 0; i < m; i++) a &= D.adj[(size_t)g[i] * D.TW + w];
         }
-        int c = popc64(a), inc = c;
+        // my slice: lane j reads word j / 4 (narrow) or j / 2 of this round
+        const uint64_t aw = __shfl_sync(0xffffffffu, a, narrow ? (lane >> 2) : (lane >> 1));
+        uint32_t sl = narrow ? (uint32_t)(aw >> (16 * (lane & 3))) & 0xffffu : (uint32_t)(aw >> (32 * (lane & 1)));
+        const int bit0 = w0 * 64 + (narrow ? 16 : 32) * lane;
+        const int c = __popc(sl);
+        int inc = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, inc, d);
+            const int v = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += v;
         }
         int off = total + inc - c;
-        int tot = __shfl_sync(0xffffffffu, inc, 31);
+        const int tot = __shfl_sync(0xffffffffu, inc, 31);
         if (total + tot > cap) return -1;
-        while (a) {
-            int b = ctz64(a);
-            a &= a - 1;
-            tt[off++] = (uint16_t)(w * 64 + b);
+        while (sl) {
+            const int b = __ffs((int)sl) - 1;
+            sl &= sl - 1;
+            tt[off++] = (uint16_t)(bit0 + b);
         }
         total += tot;
     }
@@ -570,6 +582,7 @@ __global__ void k_class_scatter(const uint16_t *__restrict__ items, unsigned n, 
 // frames (a deeper chain of uncertifiable lists goes to the exact kernel), the suffix sums exist only in the
 // branch-and-bound build.
 constexpr int kMaxFramesA = 24;
+constexpr int kMaxEdgesSmem = 256;      // = kMaxEdges (defined with the walk)
 template <int W>
 __host__ __device__ inline size_t dfs_scratch_bytes() { return (size_t)(32 * W * 8 > 64 * 8 + 32 * 4 ? 32 * W * 8 : 64 * 8 + 32 * 4); }
 template <int W>
@@ -579,6 +592,7 @@ __host__ __device__ inline size_t dfs_smem_bytes(int cap, bool prune)
     b += (size_t)cap * W * 8;          // residues
     b += (size_t)cap * 8;              // |w| of each list entry
     b += dfs_scratch_bytes<W>();       // root basis, later the level-B commutation bit-matrix (64-bit or 32-bit form)
+    b += (size_t)kMaxEdgesSmem * 2;    // edge list of the level-B walk (one chunk)
     b += (size_t)kMaxFramesA * 8;      // frame E
     b += (size_t)kMaxFramesA * 4 * 3;  // frame base, a, q
     b += (size_t)(kMaxG + 1) * 4 + 4;  // hist
@@ -646,104 +660,41 @@ SGS_D int popc_mask(uint64_t v) { return __popcll(v); }
 template <typename M>
 SGS_D bool clique_before(M A, M B) { const M x = A ^ B; return (A & (x & ((M)0 - x))) != 0; }
 
-// Walk over the cliques of the candidates (vertices 0..ncand-1 = list positions nlow..n-1, ADm[v] = neighbours of v
-// with a higher index).  Work is dealt by the SECOND vertex: a work item (l, dn) is "every clique {f, l, ...} with f
-// in dn, a set of lower neighbours of l" — far better balanced than dealing by the lowest vertex — plus, for the
-// item's owner, the singleton {l}.  A lane has up to two items.  Counts candidates per rank in hc[], keeps the
-// heaviest clique; ties go to the clique that comes first in the leaf order (clique_before), so neither the deal
-// nor the order of the walk matters.
-//
-// The loop is WARP-CONVERGED: all 32 lanes run the same iteration (at most one pop, then one vertex) until the
-// last lane has finished; the branches inside are short and rejoin before the vote.  (Left to themselves the lanes
-// drift apart through the pop / leaf / push branches and the walk issues with 3-6 active lanes per instruction:
-// ncu, profiles/r02_k_dfs_config4_ncu_source_top_before.csv.)  The two innermost frames live in registers
-// (c0/w0/m0: frame d, c1/w1/m1: frame d - 1), the local-memory stack holds frames 0..d-2: a push stores the old
-// parent, a pop reloads the new parent one pop ahead of its use.  A frame whose last vertex is being expanded is
-// not kept (rest == 0: nothing to come back to), so a pop always lands on a frame with work — except frame 0.
-// PRUNE (branch and bound): SW[v] = sum of the weights of the vertices >= v; a branch whose best conceivable
-// weight (current + every vertex from its lowest remaining candidate on) stays below `need` is not entered.
-template <typename M, bool PRUNE>
-SGS_D void lb_walk(const M *ADm, const double *WAc, int depth, uint32_t *hc, double &bw, M &bm, int la, M dna, bool owna, int lb, M dnb,
-                   const double *SW, double need)
-{
-    M cand[kMaxLB], cm[kMaxLB];
-    double ws[kMaxLB];
-    int item = 0, d = 0;
-    M c0 = 0, m0 = 0, c1 = 0, m1 = 0, upl = 0;
-    double w0 = 0.0, w1 = 0.0;
-    bool alive = true;
-#pragma unroll 1
-    while (__any_sync(0xffffffffu, alive)) {
-        if (c0 == 0) {
-            if (d > 0) {
-                d--;
-                c0 = c1; w0 = w1; m0 = m1;
-                if (d >= 1) { c1 = cand[d - 1]; w1 = ws[d - 1]; m1 = cm[d - 1]; }
-            } else if (alive) {
-                // next work item of this lane (at most two per call: rare, may diverge)
-                const int l = item == 0 ? la : lb;
-                if (item >= 2 || l < 0) alive = false;
-                else {
-                    const M dn = item == 0 ? dna : dnb;
-                    const bool own = item == 0 ? owna : true;
-                    item++;
-                    upl = ADm[l];
-                    w0 = WAc[l];
-                    m0 = (M)1 << l;
-                    c0 = dn;
-                    hc[depth + 2] += popc_mask(dn);
-                    if (own) {
-                        hc[depth + 1] += 1;
-                        if (w0 > bw || (w0 == bw && clique_before(m0, bm))) { bw = w0; bm = m0; }
-                    }
-                }
-            }
-        }
-        if (c0 != 0) {
-            const int v = ctz_mask(c0);
-            const M rest = c0 & (c0 - 1);
-            const M nc = (d == 0 ? upl : rest) & ADm[v];
-            const double nw = w0 + WAc[v];
-            if (nc == 0) {
-                if (nw >= bw) {
-                    const M cur = m0 | ((M)1 << v);
-                    if (nw > bw || clique_before(cur, bm)) { bw = nw; bm = cur; }
-                }
-                c0 = rest;
-            } else if (PRUNE && nw + SW[ctz_mask(nc)] < need) {
-                c0 = rest;       // nothing below can reach the incumbent; the clique itself cannot either (it is lighter still)
-            } else {
-                hc[depth + 2 + popc_mask(m0)] += popc_mask(nc);
-                if (rest != 0 || d == 0) {
-                    if (d >= 1) { cand[d - 1] = c1; ws[d - 1] = w1; cm[d - 1] = m1; }
-                    c1 = rest; w1 = w0; m1 = m0;
-                    d++;
-                }
-                c0 = nc; w0 = nw; m0 |= (M)1 << v;
-            }
-        }
-    }
-}
-
-// The walk for frames with at most 32 candidates and at most kMaxEdges edges (almost all of them): work items are
-// the EDGES (f, l) of the candidates' commutation graph — "every clique whose two lowest vertices are f < l" — listed
-// in shared memory (EL[e] = l | f << 8, l ascending: heavy items first) and dealt DYNAMICALLY: whenever lanes are
+// The clique walk of a certified frame (vertices 0..ncand-1 = list positions nlow..n-1, ADm[v] = neighbours of v
+// with a higher index).  Work items are the EDGES (f, l) of the candidates' commutation graph — "every clique whose
+// two lowest vertices are f < l" — listed in shared memory (EL[e] = l | f << 8, l ascending: heavy items first;
+// kMaxEdges per chunk, a frame with more edges is walked chunk by chunk) and dealt DYNAMICALLY: whenever lanes are
 // idle at the top of an iteration they take the next items off the list, numbered by a ballot (the list cursor is a
 // warp-uniform register: no atomics).  An edge's subtree holds 3-4 cliques on average, so the lanes stay level where
 // a deal by vertex leaves three quarters of them idle (measured: 7 of 32 lanes busy per iteration).
-// Same warp-converged iteration as lb_walk: at most one pop, then one vertex.  The member mask needs no stack: the
-// members above l are added in increasing order and all lie below the lowest remaining candidate of the frame a pop
-// returns to, except the vertex that frame had just expanded — the highest of them.  Candidates per rank are counted
-// in byte fields of a register (clique sizes 3-6; larger ones go straight to hc[]) and flushed every 255 iterations.
-constexpr int kMaxEdges = 256;
-template <bool PRUNE>
-SGS_D void lb_walk_edges(const uint32_t *ADm, const double *WAc, const uint16_t *EL, int nedges, int depth, uint32_t *hc, double &bw,
-                         uint32_t &bm, uint32_t ltmask, const double *SW, double need)
+//
+// The loop is WARP-CONVERGED: all 32 lanes run the same iteration (take an item if idle, at most one pop, then one
+// vertex) until the list is empty and the last lane has finished; the branches inside are short and rejoin.  (Left
+// to themselves the lanes drift apart through the pop / leaf / push branches and the walk issues with 3-6 active
+// lanes per instruction: ncu, profiles/r02_before_k_dfs_config4_source_top.csv.)  The two innermost frames live in
+// registers (c0/w0: frame d, c1/w1: frame d - 1), the local-memory stack holds frames 0..d-2.  A frame whose last
+// vertex is being expanded is not kept (rest == 0: nothing to come back to), so a pop always lands on a frame with
+// work.  The member mask needs no stack: the members above l are added in increasing order and all lie below the
+// lowest remaining candidate of the frame a pop returns to, except the vertex that frame had just expanded — the
+// highest of them.  Candidates per rank are counted in byte fields of a register (clique sizes 3-6; larger ones go
+// straight to hc[]) and flushed every 255 iterations.  Keeps the heaviest clique; ties go to the clique that comes
+// first in the leaf order (clique_before), so neither the deal nor the order of the walk matters.
+// PRUNE (branch and bound): SW[v] = sum of the weights of the vertices >= v; a branch whose best conceivable
+// weight (current + every vertex from its lowest remaining candidate on) stays below `need` is not entered.
+constexpr int kMaxEdges = kMaxEdgesSmem;
+SGS_D int clz_mask(uint32_t v) { return __clz((int)v); }
+SGS_D int clz_mask(uint64_t v) { return __clzll((long long)v); }
+
+template <typename M, bool PRUNE>
+SGS_D void lb_walk_edges(const M *ADm, const double *WAc, const uint16_t *EL, int nedges, int depth, uint32_t *hc, double &bw, M &bm,
+                         uint32_t ltmask, const double *SW, double need)
 {
-    uint32_t cand[32];
-    double ws[32];
+    constexpr int kBits = (int)sizeof(M) * 8;
+    M cand[kBits];
+    double ws[kBits];
     int d = 0, next = 0, iter = 0;
-    uint32_t c0 = 0, m0 = 0, c1 = 0, cnt = 0;
+    M c0 = 0, m0 = 0, c1 = 0;
+    uint32_t cnt = 0;
     double w0 = 0.0, w1 = 0.0;
     auto flush = [&]() {
 #pragma unroll
@@ -764,7 +715,7 @@ SGS_D void lb_walk_edges(const uint32_t *ADm, const double *WAc, const uint16_t 
                     const int l = it & 255, f = it >> 8;
                     c0 = ADm[l] & ADm[f];
                     w0 = WAc[l] + WAc[f];
-                    m0 = (1u << l) | (1u << f);
+                    m0 = ((M)1 << l) | ((M)1 << f);
                     if (c0 == 0 && w0 >= bw && (w0 > bw || clique_before(m0, bm))) { bw = w0; bm = m0; }
                 }
             }
@@ -773,25 +724,25 @@ SGS_D void lb_walk_edges(const uint32_t *ADm, const double *WAc, const uint16_t 
             // pop: the frame below has candidates left (a frame is only kept with rest != 0)
             d--;
             c0 = c1; w0 = w1;
-            m0 &= (c0 & (0u - c0)) - 1u;                      // members below the frame's lowest remaining candidate ...
-            m0 &= ~(0x80000000u >> __clz((int)m0));            // ... minus the highest: the vertex expanded last
+            m0 &= (c0 & ((M)0 - c0)) - (M)1;                               // members below the frame's lowest remaining candidate ...
+            m0 &= ~((M)1 << (kBits - 1 - clz_mask(m0)));                   // ... minus the highest: the vertex expanded last
             if (d >= 1) { c1 = cand[d - 1]; w1 = ws[d - 1]; }
         }
         if (c0 != 0) {
-            const int v = __ffs((int)c0) - 1;
-            const uint32_t rest = c0 & (c0 - 1);
-            const uint32_t nc = rest & ADm[v];
+            const int v = ctz_mask(c0);
+            const M rest = c0 & (c0 - 1);
+            const M nc = rest & ADm[v];
             const double nw = w0 + WAc[v];
-            const int sz = __popc(m0);                         // the new clique has sz + 1 vertices
+            const int sz = popc_mask(m0);                      // the new clique has sz + 1 vertices
             if (sz <= 5) cnt += 1u << (8 * (sz - 2));
             else hc[depth + sz + 1] += 1;
             if (nc == 0) {
                 if (nw >= bw) {
-                    const uint32_t cur = m0 | (1u << v);
+                    const M cur = m0 | ((M)1 << v);
                     if (nw > bw || clique_before(cur, bm)) { bw = nw; bm = cur; }
                 }
                 c0 = rest;
-            } else if (PRUNE && nw + SW[__ffs((int)nc) - 1] < need) {
+            } else if (PRUNE && nw + SW[ctz_mask(nc)] < need) {
                 c0 = rest;       // nothing below can reach the incumbent; the clique itself cannot either (it is lighter still)
             } else {
                 if (rest != 0) {
@@ -799,12 +750,48 @@ SGS_D void lb_walk_edges(const uint32_t *ADm, const double *WAc, const uint16_t 
                     c1 = rest; w1 = w0;
                     d++;
                 }
-                c0 = nc; w0 = nw; m0 |= 1u << v;
+                c0 = nc; w0 = nw; m0 |= (M)1 << v;
             }
         }
         if (++iter == 255) { flush(); iter = 0; }
     }
     flush();
+}
+
+// One certified frame: list the edges of the candidates' graph (vertex l = lane and lane + 32 lists its lower
+// neighbours dn0 / dn1) in chunks of at most kMaxEdges and walk every chunk.  Singletons and pairs are counted
+// here; a singleton is offered as the best clique (it is, if its vertex is isolated).
+template <typename M, bool PRUNE>
+SGS_D void lb_walk_frame(const M *ADm, const double *WAc, uint16_t *EL, int ncand, M dn0, M dn1, int depth, uint32_t *hc, double &bw, M &bm,
+                         int lane, const double *SW, double need)
+{
+    const int cnt0 = popc_mask(dn0), cnt1 = popc_mask(dn1);
+    int inc0 = cnt0, inc1 = cnt1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y0 = __shfl_up_sync(0xffffffffu, inc0, o), y1 = __shfl_up_sync(0xffffffffu, inc1, o);
+        if (lane >= o) { inc0 += y0; inc1 += y1; }
+    }
+    const int tot0 = __shfl_sync(0xffffffffu, inc0, 31), total = tot0 + __shfl_sync(0xffffffffu, inc1, 31);
+    const int ex0 = inc0 - cnt0, ex1 = tot0 + inc1 - cnt1;       // offset of my vertices' first edge in the full list
+    if (lane == 0) { hc[depth + 1] += (uint32_t)ncand; hc[depth + 2] += (uint32_t)total; }
+    if (lane < ncand) { bw = WAc[lane]; bm = (M)1 << lane; }
+    if (lane + 32 < ncand && WAc[lane + 32] > bw) { bw = WAc[lane + 32]; bm = (M)1 << (lane + 32); }
+    const uint32_t ltmask = (1u << lane) - 1u;
+    int start = 0;
+#pragma unroll 1
+    while (start < total) {
+        // the chunk: every vertex whose edges fit completely (offsets are monotone: a prefix of the remaining vertices)
+        const bool in0 = cnt0 > 0 && ex0 >= start && ex0 + cnt0 - start <= kMaxEdges;
+        const bool in1 = cnt1 > 0 && ex1 >= start && ex1 + cnt1 - start <= kMaxEdges;
+        const int end = __reduce_max_sync(0xffffffffu, max(in0 ? ex0 + cnt0 : start, in1 ? ex1 + cnt1 : start));
+        if (in0) { int o = ex0 - start; for (M x = dn0; x; x &= x - 1) EL[o++] = (uint16_t)(lane | (ctz_mask(x) << 8)); }
+        if (in1) { int o = ex1 - start; for (M x = dn1; x; x &= x - 1) EL[o++] = (uint16_t)((lane + 32) | (ctz_mask(x) << 8)); }
+        __syncwarp();
+        lb_walk_edges<M, PRUNE>(ADm, WAc, EL, end - start, depth, hc, bw, bm, ltmask, SW, need);
+        __syncwarp();
+        start = end;
+    }
 }
 
 // The certificate of level B on one-word rows (row i in p0 of lane i, row i + 32 in p1 of lane i): are the CANDIDATE
@@ -862,7 +849,7 @@ SGS_D float expected_cliques(int n, int e)
 // (not inlined: it is called from two places of k_dfs and a single copy keeps the hot loops inside the
 //  instruction cache)
 template <int W, bool PRUNE>
-__device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, int n, int nlow, int depth,
+__device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, uint16_t *EL, int n, int nlow, int depth,
                   uint32_t *hc, double &bw, uint64_t &bm, int lane, float split_cliques, double *SW, double need, uint32_t *pc)
 {
     // 1. the certificate: the residues of the CANDIDATES (positions nlow..n-1) are linearly independent and no
@@ -1042,47 +1029,16 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
             a32 |= (uint32_t)(row_anticommute_sw<W>(ru, sc) ^ 1) << u;
         }
         const uint32_t up32 = lane < ncand ? (a32 & ~((2u << lane) - 1u)) : 0u;
-        if (split_cliques > 0.f && ncand >= 24) {      // too big a walk for one warp of a short kernel: let the caller split it
+        if (split_cliques > 0.f && ncand >= 12) {      // too big a walk for one warp of a short kernel: let the caller split it
             int e = __popc(up32);
             for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
             if (expected_cliques(ncand, e) > split_cliques) return 2;
         }
         if (lane < ncand) AD32[lane] = up32;
         if (lane == 0) pc[kPathWalk32]++;
-        // edge list (aliases the 64-bit matrix, unused here): lane l lists its lower neighbours
-        const uint32_t dnl = lane < ncand ? (a32 & ((1u << lane) - 1u)) : 0u;
-        int eoff = __popc(dnl);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, eoff, o);
-            if (lane >= o) eoff += y;
-        }
-        const int nedges = __shfl_sync(0xffffffffu, eoff, 31);
-        if (nedges <= kMaxEdges) {
-            uint16_t *EL = (uint16_t *)AD;
-            eoff -= __popc(dnl);
-            for (uint32_t x = dnl; x; x &= x - 1) EL[eoff++] = (uint16_t)(lane | ((__ffs((int)x) - 1) << 8));
-            __syncwarp();
-            // singletons and pairs are counted here; a singleton is the best clique only if its vertex is isolated
-            if (lane == 0) { hc[depth + 1] += (uint32_t)ncand; hc[depth + 2] += (uint32_t)nedges; }
-            uint32_t bm32 = 0;
-            if (lane < ncand) { bw = WA[nlow + lane]; bm32 = 1u << lane; }
-            lb_walk_edges<PRUNE>(AD32, WA + nlow, EL, nedges, depth, hc, bw, bm32, (1u << lane) - 1u, SW, need);
-            bm = (uint64_t)bm32 << nlow;
-            __syncwarp();
-            return 1;
-        }
         __syncwarp();
-        // (more than kMaxEdges edges) deal by vertex: l = lane mod p (p = the power of two >= ncand); with k = 32 / p > 1 the lower neighbours of
-        // l are striped over k lanes (f mod k == s), so that short lists still use the whole warp
-        int lg = 0;
-        while ((1 << lg) < ncand) lg++;
-        const int k = 32 >> lg, l = lane & ((1 << lg) - 1), st = lane >> lg;
-        const uint32_t al = __shfl_sync(0xffffffffu, a32, l);
-        const uint32_t stripe = (k == 1 ? 0xffffffffu : k == 2 ? 0x55555555u : k == 4 ? 0x11111111u : k == 8 ? 0x01010101u : k == 16 ? 0x00010001u : 1u) << st;
-        const bool has = l < ncand;
         uint32_t bm32 = 0;
-        lb_walk<uint32_t, PRUNE>(AD32, WA + nlow, depth, hc, bw, bm32, has ? l : -1, has ? (al & ((1u << l) - 1u) & stripe) : 0u, st == 0, -1, 0u, SW, need);
+        lb_walk_frame<uint32_t, PRUNE>(AD32, WA + nlow, EL, ncand, lane < ncand ? (a32 & ((1u << lane) - 1u)) : 0u, 0u, depth, hc, bw, bm32, lane, SW, need);
         bm = (uint64_t)bm32 << nlow;
     } else {
         uint64_t sc0[W], sc1[W];
@@ -1112,8 +1068,8 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         if (lane == 0) pc[kPathWalk64]++;
         __syncwarp();
         uint64_t bmr = 0;
-        lb_walk<uint64_t, PRUNE>(AD, WA + nlow, depth, hc, bw, bmr, lane, a0 & ((1ULL << lane) - 1ULL), true, lane + 32 < ncand ? lane + 32 : -1,
-                                 a1 & ((1ULL << (lane + 32)) - 1ULL), SW, need);
+        lb_walk_frame<uint64_t, PRUNE>(AD, WA + nlow, EL, ncand, a0 & ((1ULL << lane) - 1ULL), lane + 32 < ncand ? (a1 & ((1ULL << (lane + 32)) - 1ULL)) : 0ULL,
+                                       depth, hc, bw, bmr, lane, SW, need);
         bm = bmr << nlow;
     }
     __syncwarp();
@@ -1160,10 +1116,15 @@ __device__ __noinline__ int level_b_pick(double bw, uint64_t bm, const uint16_t 
 #ifndef SGS_DFS_MINB
 #define SGS_DFS_MINB 6
 #endif
-constexpr int kDfsWpb = SGS_DFS_WPB, kDfsMinBlocks = SGS_DFS_MINB;
+#ifndef SGS_DFS_MINB1
+#define SGS_DFS_MINB1 8
+#endif
+constexpr int kDfsWpb = SGS_DFS_WPB;
+// one-word rows: 64 registers (8 blocks of 4 warps per SM) measured 2 % faster than 80; multi-word rows spill there (-13 %)
+template <int W> constexpr int dfs_min_blocks() { return W == 1 ? SGS_DFS_MINB1 : SGS_DFS_MINB; }
 
 template <int W, bool SPLIT, bool PRUNE>
-__global__ void __launch_bounds__(32 * kDfsWpb, kDfsMinBlocks)
+__global__ void __launch_bounds__(32 * kDfsWpb, dfs_min_blocks<W>())
 k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned int *item_counter,
       int shard, int nshards, int cap, int smem_per_warp, const unsigned int *nitems_dev, const unsigned int *__restrict__ perm,
       uint16_t *retry_out_, unsigned int *retry_count, unsigned retry_cap, const unsigned int *valid_end)
@@ -1185,6 +1146,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     uint64_t *AD = (uint64_t *)p;       // level-B commutation bit-matrix, 64-bit form
     uint32_t *AD32 = (uint32_t *)(p + 64 * 8);   // ... and 32-bit form
     p += dfs_scratch_bytes<W>();
+    uint16_t *EL = (uint16_t *)p;       p += (size_t)kMaxEdgesSmem * 2;
     double *fE = (double *)p;           p += (size_t)kMaxFramesA * 8;
     int *fbase = (int *)p;              p += (size_t)kMaxFramesA * 4;
     int *fa = (int *)p;                 p += (size_t)kMaxFramesA * 4;
@@ -1231,7 +1193,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         double bw = -1.0;
         uint64_t bm = 0;
         // a clique of weight w gives the energy Ef - w: it reaches the incumbent iff w >= Ef - thr
-        const int rc = level_b<W, PRUNE>(R + lb * W, WA + lb, AD, AD32, n, nlow, depth, hc, bw, bm, lane, split, SW, Ef - thr, pc);
+        const int rc = level_b<W, PRUNE>(R + lb * W, WA + lb, AD, AD32, EL, n, nlow, depth, hc, bw, bm, lane, split, SW, Ef - thr, pc);
         if (rc != 1) return rc;
         // does any lane's best clique reach the incumbent?
         const bool cand = bm != 0 && (Ef - bw) <= bestE;
@@ -1364,7 +1326,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         if (q0 >= a) { try_best(E0, m0); continue; }                      // no extension: a leaf
         // (a certified root whose clique walk alone would outlast the rest of a short kernel is split the same way
         //  when a next round exists: level_b answers 2)
-        if (a <= 64 && m0 + (a - q0) < kMaxG && run_level_b(0, a, q0, m0, E0, retry_out ? kSplitCliques : 0.f) == 1) continue;
+        if (a <= 64 && m0 + (a - q0) < kMaxG && run_level_b(0, a, q0, m0, E0, retry_out ? D.split_cliques : 0.f) == 1) continue;
         tfail = true;
         if (has_duplicate<W>(R, a, lane)) {
             try_best(E0, m0);

@@ -133,6 +133,8 @@ SparseDev SparsePlan::Impl::dev_view(const DevCtx &c) const
     D.slow = c.slow; D.slow_count = c.counters + 2; D.slow_cap = slow_cap;
     D.trace = getenv("SGS_TRACE") ? 1 : 0;
     D.inc = opts.prune ? c.inc : nullptr;
+    D.split_cliques = kSplitCliques;
+    if (const char *v = getenv("SGS_SPLIT_CLIQUES")) if (atof(v) > 0) D.split_cliques = (float)atof(v);
     return D;
 }
 
