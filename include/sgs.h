@@ -149,6 +149,41 @@ int sgs_klocal_sright_count(const sgs_klocal *k, int m);
 int sgs_klocal_evolve(sgs_klocal *k);                  /* StateMachine::evolve, one site          */
 int sgs_klocal_ground_state(sgs_klocal *k, sgs_result *out);   /* generate_gs + get_stab_gs      */
 
+/* ---- stepwise access to the DP states: the Python classes the BODY of py/klocal_periodic.py:9-63 uses
+ * (State.shift/copy/__hash__, StateMachinePeriodic.state_dict/.m, EnergyLevel.Es/get_state; py/state.py:150-325,
+ * 402-462, py/stab.py:176-305).  With periodic_cmax >= 0, sgs_klocal_create runs generate_Sright_periodic
+ * (py/state.py:542-567) and sets the StateMachinePeriodic's initial states. */
+typedef struct sgs_klocal_states sgs_klocal_states;       /* host snapshot of a list of states of one site       */
+#define SGS_KLOCAL_KEY_WORDS 32
+/* (m, count) pairs in the order generate_Sright_all / generate_Sright_periodic print them; returns their number */
+int sgs_klocal_sright_log(const sgs_klocal *k, int *pairs, int cap);
+/* list(state_dict.values()) of the current site, in key order */
+int sgs_klocal_get_states(sgs_klocal *k, sgs_klocal_states **out);
+int sgs_klocal_states_count(const sgs_klocal_states *s);
+void sgs_klocal_states_free(sgs_klocal_states *s);
+/* a new list holding copies of entries idx[0..count) (State.copy, list building) */
+int sgs_klocal_states_select(const sgs_klocal_states *s, const int *idx, int count, sgs_klocal_states **out);
+/* dst.append(copy of src[i]); every state of a list sits at the same site */
+int sgs_klocal_states_append(sgs_klocal_states *dst, const sgs_klocal_states *src, int i);
+/* State.m, rank and window [begin, end) of State.stab, index of State.Sright in its level (any pointer may be NULL) */
+int sgs_klocal_state_info(const sgs_klocal *k, const sgs_klocal_states *s, int i, int *m, int *rank, int *begin, int *end, int *sright);
+/* generators of State.stab: rank x W rows at absolute sites, all '+' (cpp/stab.cpp:626) */
+int sgs_klocal_state_rows(const sgs_klocal *k, const sgs_klocal_states *s, int i, uint64_t *rows);
+/* content of State.__hash__ (py/state.py:224-225): m, window group, (in)valid term indices of the next k-2 sites,
+ * right environment; key has room for SGS_KLOCAL_KEY_WORDS words */
+int sgs_klocal_state_key(const sgs_klocal *k, const sgs_klocal_states *s, int i, uint64_t *key, int *nwords);
+/* State.stab.energy_level.Es: 2^rank doubles, flat index bit (rank-1-i) set <=> generator i is '-' (cpp/stab.cpp:37-45) */
+int sgs_klocal_state_energies(const sgs_klocal_states *s, int i, double *Es);
+int sgs_klocal_state_set_energies(sgs_klocal_states *s, int i, const double *Es);
+/* State.shift(add, clear_history) applied to every state of the list (py/state.py:309-325) */
+int sgs_klocal_states_shift(sgs_klocal *k, sgs_klocal_states *s, int add, int clear_history);
+/* state_machine.state_dict = {hash(s): s for s in list}; state_machine.m = m (py/klocal_periodic.py:12-14) */
+int sgs_klocal_set_states(sgs_klocal *k, const sgs_klocal_states *s, int m);
+/* EnergyLevel.get_state(entry, original_paulis, return_stab=False) (py/stab.py:288-305): file indices and signs of the
+ * Hamiltonian terms generating the best full state behind table entry `entry`, in history order.  Walks the device
+ * history, which is valid until the machine's next evolve / set_states (SGS_ERR_ARG afterwards). */
+int sgs_klocal_state_history(sgs_klocal *k, const sgs_klocal_states *s, int i, int entry, int *terms, int8_t *signs, int cap, int *count);
+
 /* py/klocal_periodic.py:1-63 as one call: orbits of the infinite periodic chain */
 typedef struct {
     double energy;          /* energy over c periods                                          */

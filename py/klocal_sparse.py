@@ -8,10 +8,12 @@ from stabilizer_gs_b200.state import Hamiltonian, StateMachine, generate_Sright_
 
 H = Hamiltonian.from_file(sys.argv[1] if len(sys.argv) > 1 else "../hamiltonian_finite.txt")
 Sright_all = generate_Sright_all(H)
+lists = []
 SM2 = StateMachine(H, Sright_all)
 while True:
     SM2.evolve()
     print(SM2.m, len(SM2.state_dict))
+    lists.append(list(SM2.state_dict.values()))
     if SM2.m == H.n:
         break
 SM2.generate_gs()

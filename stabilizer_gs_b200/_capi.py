@@ -76,6 +76,21 @@ SYMBOLS = {
     'sgs_sparse_plan_run': (C.c_int, [C.c_void_p, C.POINTER(Result)]),
     'sgs_sparse_plan_free': (None, [C.c_void_p]),
     'sgs_klocal_search': (C.c_int, [C.c_void_p, C.POINTER(Opts), C.POINTER(Result)]),
+    'sgs_klocal_sright_log': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int]),
+    'sgs_klocal_get_states': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    'sgs_klocal_states_count': (C.c_int, [C.c_void_p]),
+    'sgs_klocal_states_free': (None, [C.c_void_p]),
+    'sgs_klocal_states_select': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    'sgs_klocal_states_append': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    'sgs_klocal_state_info': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 5),
+    'sgs_klocal_state_rows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    'sgs_klocal_state_key': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    'sgs_klocal_state_energies': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    'sgs_klocal_state_set_energies': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    'sgs_klocal_states_shift': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    'sgs_klocal_set_states': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    'sgs_klocal_state_history': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int8), C.c_int,
+                                           C.POINTER(C.c_int)]),
     'sgs_klocal_create': (C.c_int, [C.c_void_p, C.POINTER(Opts), C.c_int, C.POINTER(C.c_void_p)]),
     'sgs_klocal_free': (None, [C.c_void_p]),
     'sgs_klocal_m': (C.c_int, [C.c_void_p]),

@@ -210,6 +210,109 @@ int sgs_klocal_ground_state(sgs_klocal *k, sgs_result *out)
     SGS_GUARD_END
 }
 
+struct sgs_klocal_states { KlocalStates *S; };
+
+int sgs_klocal_sright_log(const sgs_klocal *k, int *pairs, int cap) { return k ? klocal_sright_log(*k->M, pairs, pairs ? cap : 0) : 0; }
+
+int sgs_klocal_get_states(sgs_klocal *k, sgs_klocal_states **out)
+{
+    SGS_GUARD_BEGIN
+    if (!k || !out) return fail(SGS_ERR_ARG, "null argument");
+    KlocalStates *S = nullptr;
+    Status s = klocal_get_states(*k->M, &S);
+    if (!s.ok()) return done(s);
+    *out = new sgs_klocal_states{S};
+    return SGS_OK;
+    SGS_GUARD_END
+}
+
+int sgs_klocal_states_count(const sgs_klocal_states *s) { return s ? klocal_states_count(s->S) : 0; }
+void sgs_klocal_states_free(sgs_klocal_states *s) { if (s) { klocal_states_free(s->S); delete s; } }
+
+int sgs_klocal_states_select(const sgs_klocal_states *s, const int *idx, int count, sgs_klocal_states **out)
+{
+    SGS_GUARD_BEGIN
+    if (!s || !out || (count > 0 && !idx)) return fail(SGS_ERR_ARG, "null argument");
+    KlocalStates *S = nullptr;
+    Status st = klocal_states_select(s->S, idx, count, &S);
+    if (!st.ok()) return done(st);
+    *out = new sgs_klocal_states{S};
+    return SGS_OK;
+    SGS_GUARD_END
+}
+
+int sgs_klocal_states_append(sgs_klocal_states *dst, const sgs_klocal_states *src, int i)
+{
+    SGS_GUARD_BEGIN
+    if (!dst || !src) return fail(SGS_ERR_ARG, "null argument");
+    return done(klocal_states_append(dst->S, src->S, i));
+    SGS_GUARD_END
+}
+
+int sgs_klocal_state_info(const sgs_klocal *k, const sgs_klocal_states *s, int i, int *m, int *rank, int *begin, int *end, int *sright)
+{
+    SGS_GUARD_BEGIN
+    if (!k || !s) return fail(SGS_ERR_ARG, "null argument");
+    return done(klocal_state_info(*k->M, s->S, i, m, rank, begin, end, sright));
+    SGS_GUARD_END
+}
+
+int sgs_klocal_state_rows(const sgs_klocal *k, const sgs_klocal_states *s, int i, uint64_t *rows)
+{
+    SGS_GUARD_BEGIN
+    if (!k || !s || !rows) return fail(SGS_ERR_ARG, "null argument");
+    return done(klocal_state_rows(*k->M, s->S, i, rows));
+    SGS_GUARD_END
+}
+
+int sgs_klocal_state_key(const sgs_klocal *k, const sgs_klocal_states *s, int i, uint64_t *key, int *nwords)
+{
+    SGS_GUARD_BEGIN
+    if (!k || !s || !key || !nwords) return fail(SGS_ERR_ARG, "null argument");
+    return done(klocal_state_key(*k->M, s->S, i, key, SGS_KLOCAL_KEY_WORDS, nwords));
+    SGS_GUARD_END
+}
+
+int sgs_klocal_state_energies(const sgs_klocal_states *s, int i, double *Es)
+{
+    SGS_GUARD_BEGIN
+    if (!s || !Es) return fail(SGS_ERR_ARG, "null argument");
+    return done(klocal_state_energies(s->S, i, Es, 0));
+    SGS_GUARD_END
+}
+
+int sgs_klocal_state_set_energies(sgs_klocal_states *s, int i, const double *Es)
+{
+    SGS_GUARD_BEGIN
+    if (!s || !Es) return fail(SGS_ERR_ARG, "null argument");
+    return done(klocal_state_energies(s->S, i, const_cast<double *>(Es), 1));
+    SGS_GUARD_END
+}
+
+int sgs_klocal_states_shift(sgs_klocal *k, sgs_klocal_states *s, int add, int clear_history)
+{
+    SGS_GUARD_BEGIN
+    if (!k || !s) return fail(SGS_ERR_ARG, "null argument");
+    return done(klocal_states_shift(*k->M, s->S, add, clear_history));
+    SGS_GUARD_END
+}
+
+int sgs_klocal_set_states(sgs_klocal *k, const sgs_klocal_states *s, int m)
+{
+    SGS_GUARD_BEGIN
+    if (!k || !s) return fail(SGS_ERR_ARG, "null argument");
+    return done(klocal_set_states(*k->M, s->S, m));
+    SGS_GUARD_END
+}
+
+int sgs_klocal_state_history(sgs_klocal *k, const sgs_klocal_states *s, int i, int entry, int *terms, int8_t *signs, int cap, int *count)
+{
+    SGS_GUARD_BEGIN
+    if (!k || !s || !count || (cap > 0 && (!terms || !signs))) return fail(SGS_ERR_ARG, "null argument");
+    return done(klocal_state_history(*k->M, s->S, i, entry, terms, signs, cap, count));
+    SGS_GUARD_END
+}
+
 int sgs_klocal_search(const sgs_ham *h, const sgs_opts *opts, sgs_result *out)
 {
     SGS_GUARD_BEGIN

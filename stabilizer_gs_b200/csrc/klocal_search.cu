@@ -149,6 +149,13 @@ struct KlocalMachine::Impl {
     Status ground_state(sgs_result *out);
     Status traceback(int state, int entry, std::vector<std::pair<int, int>> &out);   // (file index, sign) in history order
     Status fetch_log(std::vector<DpStepLog> &log);
+    // periodic chain / stepwise access (py/klocal_periodic.py, py/state.py:309-325,402-462,542-567)
+    int epoch = 0;                 // bumped whenever the device states or their history change (set_states, advance)
+    std::vector<int> sr_log;       // (m, count) pairs in the order generate_Sright_* prints them
+    Status gen_sright_periodic(int cmax);
+    Status shift_states(std::vector<HostState> &hs, int from_m, int add);
+    std::vector<uint64_t> key_of(const HostState &h, int m) const;
+    void dedupe_sort(std::vector<HostState> &hs, int m, std::vector<int> *origin = nullptr) const;
     template <typename T> Status take(T **p, size_t count) { void *q = nullptr; SGS_CUDA_TRY(pool.take(&q, std::max<size_t>(count, 1) * sizeof(T))); *p = (T *)q; return Status(); }
 };
 
@@ -456,6 +463,7 @@ Status KlocalMachine::Impl::set_states(const std::vector<HostState> &hs, int m, 
 {
     if ((int)hs.size() > caps) return Status::fail(SGS_ERR_OVERFLOW, "k-local DP: more states than the batch capacity");
     m_ = m;
+    epoch++;
     const size_t ns = std::max<size_t>(hs.size(), 1);
     std::vector<DpState> ss(ns);
     std::vector<double> ee(ns * tstride, 0.0);
@@ -512,6 +520,7 @@ Status KlocalMachine::Impl::advance(int nsteps)
         return Status::fail(SGS_ERR_ARG, "no right-environment level for this site");
     if (!seg_open) { SGS_CUDA_TRY(cudaEventRecord(e0, st)); seg_open = true; }
     hctl_valid = false;
+    epoch++;
     int m0 = m_, resume = 0;
     void *args[] = {&terms, &dp, &m0, &nsteps, &resume};
     const void *const fns[3] = {(const void *)k_dp_run<kGrid>, (const void *)k_dp_run<kCluster>, (const void *)k_dp_run<kBlock>};
@@ -604,6 +613,100 @@ Status KlocalMachine::Impl::ground_state(sgs_result *out)
     return Status();
 }
 
+// generate_Sright_periodic (py/state.py:542-567): backward sweeps over one period, shifted by +l, until the set
+// of right environments at the period boundary is a fixed point; then one sweep over the whole unrolled chain.
+// Fills sr_log with the (m, count) pairs the reference prints.
+Status KlocalMachine::Impl::gen_sright_periodic(int cmax)
+{
+    const int l = H.l, kk = H.k;
+    if (l <= 0) return Status::fail(SGS_ERR_ARG, "not a periodic Hamiltonian");
+    const int end = l * (1 + cmax) + kk;
+    if (end > max_m) return Status::fail(SGS_ERR_ARG, "periodic chain: cmax exceeds the unrolled length of the Hamiltonian");
+    sr_log.clear();
+    Status s = make_top_level(end);
+    if (!s.ok()) return s;
+    std::vector<DpGroup> id;
+    bool have_id = false;
+    for (;;) {
+        s = run_sright(end, end - l);
+        if (!s.ok()) return s;
+        for (int m = end - 1; m >= end - l; m--) { sr_log.push_back(m); sr_log.push_back(hlev[m].count); }
+        const std::vector<DpGroup> *cur = nullptr;
+        s = host_groups(end - l, &cur);
+        if (!s.ok()) return s;
+        bool same = have_id && id.size() == cur->size();
+        for (size_t i = 0; same && i < id.size(); i++) same = group_equal(id[i], (*cur)[i]);
+        id = *cur;
+        have_id = true;
+        // stabs shifted by +l: same relative rows, now the level-`end` list
+        s = set_level(end, hlev[end - l]);
+        if (!s.ok()) return s;
+        if (same) break;
+    }
+    s = run_sright(end, 0);
+    if (!s.ok()) return s;
+    for (int m = end - 1; m >= 0; m--) { sr_log.push_back(m); sr_log.push_back(hlev[m].count); }
+    return Status();
+}
+
+// State.shift(add) (py/state.py:309-322): rows are origin-relative, so the shift is a relabelling of the level;
+// only the right environment has to be looked up, by content, in the destination level.
+Status KlocalMachine::Impl::shift_states(std::vector<HostState> &hs, int from_m, int add)
+{
+    if (from_m + add < 0 || from_m + add > max_m) return Status::fail(SGS_ERR_ARG, "shift leaves the chain");
+    const std::vector<DpGroup> *A = nullptr, *B = nullptr;
+    Status sg = host_groups(from_m, &A);
+    if (sg.ok()) sg = host_groups(from_m + add, &B);
+    if (!sg.ok()) return sg;
+    for (auto &h : hs) {
+        if (h.s.sright < 0 || h.s.sright >= (int)A->size()) return Status::fail(SGS_ERR_ARG, "state with an unknown right environment");
+        const DpGroup &G = (*A)[h.s.sright];
+        int found = -1;
+        for (size_t i = 0; i < B->size(); i++) if (group_equal((*B)[i], G)) { found = (int)i; break; }
+        if (found < 0) return Status::fail(SGS_ERR_ARG, "periodic shift: right environment not found at the shifted site (increase cmax)");
+        h.s.sright = found;
+    }
+    return Status();
+}
+
+// State.__hash__ content (py/state.py:224-225; cpp/state.cpp:311-330): window group, the (in)valid indices of the
+// terms whose last site is in [m+1, min(m+k-1, n)), right environment.  (m itself is added by the caller.)
+std::vector<uint64_t> KlocalMachine::Impl::key_of(const HostState &h, int m) const
+{
+    const int klo = boff[std::min(m + 1, n + 1)] - boff[m];
+    const int khi = boff[std::min(std::max(m + k - 1, m + 1), n)] - boff[m];
+    std::vector<uint64_t> key;
+    key.push_back((uint64_t)h.s.r);
+    key.push_back((uint64_t)h.s.sright);
+    for (int i = 0; i < kDpRows; i++) key.push_back(i < h.s.r ? h.s.g[i] : 0);
+    uint64_t v[kDpVW] = {0, 0, 0, 0};
+    for (int bb = klo; bb < khi; bb++) if ((h.s.valid[bb >> 6] >> (bb & 63)) & 1) v[bb >> 6] |= 1ULL << (bb & 63);
+    for (int i = 0; i < kDpVW; i++) key.push_back(v[i]);
+    return key;
+}
+
+// state_dict = {hash(state): state}: a later state with the same key replaces an earlier one; then key order.
+// origin (optional) receives, for every kept state, its position in the input list.
+void KlocalMachine::Impl::dedupe_sort(std::vector<HostState> &hs, int m, std::vector<int> *origin) const
+{
+    std::vector<HostState> outv;
+    std::vector<int> org;
+    for (size_t i = 0; i < hs.size(); i++) {
+        bool rep = false;
+        for (size_t o = 0; o < outv.size(); o++)
+            if (key_of(outv[o], m) == key_of(hs[i], m)) { outv[o] = hs[i]; org[o] = (int)i; rep = true; break; }
+        if (!rep) { outv.push_back(hs[i]); org.push_back((int)i); }
+    }
+    std::vector<int> perm(outv.size());
+    for (size_t i = 0; i < perm.size(); i++) perm[i] = (int)i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key_of(outv[a], m) < key_of(outv[b], m); });
+    std::vector<HostState> res;
+    std::vector<int> ro;
+    for (int i : perm) { res.push_back(outv[i]); ro.push_back(org[i]); }
+    hs.swap(res);
+    if (origin) origin->swap(ro);
+}
+
 // ------------------------------------------------------------------------------------------------ public
 
 KlocalMachine::KlocalMachine() : impl_(new Impl()) {}
@@ -631,6 +734,13 @@ Status KlocalMachine::create(const Hamiltonian &H, const sgs_opts &opts, int per
                     std::chrono::duration<double>(t1 - t0).count() * 1e3, std::chrono::duration<double>(t2 - t1).count() * 1e3,
                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count() * 1e3);
     }
+    else if (H.l > 0) {
+        // StateMachinePeriodic(H, generate_Sright_periodic(H, cmax)) (py/state.py:402-416,542-567)
+        s = M->impl_->gen_sright_periodic(periodic_cmax);
+        if (!s.ok()) return s;
+        s = M->impl_->init_states();
+        if (!s.ok()) return s;
+    }
     out = std::move(M);
     return Status();
 }
@@ -645,6 +755,165 @@ int KlocalMachine::nstates() const
 int KlocalMachine::sright_count(int m) const { return m < 0 || m >= (int)impl_->hlev.size() ? 0 : impl_->hlev[m].count; }
 Status KlocalMachine::evolve() { return impl_->advance(1); }
 Status KlocalMachine::ground_state(sgs_result *out) { return impl_->ground_state(out); }
+
+// ------------------------------------------------------------------------------------------------ stepwise access
+struct KlocalStates {
+    std::vector<HostState> hs;
+    std::vector<int> dev;      // device index each entry was read from (-1: none)
+    int m = 0;                 // site of every state in the list
+    int epoch = -1;            // machine epoch the device indices belong to
+};
+
+void klocal_states_free(KlocalStates *s) { delete s; }
+int klocal_states_count(const KlocalStates *s) { return s ? (int)s->hs.size() : 0; }
+
+// state_dict.values() of the machine's current site, in key order (the device order)
+Status klocal_get_states(KlocalMachine &M, KlocalStates **out)
+{
+    KlocalMachine::Impl &K = *M.impl();
+    std::unique_ptr<KlocalStates> S(new KlocalStates());
+    Status s = K.get_states(S->hs);
+    if (!s.ok()) return s;
+    S->dev.resize(S->hs.size());
+    for (size_t i = 0; i < S->dev.size(); i++) S->dev[i] = (int)i;
+    S->m = K.m_;
+    S->epoch = K.epoch;
+    *out = S.release();
+    return Status();
+}
+
+Status klocal_states_select(const KlocalStates *s, const int *idx, int count, KlocalStates **out)
+{
+    std::unique_ptr<KlocalStates> S(new KlocalStates());
+    S->m = s->m; S->epoch = s->epoch;
+    for (int i = 0; i < count; i++) {
+        if (idx[i] < 0 || idx[i] >= (int)s->hs.size()) return Status::fail(SGS_ERR_ARG, "state index out of range");
+        S->hs.push_back(s->hs[idx[i]]);
+        S->dev.push_back(s->dev[idx[i]]);
+    }
+    *out = S.release();
+    return Status();
+}
+
+// list building: dst.append(copy of src[i]); all states of a list sit at one site
+Status klocal_states_append(KlocalStates *dst, const KlocalStates *src, int i)
+{
+    if (!src || i < 0 || i >= (int)src->hs.size()) return Status::fail(SGS_ERR_ARG, "state index out of range");
+    if (dst->hs.empty()) { dst->m = src->m; dst->epoch = src->epoch; }
+    else if (dst->m != src->m) return Status::fail(SGS_ERR_ARG, "states of different sites in one list");
+    dst->hs.push_back(src->hs[i]);
+    dst->dev.push_back(dst->epoch == src->epoch ? src->dev[i] : -1);
+    return Status();
+}
+
+static Status check_index(const KlocalStates *s, int i)
+{
+    if (!s || i < 0 || i >= (int)s->hs.size()) return Status::fail(SGS_ERR_ARG, "state index out of range");
+    return Status();
+}
+
+// State.m, rank and window of State.stab (py/state.py:150-176: the projected group sits on the k-1 sites below m)
+Status klocal_state_info(const KlocalMachine &M, const KlocalStates *s, int i, int *m, int *rank, int *begin, int *end, int *sright)
+{
+    SGS_TRY(check_index(s, i));
+    const KlocalMachine::Impl &K = *const_cast<KlocalMachine &>(M).impl();
+    if (m) *m = s->m;
+    if (rank) *rank = s->hs[i].s.r;
+    if (begin) *begin = std::max(s->m - K.k + 1, 0);
+    if (end) *end = s->m;
+    if (sright) *sright = s->hs[i].s.sright;
+    return Status();
+}
+
+// the generators of State.stab as absolute W-word rows (all signs '+': StabEnergies keeps them so, cpp/stab.cpp:626)
+Status klocal_state_rows(const KlocalMachine &M, const KlocalStates *s, int i, uint64_t *rows)
+{
+    SGS_TRY(check_index(s, i));
+    const KlocalMachine::Impl &K = *const_cast<KlocalMachine &>(M).impl();
+    const int Wout = (2 * K.n + 63) / 64, o = s->m - K.k + 1;       // origin of the relative rows
+    for (int g = 0; g < s->hs[i].s.r; g++) {
+        for (int w = 0; w < Wout; w++) rows[(size_t)g * Wout + w] = 0;
+        const uint64_t rel = s->hs[i].s.g[g];
+        for (int j = 0; j < 32; j++) {
+            const uint64_t v = (rel >> (2 * j)) & 3;
+            const int site = o + j;
+            if (v && site >= 0 && site < K.n) rows[(size_t)g * Wout + ((2 * site) >> 6)] |= v << ((2 * site) & 63);
+        }
+    }
+    return Status();
+}
+
+Status klocal_state_key(const KlocalMachine &M, const KlocalStates *s, int i, uint64_t *key, int cap, int *nwords)
+{
+    SGS_TRY(check_index(s, i));
+    const KlocalMachine::Impl &K = *const_cast<KlocalMachine &>(M).impl();
+    std::vector<uint64_t> kk = K.key_of(s->hs[i], s->m);
+    kk.insert(kk.begin(), (uint64_t)(int64_t)s->m);
+    if ((int)kk.size() > cap) return Status::fail(SGS_ERR_ARG, "key buffer too small");
+    memcpy(key, kk.data(), kk.size() * 8);
+    *nwords = (int)kk.size();
+    return Status();
+}
+
+// EnergyLevel.Es of the state (2^rank doubles, flat index bit (rank-1-i) set <=> generator i carries '-'); set != 0 writes
+Status klocal_state_energies(const KlocalStates *s, int i, double *Es, int set)
+{
+    SGS_TRY(check_index(s, i));
+    HostState &h = const_cast<KlocalStates *>(s)->hs[i];
+    const size_t sz = (size_t)1 << h.s.r;
+    if (set) h.E.assign(Es, Es + sz);
+    else memcpy(Es, h.E.data(), sz * sizeof(double));
+    return Status();
+}
+
+// State.shift(add, clear_history) for every state of the list (py/state.py:309-325)
+Status klocal_states_shift(KlocalMachine &M, KlocalStates *s, int add, int clear_history)
+{
+    KlocalMachine::Impl &K = *M.impl();
+    SGS_TRY(K.shift_states(s->hs, s->m, add));
+    s->m += add;
+    if (clear_history) {
+        for (auto &h : s->hs) std::fill(h.E.begin(), h.E.end(), 0.0);     // EnergyLevel.clear (py/stab.py:282-286)
+        for (auto &d : s->dev) d = -1;
+    }
+    return Status();
+}
+
+// StateMachinePeriodic.state_dict = {hash(state): state ...}; .m = m  (py/klocal_periodic.py:12-14): later states
+// replace earlier ones with the same key, the machine holds them in key order; its history starts here.
+Status klocal_set_states(KlocalMachine &M, const KlocalStates *s, int m)
+{
+    KlocalMachine::Impl &K = *M.impl();
+    if (m != s->m) return Status::fail(SGS_ERR_ARG, "states of another site (shift them first)");
+    std::vector<HostState> hs = s->hs;
+    K.dedupe_sort(hs, m);
+    return K.set_states(hs, m, true);
+}
+
+// EnergyLevel.get_state(index, original_paulis, return_stab=False) (py/stab.py:288-305): the signed Hamiltonian terms
+// that generate the best full state reaching table entry `entry` of state i, in history order
+Status klocal_state_history(KlocalMachine &M, const KlocalStates *s, int i, int entry, int *terms, int8_t *signs, int cap, int *count)
+{
+    SGS_TRY(check_index(s, i));
+    KlocalMachine::Impl &K = *M.impl();
+    if (s->dev[i] < 0) { *count = 0; return Status(); }                  // history cleared
+    if (s->epoch != K.epoch) return Status::fail(SGS_ERR_ARG, "the machine has moved on: this state's history is no longer on the device");
+    if (entry < 0 || entry >= (1 << s->hs[i].s.r)) return Status::fail(SGS_ERR_ARG, "table entry out of range");
+    std::vector<std::pair<int, int>> h;
+    SGS_TRY(K.traceback(s->dev[i], entry, h));
+    if ((int)h.size() > cap) return Status::fail(SGS_ERR_ARG, "history buffer too small");
+    for (size_t g = 0; g < h.size(); g++) { terms[g] = h[g].first; signs[g] = (int8_t)h[g].second; }
+    *count = (int)h.size();
+    return Status();
+}
+
+int klocal_sright_log(const KlocalMachine &M, int *pairs, int cap)
+{
+    const KlocalMachine::Impl &K = *const_cast<KlocalMachine &>(M).impl();
+    const int np = (int)K.sr_log.size() / 2;
+    for (int i = 0; i < np && i < cap; i++) { pairs[2 * i] = K.sr_log[2 * i]; pairs[2 * i + 1] = K.sr_log[2 * i + 1]; }
+    return np;
+}
 
 Status klocal_search(const Hamiltonian &H, const sgs_opts &opts, sgs_result *out)
 {
@@ -712,74 +981,12 @@ static Status periodic_once(const Hamiltonian &H, int cmax, int c, const sgs_opt
     if (l <= 0) return Status::fail(SGS_ERR_ARG, "not a periodic Hamiltonian");
     std::vector<int> log, fixed;
 
-    // ---- generate_Sright_periodic ----
-    const int end = l * (1 + cmax) + k;
-    s = K.make_top_level(end);
-    if (!s.ok()) return s;
-    std::vector<DpGroup> id;
-    bool have_id = false;
-    for (;;) {
-        s = K.run_sright(end, end - l);
-        if (!s.ok()) return s;
-        for (int m = end - 1; m >= end - l; m--) { log.push_back(m); log.push_back(K.hlev[m].count); }
-        const std::vector<DpGroup> *cur = nullptr;
-        s = K.host_groups(end - l, &cur);
-        if (!s.ok()) return s;
-        bool same = have_id && id.size() == cur->size();
-        for (size_t i = 0; same && i < id.size(); i++) same = group_equal(id[i], (*cur)[i]);
-        id = *cur;
-        have_id = true;
-        // stabs shifted by +l: same relative rows, now the level-`end` list
-        s = K.set_level(end, K.hlev[end - l]);
-        if (!s.ok()) return s;
-        if (same) break;
-    }
-    s = K.run_sright(end, 0);
-    if (!s.ok()) return s;
-    for (int m = end - 1; m >= 0; m--) { log.push_back(m); log.push_back(K.hlev[m].count); }
-
-    // State.shift(add): relabel the level; the right environment is looked up by content
-    auto shift_states = [&](std::vector<HostState> &hs, int from_m, int add) -> Status {
-        const std::vector<DpGroup> *A = nullptr, *B = nullptr;
-        Status sg = K.host_groups(from_m, &A);
-        if (sg.ok()) sg = K.host_groups(from_m + add, &B);
-        if (!sg.ok()) return sg;
-        for (auto &h : hs) {
-            const DpGroup &G = (*A)[h.s.sright];
-            int found = -1;
-            for (size_t i = 0; i < B->size(); i++) if (group_equal((*B)[i], G)) { found = (int)i; break; }
-            if (found < 0) return Status::fail(SGS_ERR_ARG, "periodic shift: right environment not found at the shifted site (increase cmax)");
-            h.s.sright = found;
-        }
-        return Status();
-    };
-    // State.__hash__ content (py/state.py:224-225): m, window group, (in)valid indices for last site in
-    // [m+1, min(m+k-1, n)), right environment.  All lists compared here sit at m0 = k + l - 1.
+    // ---- generate_Sright_periodic: done by create() ----
+    log = K.sr_log;
     const int m0k = k + l - 1;
-    const int klo = K.boff[std::min(m0k + 1, n + 1)] - K.boff[m0k];
-    const int khi = K.boff[std::min(std::max(m0k + k - 1, m0k + 1), n)] - K.boff[m0k];
-    auto key_of = [&](const HostState &h) {
-        std::vector<uint64_t> key;
-        key.push_back((uint64_t)h.s.r);
-        key.push_back((uint64_t)h.s.sright);
-        for (int i = 0; i < kDpRows; i++) key.push_back(i < h.s.r ? h.s.g[i] : 0);
-        uint64_t v[kDpVW] = {0, 0, 0, 0};
-        for (int bb = klo; bb < khi; bb++) if ((h.s.valid[bb >> 6] >> (bb & 63)) & 1) v[bb >> 6] |= 1ULL << (bb & 63);
-        for (int i = 0; i < kDpVW; i++) key.push_back(v[i]);
-        return key;
-    };
-    auto same_key = [&](const HostState &a, const HostState &b) { return key_of(a) == key_of(b); };
-    // state_dict = {hash(state): state}: a later state with the same key replaces an earlier one; key order
-    auto dedupe_sort = [&](std::vector<HostState> &hs) {
-        std::vector<HostState> outv;
-        for (auto &h : hs) {
-            bool rep = false;
-            for (auto &o : outv) if (same_key(o, h)) { o = h; rep = true; break; }
-            if (!rep) outv.push_back(h);
-        }
-        std::stable_sort(outv.begin(), outv.end(), [&](const HostState &a, const HostState &b) { return key_of(a) < key_of(b); });
-        hs.swap(outv);
-    };
+    auto same_key = [&](const HostState &a, const HostState &b) { return K.key_of(a, m0k) == K.key_of(b, m0k); };
+    auto shift_states = [&](std::vector<HostState> &hs, int from_m, int add) { return K.shift_states(hs, from_m, add); };
+    auto dedupe_sort = [&](std::vector<HostState> &hs) { K.dedupe_sort(hs, m0k); };
     // periodic_evolve_states (py/klocal_periodic.py:11-18)
     auto periodic_evolve = [&](std::vector<HostState> hs, bool clear_history, int cc, std::vector<HostState> &res) -> Status {
         dedupe_sort(hs);
@@ -795,9 +1002,7 @@ static Status periodic_once(const Hamiltonian &H, int cmax, int c, const sgs_opt
         if (clear_history) for (auto &h : res) std::fill(h.E.begin(), h.E.end(), 0.0);     // EnergyLevel.clear, py/stab.py:282-286
         return Status();
     };
-    // ---- driver: py/klocal_periodic.py:21-34 ----
-    s = K.init_states();
-    if (!s.ok()) return s;
+    // ---- driver: py/klocal_periodic.py:21-34 (the initial states are set by create()) ----
     s = K.advance(k + 2 * l - 1);
     if (!s.ok()) return s;
     std::vector<HostState> states;
