@@ -130,7 +130,7 @@ void orow_to_string(const orow *r, int begin, int end, char *out)
 
 static void mask_set(omask *m, int i) { m->w[i >> 6] |= 1ULL << (i & 63); }
 static int mask_get(const omask *m, int i) { return (int)((m->w[i >> 6] >> (i & 63)) & 1); }
-static void mask_xor(omask *a, const omask *b) { a->w[0] ^= b->w[0]; a->w[1] ^= b->w[1]; }
+static void mask_xor(omask *a, const omask *b) { for (int i = 0; i < OMW; i++) a->w[i] ^= b->w[i]; }
 
 void ostab_init(ostab *s, int begin, int end) { s->m = 0; s->begin = begin; s->end = end; }
 
@@ -195,7 +195,7 @@ int ostab_decompose(const ostab *s, const orow *P, omask *x, int *sign)
     orow prod;
     memset(&prod, 0, sizeof(prod));       /* identity, q = 0: Pauli::reduce_dot folds from I (cpp/stab.cpp:340-345) */
     omask xm;
-    xm.w[0] = xm.w[1] = 0;
+    memset(&xm, 0, sizeof(xm));
     for (int i = 0; i < s->m; i++) {
         int p = orow_lowbit(&s->g[i]);
         if (p >= 0 && orow_bit(P, p)) { orow_dot(&prod, &prod, &s->g[i]); mask_set(&xm, i); }

@@ -27,13 +27,16 @@
 extern "C" {
 #endif
 
-#define OW 4              /* u64 words per row: up to 128 qubit positions            */
+#ifndef OW
+#define OW 4              /* u64 words per row: up to 128 qubit positions (make wide: OW = 12, 384 positions) */
+#endif
 #define OMAXQ (OW * 32)   /* positions; n (plus the DP's one-site overhang) < OMAXQ   */
 #define OMAXM OMAXQ       /* max generators of a group                               */
 #define OMAXTAB 26        /* max rank for which a 2^m energy table is materialised   */
 
 typedef struct { uint64_t b[OW]; int q; } orow;              /* one Pauli string       */
-typedef struct { uint64_t w[2]; } omask;                     /* subset of <=128 rows   */
+#define OMW ((OMAXM + 63) / 64)
+typedef struct { uint64_t w[OMW]; } omask;                   /* subset of <= OMAXM rows */
 typedef struct { int m, begin, end; orow g[OMAXM]; } ostab;  /* canonical signed group */
 
 /* ---- Hamiltonian (cpp/state.cpp:58-96, py/state.py:34-72) ---- */

@@ -69,24 +69,32 @@ int sgs_ham_from_arrays(int n, int k, int T, const uint64_t *zx, const double *w
 {
     SGS_GUARD_BEGIN
     if (!out || (T > 0 && (!zx || !w))) return fail(SGS_ERR_ARG, "null argument");
-    if (n <= 0 || n + 1 > SGS_MAX_QUBITS || k <= 0 || T < 0) return fail(SGS_ERR_ARG, "n, k or T out of range");
+    if (n <= 0 || n > (1 << 20) || k <= 0 || T < 0) return fail(SGS_ERR_ARG, "n, k or T out of range");
     std::unique_ptr<sgs_ham> h(new sgs_ham());
     h->H.n = n; h->H.k = k;
+    h->H.wide = n + 1 > SGS_MAX_QUBITS;
     const int W = (2 * n + 63) / 64;
     for (int t = 0; t < T; t++) {
-        PackedRow r;
-        for (int i = 0; i < W; i++) r.w[i] = zx[(size_t)t * W + i];
-        int b = n, e = 0;
-        for (int j = 0; j < n; j++)
-            if ((r.w[(2 * j) >> 6] >> ((2 * j) & 63)) & 3) { if (j < b) b = j; e = j + 1; }
-        if (2 * n < 64 * W) {
-            // bits beyond qubit n-1 are not part of the Hamiltonian
-            for (int bit = 2 * n; bit < 64 * W; bit++) if ((r.w[bit >> 6] >> (bit & 63)) & 1) return fail(SGS_ERR_ARG, "term has bits beyond qubit n-1");
+        const uint64_t *r = zx + (size_t)t * W;
+        std::vector<int> sites, codes;
+        for (int wi = 0; wi < W; wi++) {
+            if (!r[wi]) continue;
+            for (int j = 32 * wi; j < 32 * wi + 32; j++) {
+                const int v = (int)((r[wi] >> ((2 * j) & 63)) & 3);
+                if (!v) continue;
+                if (j >= n) return fail(SGS_ERR_ARG, "term has bits beyond qubit n-1");
+                sites.push_back(j); codes.push_back(v);
+            }
         }
+        int b = sites.empty() ? 0 : sites.front(), e = sites.empty() ? 1 : sites.back() + 1;
         if (begin && end) { b = begin[t]; e = end[t]; }
         if (e <= b) { b = 0; e = 1; }     // identity string: window [0,1)
         if (b < 0 || e > n) return fail(SGS_ERR_ARG, "term window out of range");
-        h->H.add_term(r, w[t], b, e);
+        if (!sites.empty() && (b > sites.front() || e < sites.back() + 1)) return fail(SGS_ERR_ARG, "term window does not cover its letters");
+        // the window may be wider than the support (Pauli(str, qubits) with explicit I letters): pad with identity sites
+        if (sites.empty() || sites.front() != b) { sites.insert(sites.begin(), b); codes.insert(codes.begin(), 0); }
+        if (sites.back() != e - 1) { sites.push_back(e - 1); codes.push_back(0); }
+        if (!h->H.add_term_sites(sites, codes, w[t])) return fail(SGS_ERR_LIMIT, "with n > 127 a term may span at most 32 sites");
     }
     h->H.finalize();
     *out = h.release();
@@ -106,7 +114,7 @@ int sgs_ham_terms(const sgs_ham *h, uint64_t *zx, double *w, int *begin, int *en
     if (!h) return fail(SGS_ERR_ARG, "null handle");
     const int W = (2 * h->H.n + 63) / 64;
     for (int t = 0; t < h->H.T(); t++) {
-        if (zx) for (int i = 0; i < W; i++) zx[(size_t)t * W + i] = h->H.terms[t].w[i];
+        if (zx) h->H.row_words(t, zx + (size_t)t * W, W);
         if (w) w[t] = h->H.weights[t];
         if (begin) begin[t] = h->H.begin[t];
         if (end) end[t] = h->H.end[t];

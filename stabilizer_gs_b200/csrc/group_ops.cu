@@ -202,6 +202,179 @@ Status group_canonicalize(int device, int n, int m, uint64_t *rows, int8_t *sign
     return Status();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide groups (n > 127 or more than 128 generators: the ground state of a long k-local chain).  Same results as
+// k_canonicalize / k_group_energy — the RREF of a row space is unique and so is the sign of each of its elements —
+// with rows of any width kept in global memory.
+//   k_rref_wide     one block: Gauss-Jordan on the bit matrix [rows | I] by columns (lowest bit first), so that the
+//                   rows come out sorted by pivot and the identity half records which generators multiply into each
+//                   canonical row (Gauss_elimination_full, cpp/linear.cpp:129)
+//   k_products_wide one warp per canonical row: the phase-tracked product of the selected signed generators
+//                   (Stab::transform, cpp/stab.cpp:442-449; Pauli::dot :320-330)
+//   k_signs_wide    one warp per term: reduction over the canonical rows, pivot by pivot (Stab::energy :579-587)
+__global__ void __launch_bounds__(1024) k_rref_wide(int m, int nbits, int W, int Wu, uint64_t *Mx, int *perm, int *piv, int *rank_out,
+                                                    int *row_of_bit)
+{
+    __shared__ int s_min[32];
+    __shared__ int s_piv;
+    extern __shared__ unsigned char s_flag[];          // [m] row has the pivot bit
+    const int tid = threadIdx.x, nth = blockDim.x, Wt = W + Wu;
+    for (int i = tid; i < m; i += nth) perm[i] = i;
+    for (int b = tid; b < nbits; b += nth) row_of_bit[b] = -1;
+    __syncthreads();
+    int r = 0;
+    for (int c = 0; c < nbits && r < m; c++) {
+        const int cw = c >> 6;
+        const uint64_t cb = 1ULL << (c & 63);
+        int best = m;
+        for (int i = r + tid; i < m; i += nth) if (Mx[(size_t)perm[i] * Wt + cw] & cb) { best = i; break; }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if ((tid & 31) == 0) s_min[tid >> 5] = best;
+        __syncthreads();
+        if (tid < 32) {
+            int v = tid < (nth >> 5) ? s_min[tid] : m;
+            v = __reduce_min_sync(0xffffffffu, v);
+            if (tid == 0) s_piv = v;
+        }
+        __syncthreads();
+        const int pv = s_piv;
+        if (pv >= m) continue;                           // (uniform: every thread read s_piv after the barrier)
+        if (tid == 0) { const int t = perm[r]; perm[r] = perm[pv]; perm[pv] = t; piv[r] = c; row_of_bit[c] = r; }
+        __syncthreads();
+        const int pr = perm[r];
+        for (int i = tid; i < m; i += nth) s_flag[i] = (i != r && (Mx[(size_t)perm[i] * Wt + cw] & cb)) ? 1 : 0;
+        __syncthreads();
+        for (int idx = tid; idx < m * Wt; idx += nth) {
+            const int i = idx / Wt, w = idx - i * Wt;
+            if (s_flag[i]) Mx[(size_t)perm[i] * Wt + w] ^= Mx[(size_t)pr * Wt + w];
+        }
+        __syncthreads();
+        r++;
+    }
+    if (tid == 0) *rank_out = r;
+}
+
+// G: the m signed generators (W words each), qG their phases; canonical row i = product over the set bits of its
+// combination mask.  Lane l holds words l, l + 32, ... of the accumulator (W <= 32 * kWideWpl).
+constexpr int kWideWpl = 8;
+__global__ void k_products_wide(int m, int W, int Wu, const uint64_t *__restrict__ Mx, const int *__restrict__ perm, const int *rank,
+                                const uint64_t *__restrict__ G, const int *__restrict__ qG, uint64_t *__restrict__ C, int *__restrict__ qC,
+                                int8_t *__restrict__ signs)
+{
+    const int lane = threadIdx.x & 31, i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, Wt = W + Wu;
+    if (i >= *rank) return;
+    const uint64_t *U = Mx + (size_t)perm[i] * Wt + W;
+    uint64_t acc[kWideWpl];
+#pragma unroll
+    for (int k = 0; k < kWideWpl; k++) acc[k] = 0;
+    int q = 0;
+    for (int uw = 0; uw < Wu; uw++) {
+        uint64_t bits = U[uw];
+        while (bits) {
+            const int j = uw * 64 + ctz64(bits);
+            bits &= bits - 1;
+            if (j >= m) break;
+            uint64_t par = 0;
+#pragma unroll
+            for (int k = 0; k < kWideWpl; k++) {
+                const int w = lane + 32 * k;
+                if (w < W) { const uint64_t g = G[(size_t)j * W + w]; par ^= (acc[k] >> 1) & g & kEven; acc[k] ^= g; }
+            }
+            const unsigned p = __reduce_xor_sync(0xffffffffu, (unsigned)parity64(par));
+            q = (q + qG[j] + 2 * (int)(p & 1)) & 3;
+        }
+    }
+    int ny = 0;
+#pragma unroll
+    for (int k = 0; k < kWideWpl; k++) {
+        const int w = lane + 32 * k;
+        if (w < W) { C[(size_t)i * W + w] = acc[k]; ny += popc64(acc[k] & (acc[k] >> 1) & kEven); }
+    }
+    ny = __reduce_add_sync(0xffffffffu, ny);
+    if (lane == 0) {
+        const int sg = ((q + ny) & 3) == 0 ? 1 : -1;
+        signs[i] = (int8_t)sg;
+        qC[i] = (4 - (ny & 3)) & 3;                      // phase of the row taken with sign '+' ...
+        if (sg < 0) qC[i] = (qC[i] + 2) & 3;             // ... and with its own sign
+    }
+}
+
+__global__ void k_signs_wide(int T, int W, int nbits, const int *rank, const uint64_t *__restrict__ C, const int *__restrict__ qC,
+                             const int *__restrict__ row_of_bit, const uint64_t *__restrict__ P, int8_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31, t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= T) return;
+    (void)rank;
+    uint64_t v[kWideWpl];
+    int ny = 0;
+#pragma unroll
+    for (int k = 0; k < kWideWpl; k++) {
+        const int w = lane + 32 * k;
+        v[k] = w < W ? P[(size_t)t * W + w] : 0;
+        ny += popc64(v[k] & (v[k] >> 1) & kEven);
+    }
+    ny = __reduce_add_sync(0xffffffffu, ny);
+    int q = (4 - (ny & 3)) & 3;
+    bool member = true;
+    for (;;) {
+        // lowest set bit of v (every element of the row space has its lowest bit at a pivot; RREF rows carry no other pivot)
+        int low = nbits;
+#pragma unroll
+        for (int k = kWideWpl - 1; k >= 0; k--) if (v[k]) low = (lane + 32 * k) * 64 + ctz64(v[k]);
+        low = __reduce_min_sync(0xffffffffu, low);
+        if (low >= nbits) break;                          // v == identity: a member
+        const int i = row_of_bit[low];
+        if (i < 0) { member = false; break; }
+        uint64_t par = 0;
+#pragma unroll
+        for (int k = 0; k < kWideWpl; k++) {
+            const int w = lane + 32 * k;
+            if (w < W) { const uint64_t g = C[(size_t)i * W + w]; par ^= (v[k] >> 1) & g & kEven; v[k] ^= g; }
+        }
+        const unsigned p = __reduce_xor_sync(0xffffffffu, (unsigned)parity64(par));
+        q = (q + qC[i] + 2 * (int)(p & 1)) & 3;
+    }
+    if (lane == 0) out[t] = member ? (int8_t)((q & 2) ? -1 : 1) : (int8_t)0;
+}
+
+Status group_finish_wide(cudaStream_t st, int n, int m, uint64_t *rows, int8_t *signs, int *rank, int T, const uint64_t *P, int8_t *term_signs)
+{
+    const int W = (2 * n + 63) / 64, Wu = (std::max(m, 1) + 63) / 64, Wt = W + Wu, nbits = 2 * n;
+    if (W > 32 * kWideWpl) return Status::fail(SGS_ERR_LIMIT, "ground-state group: more than 8192 qubits");
+    const int mm = std::max(m, 1), Tn = std::max(T, 1);
+    std::vector<uint64_t> hM((size_t)mm * Wt, 0);
+    std::vector<int> hq(mm, 0);
+    for (int i = 0; i < m; i++) {
+        int ny = 0;
+        for (int w = 0; w < W; w++) { const uint64_t x = rows[(size_t)i * W + w]; hM[(size_t)i * Wt + w] = x; ny += __builtin_popcountll(x & (x >> 1) & kEven); }
+        hM[(size_t)i * Wt + W + (i >> 6)] |= 1ULL << (i & 63);
+        hq[i] = ((4 - (ny & 3)) & 3);
+        if (signs[i] < 0) hq[i] = (hq[i] + 2) & 3;
+    }
+    DevBuf<uint64_t> dM, dG, dC, dP; DevBuf<int> dperm, dpiv, drank, drob, dqG, dqC; DevBuf<int8_t> dsg, dout;
+    SGS_CUDA_TRY(dM.alloc(hM.size())); SGS_CUDA_TRY(dG.alloc((size_t)mm * W)); SGS_CUDA_TRY(dC.alloc((size_t)mm * W)); SGS_CUDA_TRY(dP.alloc((size_t)Tn * W));
+    SGS_CUDA_TRY(dperm.alloc(mm)); SGS_CUDA_TRY(dpiv.alloc(mm)); SGS_CUDA_TRY(drank.alloc(1)); SGS_CUDA_TRY(drob.alloc(std::max(nbits, 1)));
+    SGS_CUDA_TRY(dqG.alloc(mm)); SGS_CUDA_TRY(dqC.alloc(mm)); SGS_CUDA_TRY(dsg.alloc(mm)); SGS_CUDA_TRY(dout.alloc(Tn));
+    SGS_CUDA_TRY(cudaMemcpyAsync(dM.p, hM.data(), hM.size() * 8, cudaMemcpyHostToDevice, st));
+    if (m) SGS_CUDA_TRY(cudaMemcpyAsync(dG.p, rows, (size_t)m * W * 8, cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(dqG.p, hq.data(), (size_t)mm * 4, cudaMemcpyHostToDevice, st));
+    if (T) SGS_CUDA_TRY(cudaMemcpyAsync(dP.p, P, (size_t)T * W * 8, cudaMemcpyHostToDevice, st));
+    SGS_CUDA_TRY(cudaFuncSetAttribute(k_rref_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(mm, 1024)));
+    k_rref_wide<<<1, 1024, mm, st>>>(m, nbits, W, Wu, dM.p, dperm.p, dpiv.p, drank.p, drob.p);
+    k_products_wide<<<(mm * 32 + 127) / 128, 128, 0, st>>>(m, W, Wu, dM.p, dperm.p, drank.p, dG.p, dqG.p, dC.p, dqC.p, dsg.p);
+    k_signs_wide<<<(Tn * 32 + 127) / 128, 128, 0, st>>>(T, W, nbits, drank.p, dC.p, dqC.p, drob.p, dP.p, dout.p);
+    SGS_CUDA_TRY(cudaGetLastError());
+    SGS_CUDA_TRY(cudaMemcpyAsync(rank, drank.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<uint64_t> hc((size_t)mm * W, 0);
+    SGS_CUDA_TRY(cudaMemcpy(hc.data(), dC.p, hc.size() * 8, cudaMemcpyDeviceToHost));
+    if (m) SGS_CUDA_TRY(cudaMemcpy(signs, dsg.p, m, cudaMemcpyDeviceToHost));
+    if (T) SGS_CUDA_TRY(cudaMemcpy(term_signs, dout.p, T, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; i++)
+        for (int w = 0; w < W; w++) rows[(size_t)i * W + w] = i < *rank ? hc[(size_t)i * W + w] : 0;
+    return Status();
+}
+
 // K1 + K2 back to back on the caller's stream and workspace (no allocation, one synchronisation): canonicalise
 // the m generator rows, then the sign of every one of the T terms under the canonical group.
 size_t group_finish_ws_bytes(int T) { return (size_t)kMaxRows * 4 * 8 + (size_t)std::max(T, 1) * 4 * 8 + kMaxRows + std::max(T, 1) + 64 + 1024; }
@@ -209,7 +382,7 @@ size_t group_finish_ws_bytes(int T) { return (size_t)kMaxRows * 4 * 8 + (size_t)
 Status group_finish(cudaStream_t st, void *ws, int n, int m, uint64_t *rows, int8_t *signs, int *rank, int T, const uint64_t *P,
                     int8_t *term_signs)
 {
-    if (m > kMaxRows) return Status::fail(SGS_ERR_LIMIT, "at most 128 generator rows");
+    if (m > kMaxRows || n + 1 > 128) return group_finish_wide(st, n, m, rows, signs, rank, T, P, term_signs);
     const int Win = (2 * n + 63) / 64, W = words_for(n), Tn = std::max(T, 1);
     char *base = (char *)ws;
     uint64_t *d_rows = (uint64_t *)base; base += (size_t)kMaxRows * 4 * 8;

@@ -15,17 +15,24 @@ struct PackedRow {
     uint64_t w[kMaxWords] = {0, 0, 0, 0};
 };
 
+constexpr int kCompactSites = 32;     // a compact row holds a term that spans at most 32 sites
+
 struct Hamiltonian {
     int n = 0, k = 0, l = 0;            // l: period (periodic files), else 0
-    int W = 1;                          // words per row = ceil(2 * (n + 1) / 64): the DP's level-n window overhangs by one site
-    std::vector<PackedRow> terms;       // file order
+    int W = 1;                          // words per absolute row = ceil(2 * n / 64) (any n)
+    bool wide = false;                  // n + 1 > 128: absolute rows do not fit a PackedRow; every term must be compact
+    std::vector<PackedRow> terms;       // file order, absolute rows (all zero in a wide Hamiltonian)
+    std::vector<uint64_t> crow;         // file order, compact rows: bit 2j = z, 2j+1 = x of site begin + j (0 if the term spans > 32 sites)
+    std::vector<uint8_t> compact;       // 1 if crow[t] holds the term
     std::vector<double> weights;
     std::vector<int> begin, end;        // term windows [min site, max site + 1)
     std::vector<int> order;             // paulis_list order → file index
     std::vector<int> bucket_off;        // n + 1 offsets into `order` by last site
 
-    int T() const { return (int)terms.size(); }
-    void add_term(const PackedRow &r, double w, int b, int e);
+    int T() const { return (int)weights.size(); }
+    void add_term(const PackedRow &r, double w, int b, int e);               // n + 1 <= 128 only
+    bool add_term_sites(const std::vector<int> &sites, const std::vector<int> &codes, double w);   // any n; codes: 0 I, 1 Z, 2 X, 3 Y
+    void row_words(int t, uint64_t *out, int Wout) const;                    // absolute row of term t as Wout words
     void finalize();                    // builds order / bucket_off / W
 };
 

@@ -41,7 +41,8 @@ static_assert(kDpMaxSr <= 32, "one lane per echelon row");
 
 struct DpTerms {                   // Hamiltonian in paulis_list order
     int n, k, T, W;
-    const uint64_t *rows;          // [T * W] absolute rows
+    const uint64_t *rows;          // [T] compact rows: bit 2j = z, 2j+1 = x of site tb[t] + j (a term spans <= k <= 15 sites)
+    const int *tb;                 // [T] first site of each term's window
     const double *w;               // [T]
     const int *boff;               // [n + 2] bucket offsets by last site (boff[n+1] = T)
     const int *file_index;         // [T] position -> file index
@@ -72,17 +73,15 @@ struct DpBack {                    // back-pointer of one table entry
     uint16_t signs;                // bit a: the a-th generator added at this site carries '-'
 };
 
-// ---- 64-bit window extraction from an absolute W-word row: bits [2*o, 2*o + 64) (o may be negative)
-SGS_D uint64_t rel_row(const uint64_t *row, int W, int o)
+// ---- a term as a 64-bit row relative to origin o: bit 2j = z, 2j+1 = x of site o + j (bits outside are dropped).
+// Every object of a site step lives on <= 2k sites, so the chain length n never enters: the DP runs at any n
+// (cpp/state.cpp:411, cpp/stab.cpp:782-809 carry a k-site window the same way).
+SGS_D uint64_t term_rel(const DpTerms &H, int pos, int o)
 {
-    const int sh = 2 * o;
-    uint64_t out = 0;
-    for (int w = 0; w < W; w++) {
-        const int lo = w * 64 - sh;              // position of word w's bit 0 in the output
-        if (lo <= -64 || lo >= 64) continue;
-        out |= lo >= 0 ? (row[w] << lo) : (row[w] >> (-lo));
-    }
-    return out;
+    const int sh = 2 * (H.tb[pos] - o);
+    const uint64_t r = H.rows[pos];
+    if (sh >= 64 || sh <= -64) return 0;
+    return sh >= 0 ? (r << sh) : (r >> (-sh));
 }
 
 SGS_D int q_plus(uint64_t r) { return (4 - (popc64(r & (r >> 1) & kEven) & 3)) & 3; }
@@ -390,7 +389,7 @@ SGS_D void sr_seed(const DpGroup &G, int p, SrBranch &b)
 // (cpp/state.cpp:129-145).  Returns the number of branches written to out[0..2).
 SGS_D int sr_branch(const DpTerms &H, int o, int b0, int pos, const SrBranch &Bc, SrBranch *out)
 {
-    const uint64_t P = rel_row(H.rows + (size_t)pos * H.W, H.W, o);
+    const uint64_t P = term_rel(H, pos, o);
     bool com = true;
     for (int i = 0; i < Bc.r; i++) com &= !anti(Bc.g[i], P);
     if (!com || in_rref(Bc.g, Bc.r, P)) { out[0] = Bc; return 1; }
@@ -399,7 +398,7 @@ SGS_D int sr_branch(const DpTerms &H, int o, int b0, int pos, const SrBranch &Bc
     signed_add(inc.g, inc.q, inc.r, P, q_plus(P));
     bool ok = inc.r <= kDpRows;
     for (int t = b0; t < pos && ok; t++)
-        if ((Bc.excl >> (t - b0)) & 1) ok = !in_rref(inc.g, inc.r, rel_row(H.rows + (size_t)t * H.W, H.W, o));
+        if ((Bc.excl >> (t - b0)) & 1) ok = !in_rref(inc.g, inc.r, term_rel(H, t, o));
     if (ok) out[nn++] = inc;
     out[nn] = Bc;
     out[nn].excl |= 1u << (pos - b0);
@@ -758,7 +757,7 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
         {
             const int b0 = H.boff[m], nwin = min(H.boff[min(m + k + 2, H.n + 1)] - b0, 64 * kDpVW);
             __syncthreads();
-            for (int i = threadIdx.x; i < nwin; i += blockDim.x) relw[i] = rel_row(H.rows + (size_t)(b0 + i) * H.W, H.W, m - k + 1);
+            for (int i = threadIdx.x; i < nwin; i += blockDim.x) relw[i] = term_rel(H, b0 + i, m - k + 1);
             __syncthreads();
         }
         for (int s = wid; s < nin; s += nw) {
@@ -1028,7 +1027,7 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_sr_run(DpTerms 
         if (CL && (!paths || (Ln.count << nt) > kBailC * nth)) { bail = true; break; }    // the next kernel takes over from this level
         if (paths) {
             __syncthreads();
-            if ((int)threadIdx.x < nt) srel[threadIdx.x] = rel_row(H.rows + (size_t)(b0 + threadIdx.x) * H.W, H.W, o);
+            if ((int)threadIdx.x < nt) srel[threadIdx.x] = term_rel(H, b0 + threadIdx.x, o);
             __syncthreads();
             const int npath = Ln.count << nt;
             for (int bw = tid - lane; bw < npath; bw += nth) {        // warp-uniform: one allocation per warp

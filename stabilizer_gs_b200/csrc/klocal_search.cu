@@ -249,26 +249,30 @@ Status KlocalMachine::Impl::init()
         SGS_CUDA_TRY(pool.open(device, dpb + srb + ((size_t)16 << 20)));
     }
     const int Tn = std::max(T, 1);
-    std::vector<uint64_t> rows((size_t)Tn * W, 0);
+    std::vector<uint64_t> rows((size_t)Tn, 0);
     std::vector<double> w(Tn, 0.0);
-    std::vector<int> fidx(Tn, 0);
+    std::vector<int> fidx(Tn, 0), tbeg(Tn, 0);
     for (int p = 0; p < T; p++) {
         const int f = H.order[p];
-        for (int i = 0; i < W; i++) rows[(size_t)p * W + i] = H.terms[f].w[i];
+        if (!H.compact[f]) return Status::fail(SGS_ERR_LIMIT, "k-local DP: a term spans more than 32 sites");
+        rows[p] = H.crow[f];
+        tbeg[p] = H.begin[f];
         w[p] = H.weights[f];
         fidx[p] = f;
     }
     boff = H.bucket_off;            // n + 1 entries, boff[n] = T
     boff.push_back(T);              // boff[n + 1]
-    uint64_t *d_rows; double *d_w; int *d_boff, *d_fidx;
+    uint64_t *d_rows; double *d_w; int *d_boff, *d_fidx, *d_tb;
     SGS_TRY(take(&d_rows, rows.size())); SGS_TRY(take(&d_w, w.size())); SGS_TRY(take(&d_boff, boff.size())); SGS_TRY(take(&d_fidx, fidx.size()));
+    SGS_TRY(take(&d_tb, tbeg.size()));
+    SGS_CUDA_TRY(cudaMemcpyAsync(d_tb, tbeg.data(), tbeg.size() * 4, cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaMemcpyAsync(d_w, w.data(), w.size() * 8, cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaMemcpyAsync(d_boff, boff.data(), boff.size() * 4, cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaMemcpyAsync(d_fidx, fidx.data(), fidx.size() * 4, cudaMemcpyHostToDevice, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));                // the host vectors go out of scope
     terms.n = n; terms.k = k; terms.T = T; terms.W = W;
-    terms.rows = d_rows; terms.w = d_w; terms.boff = d_boff; terms.file_index = d_fidx;
+    terms.rows = d_rows; terms.tb = d_tb; terms.w = d_w; terms.boff = d_boff; terms.file_index = d_fidx;
     hlev.assign(max_m + 2, DpLevelDev{});
     SGS_TRY(take(&d_levels, hlev.size()));
     SGS_CUDA_TRY(cudaMemsetAsync(d_levels, 0, hlev.size() * sizeof(DpLevelDev), st));
@@ -587,12 +591,12 @@ Status KlocalMachine::Impl::ground_state(sgs_result *out)
     std::vector<uint64_t> rows((size_t)std::max(mg, 1) * Wout, 0);
     std::vector<int8_t> signs(std::max(mg, 1), 1);
     for (int i = 0; i < mg; i++) {
-        for (int w = 0; w < Wout; w++) rows[(size_t)i * Wout + w] = H.terms[hist[i].first].w[w];
+        H.row_words(hist[i].first, rows.data() + (size_t)i * Wout, Wout);
         signs[i] = (int8_t)hist[i].second;
     }
     int rankc = 0;
     std::vector<uint64_t> P((size_t)std::max(T, 1) * Wout, 0);
-    for (int t = 0; t < T; t++) for (int w = 0; w < Wout; w++) P[(size_t)t * Wout + w] = H.terms[t].w[w];
+    for (int t = 0; t < T; t++) H.row_words(t, P.data() + (size_t)t * Wout, Wout);
     std::vector<int8_t> ts(std::max(T, 1), 0);
     s = group_finish(st, d_finish, n, mg, rows.data(), signs.data(), &rankc, T, P.data(), ts.data());   // K1 + K2 on the device
     if (!s.ok()) return s;
@@ -1062,7 +1066,9 @@ static Status periodic_once(const Hamiltonian &H, int cmax, int c, const sgs_opt
     }
     const int Wout = (2 * n + 63) / 64;
     auto gen_string = [&](const Orb &o, size_t g) {
-        return row_to_string(H.terms[o.gens[g].first].w, o.gens[g].second, o.begin, o.end);
+        std::vector<uint64_t> rw(Wout);
+        H.row_words(o.gens[g].first, rw.data(), Wout);
+        return row_to_string(rw.data(), o.gens[g].second, o.begin, o.end);
     };
     std::sort(orbits.begin(), orbits.end(), [&](const Orb &a, const Orb &b) {
         if (a.energy != b.energy) return a.energy < b.energy;
@@ -1091,7 +1097,7 @@ static Status periodic_once(const Hamiltonian &H, int cmax, int c, const sgs_opt
         o.gens = (uint64_t *)calloc(std::max(o.m, 1) * (size_t)Wout, 8);
         o.signs = (int8_t *)calloc(std::max(o.m, 1), 1);
         for (int g = 0; g < o.m; g++) {
-            for (int w = 0; w < Wout; w++) o.gens[(size_t)g * Wout + w] = H.terms[orbits[i].gens[g].first].w[w];
+            H.row_words(orbits[i].gens[g].first, o.gens + (size_t)g * Wout, Wout);
             o.signs[g] = (int8_t)orbits[i].gens[g].second;
         }
     }

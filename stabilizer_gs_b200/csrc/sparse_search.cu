@@ -141,7 +141,7 @@ SparseDev SparsePlan::Impl::dev_view(const DevCtx &c) const
 Status SparsePlan::Impl::init()
 {
     n = H.n; T = H.T();
-    if (n > 2 * 64) return Status::fail(SGS_ERR_LIMIT, "sparse search supports n <= 128");
+    if (H.wide || n + 1 > SGS_MAX_QUBITS) return Status::fail(SGS_ERR_LIMIT, "sparse search supports n <= 127 (the k-local DP takes any n)");
     if (T > 65535) return Status::fail(SGS_ERR_LIMIT, "sparse search supports at most 65535 terms");
     if (T > 8192) return Status::fail(SGS_ERR_LIMIT, "sparse search supports at most 8192 terms (shared-memory lists)");
     {

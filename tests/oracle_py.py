@@ -9,9 +9,11 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, 'oracle')
-LIB = os.path.join(ORACLE_DIR, 'liboracle.so')
-
-OW = 4
+# SGS_ORACLE_OW=12 selects the wide build (rows of 12 words, chains of up to 382 sites); the table sizes of the
+# energy tables limit it to the k-local DP in practice
+OW = int(os.environ.get('SGS_ORACLE_OW', '4'))
+assert OW in (4, 12)
+LIB = os.path.join(ORACLE_DIR, 'liboracle.so' if OW == 4 else 'liboracle_w12.so')
 OMAXQ = OW * 32
 OMAXM = OMAXQ
 
@@ -21,7 +23,7 @@ class ORow(C.Structure):
 
 
 class OMask(C.Structure):
-    _fields_ = [('w', C.c_uint64 * 2)]
+    _fields_ = [('w', C.c_uint64 * ((OMAXM + 63) // 64))]
 
 
 class OStab(C.Structure):

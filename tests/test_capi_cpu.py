@@ -43,9 +43,14 @@ def test_periodic_parser_replicates_terms():
 
 def test_parse_errors():
     Sg = S()
-    for bad in ("", "x y\n", "2 2\n 1.0 QZ 0 1\n", "2 2\n 1.0 ZZ 0\n", "2 2\n 1.0 ZZ 0 5\n", "200 2\n 1.0 Z 0\n"):
+    for bad in ("", "x y\n", "2 2\n 1.0 QZ 0 1\n", "2 2\n 1.0 ZZ 0\n", "2 2\n 1.0 ZZ 0 5\n", "200 40\n 1.0 ZZ 0 39\n"):
         with pytest.raises(Sg.SgsError):
             Sg.HamHandle.from_text(bad)
+    # n > 127 parses (the k-local DP runs at any n); rows come back at full width
+    H = Sg.HamHandle.from_text("200 2\n 1.0 Z 0\n -0.5 XY 198 199\n")
+    assert (H.n, H.words, H.nterms) == (200, 7, 2)
+    rows, w, b, e = H.terms()
+    assert rows[0][0] == 1 and rows[1][6] == (2 << (2 * 198 - 384)) | (3 << (2 * 199 - 384)) and (b[1], e[1]) == (198, 200)
     # the Python reference stops at the first blank line (py/state.py:41-43)
     H = Sg.HamHandle.from_text("2 2\n 1.0 ZZ 0 1\n\n 1.0 XX 0 1\n")
     assert H.nterms == 1
