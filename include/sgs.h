@@ -157,6 +157,11 @@ typedef struct sgs_klocal_states sgs_klocal_states;       /* host snapshot of a 
 #define SGS_KLOCAL_KEY_WORDS 32
 /* (m, count) pairs in the order generate_Sright_all / generate_Sright_periodic print them; returns their number */
 int sgs_klocal_sright_log(const sgs_klocal *k, int *pairs, int cap);
+/* the i-th right environment of level m (std::get<0>(Sright_all.at(m)), cpp/state.cpp:218-238; printed by
+ * klocal_sparse -v 1, cpp/klocal_sparse.cpp:28-37): signed canonical generators on [begin, end); rows = rank x W */
+int sgs_klocal_sright_group(sgs_klocal *k, int m, int i, int *rank, int *begin, int *end, uint64_t *rows, int8_t *signs);
+/* State::get_valid_Ps(valid_range()) (cpp/state.cpp:293-309): file indices of the terms still valid for the state */
+int sgs_klocal_state_valid_terms(const sgs_klocal *k, const sgs_klocal_states *s, int i, int *terms, int cap, int *count);
 /* list(state_dict.values()) of the current site, in key order */
 int sgs_klocal_get_states(sgs_klocal *k, sgs_klocal_states **out);
 int sgs_klocal_states_count(const sgs_klocal_states *s);

@@ -77,6 +77,8 @@ SYMBOLS = {
     'sgs_sparse_plan_free': (None, [C.c_void_p]),
     'sgs_klocal_search': (C.c_int, [C.c_void_p, C.POINTER(Opts), C.POINTER(Result)]),
     'sgs_klocal_sright_log': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int]),
+    'sgs_klocal_sright_group': (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_uint64), C.POINTER(C.c_int8)]),
+    'sgs_klocal_state_valid_terms': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     'sgs_klocal_get_states': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     'sgs_klocal_states_count': (C.c_int, [C.c_void_p]),
     'sgs_klocal_states_free': (None, [C.c_void_p]),

@@ -222,6 +222,14 @@ struct sgs_klocal_states { KlocalStates *S; };
 
 int sgs_klocal_sright_log(const sgs_klocal *k, int *pairs, int cap) { return k ? klocal_sright_log(*k->M, pairs, pairs ? cap : 0) : 0; }
 
+int sgs_klocal_sright_group(sgs_klocal *k, int m, int i, int *rank, int *begin, int *end, uint64_t *rows, int8_t *signs)
+{
+    SGS_GUARD_BEGIN
+    if (!k) return fail(SGS_ERR_ARG, "null handle");
+    return done(klocal_sright_group(*k->M, m, i, rank, begin, end, rows, signs));
+    SGS_GUARD_END
+}
+
 int sgs_klocal_get_states(sgs_klocal *k, sgs_klocal_states **out)
 {
     SGS_GUARD_BEGIN
@@ -278,6 +286,14 @@ int sgs_klocal_state_key(const sgs_klocal *k, const sgs_klocal_states *s, int i,
     SGS_GUARD_BEGIN
     if (!k || !s || !key || !nwords) return fail(SGS_ERR_ARG, "null argument");
     return done(klocal_state_key(*k->M, s->S, i, key, SGS_KLOCAL_KEY_WORDS, nwords));
+    SGS_GUARD_END
+}
+
+int sgs_klocal_state_valid_terms(const sgs_klocal *k, const sgs_klocal_states *s, int i, int *terms, int cap, int *count)
+{
+    SGS_GUARD_BEGIN
+    if (!k || !s || !count || (cap > 0 && !terms)) return fail(SGS_ERR_ARG, "null argument");
+    return done(klocal_state_valid_terms(*k->M, s->S, i, terms, cap, count));
     SGS_GUARD_END
 }
 

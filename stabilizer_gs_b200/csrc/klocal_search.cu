@@ -911,6 +911,56 @@ Status klocal_state_history(KlocalMachine &M, const KlocalStates *s, int i, int 
     return Status();
 }
 
+// relative rows (origin o: bit 2j = z, 2j+1 = x of site o + j) -> absolute Wout-word rows
+static void rel_to_abs(uint64_t rel, int o, int n, uint64_t *row, int Wout)
+{
+    for (int w = 0; w < Wout; w++) row[w] = 0;
+    for (int j = 0; j < 32; j++) {
+        const uint64_t v = (rel >> (2 * j)) & 3;
+        const int site = o + j;
+        if (v && site >= 0 && site < n) row[(2 * site) >> 6] |= v << ((2 * site) & 63);
+    }
+}
+
+// the i-th right environment of level m (std::get<0>(Sright_all.at(m)), cpp/state.cpp:218-238): a signed canonical
+// group on the k sites ending at m
+Status klocal_sright_group(KlocalMachine &M, int m, int i, int *rank, int *begin, int *end, uint64_t *rows, int8_t *signs)
+{
+    KlocalMachine::Impl &K = *M.impl();
+    const std::vector<DpGroup> *G = nullptr;
+    SGS_TRY(K.host_groups(m, &G));
+    if (i < 0 || i >= (int)G->size()) return Status::fail(SGS_ERR_ARG, "right-environment index out of range");
+    const DpGroup &g = (*G)[i];
+    const int Wout = (2 * K.n + 63) / 64;
+    if (rank) *rank = g.r;
+    if (begin) *begin = std::max(m - K.k + 1, 0);
+    if (end) *end = m + 1;                          // (the level-n group overhangs the chain by one site, cpp/state.cpp:219)
+    for (int a = 0; a < g.r; a++) {
+        if (rows) rel_to_abs(g.g[a], m - K.k + 1, K.n, rows + (size_t)a * Wout, Wout);
+        if (signs) signs[a] = g.neg[a] ? -1 : 1;
+    }
+    return Status();
+}
+
+// State::get_valid_Ps(valid_range()) (cpp/state.cpp:293-309): file indices of the still-valid terms whose last site
+// lies in [m + 1, min(m + k - 1, n)), bucket by bucket
+Status klocal_state_valid_terms(const KlocalMachine &M, const KlocalStates *s, int i, int *terms, int cap, int *count)
+{
+    if (!s || i < 0 || i >= (int)s->hs.size()) return Status::fail(SGS_ERR_ARG, "state index out of range");
+    const KlocalMachine::Impl &K = *const_cast<KlocalMachine &>(M).impl();
+    const int m = s->m;
+    const int klo = K.boff[std::min(m + 1, K.n + 1)] - K.boff[m];
+    const int khi = K.boff[std::min(std::max(m + K.k - 1, m + 1), K.n)] - K.boff[m];
+    int c = 0;
+    for (int bb = klo; bb < khi; bb++) {
+        if (!((s->hs[i].s.valid[bb >> 6] >> (bb & 63)) & 1)) continue;
+        if (c >= cap) return Status::fail(SGS_ERR_ARG, "term buffer too small");
+        terms[c++] = K.H.order[K.boff[m] + bb];
+    }
+    *count = c;
+    return Status();
+}
+
 int klocal_sright_log(const KlocalMachine &M, int *pairs, int cap)
 {
     const KlocalMachine::Impl &K = *const_cast<KlocalMachine &>(M).impl();

@@ -45,6 +45,8 @@ Status klocal_states_shift(KlocalMachine &M, KlocalStates *s, int add, int clear
 Status klocal_set_states(KlocalMachine &M, const KlocalStates *s, int m);
 Status klocal_state_history(KlocalMachine &M, const KlocalStates *s, int i, int entry, int *terms, int8_t *signs, int cap, int *count);
 int klocal_sright_log(const KlocalMachine &M, int *pairs, int cap);
+Status klocal_sright_group(KlocalMachine &M, int m, int i, int *rank, int *begin, int *end, uint64_t *rows, int8_t *signs);
+Status klocal_state_valid_terms(const KlocalMachine &M, const KlocalStates *s, int i, int *terms, int cap, int *count);
 
 Status klocal_search(const Hamiltonian &H, const sgs_opts &opts, sgs_result *out);
 Status klocal_periodic(const Hamiltonian &H, int cmax, int c, const sgs_opts &opts, sgs_periodic_result *out);
