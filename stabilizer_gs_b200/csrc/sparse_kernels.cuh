@@ -287,7 +287,7 @@ SGS_D int residue_leader(const uint64_t *R, int i, const uint32_t *tab, int slot
 template <int W>
 __global__ void __launch_bounds__(128)
 k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *__restrict__ out,
-          unsigned int *out_count, unsigned out_cap, int shard, int nshards, int smem_per_warp, int own_only)
+          unsigned int *out_count, unsigned out_cap, int shard, int nshards, int smem_per_warp, int own_only, unsigned int *fetch)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -320,7 +320,15 @@ k_general(SparseDev D, const uint16_t *__restrict__ in, unsigned nin, uint16_t *
     unsigned slowNodes = 0;
     __syncwarp();
 
-    for (unsigned node = gw; node < nin; node += nw) {
+    // fetch != null (parent-sharded level: a shard evaluates one node in nshards, at ~15 us each): nodes are handed out
+    // one by one, so that no warp is left with several owned nodes while others have none
+    for (unsigned node = gw;; node += nw) {
+        if (fetch) {
+            unsigned f = 0;
+            if (lane == 0) f = atomicAdd(fetch, 1u);
+            node = __shfl_sync(0xffffffffu, f, 0);
+        }
+        if (node >= nin) break;
         if (*(volatile unsigned int *)&D.stats->error) break;      // a limit was hit somewhere: the search is void, stop early
         const uint16_t *rec = in + (size_t)node * D.S;
         const int m = rec[0];
@@ -1496,23 +1504,65 @@ SGS_D bool rec_better(const BestRec *recs, int a, int b)     // is record a stri
     return a != b && tuple_before(recs[a].g, recs[a].m, recs[b].g, recs[b].m);
 }
 
-__global__ void __launch_bounds__(1024) k_reduce_best(const BestRec *__restrict__ recs, int nrecs, BestRec *__restrict__ out)
+// what one shard contributes to the combination: its best record and the counters that add up over shards.
+// One ncclAllGather of these records is the search's only collective.
+struct ShardRec {
+    BestRec best;
+    unsigned long long sums[kStatsSummed];
+};
+
+// block argmin over records: (E, index) pairs travel through shared memory, the records themselves are only touched
+// again on exact ties (tuple order).  Returns the winner's index in every thread (-1: no valid record).
+SGS_D int block_argmin(const BestRec *__restrict__ recs, int nrecs, int stride_bytes, double *sE, int *sI)
 {
-    __shared__ int sbest[1024];
     const int tid = threadIdx.x;
+    auto rec = [&](int i) { return (const BestRec *)((const char *)recs + (size_t)i * stride_bytes); };
+    auto better = [&](double ea, int a, double eb, int b) {       // is (ea, a) strictly better than (eb, b)?
+        if (a < 0) return false;
+        if (b < 0) return true;
+        if (ea != eb) return ea < eb;
+        return a != b && tuple_before(rec(a)->g, rec(a)->m, rec(b)->g, rec(b)->m);
+    };
+    double e = 0.0;
     int best = -1;
-    for (int i = tid; i < nrecs; i += blockDim.x)
-        if (recs[i].valid && rec_better(recs, i, best)) best = i;
-    sbest[tid] = best;
+    // (the records are 144 bytes apart: eight independent loads in flight per thread instead of a chain of misses)
+    for (int i0 = tid; i0 < nrecs; i0 += 8 * blockDim.x) {
+        double ev[8];
+        int vv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = i0 + k * blockDim.x;
+            vv[k] = i < nrecs ? rec(i)->valid : 0;
+            ev[k] = i < nrecs ? rec(i)->E : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (vv[k] && better(ev[k], i0 + k * (int)blockDim.x, e, best)) { e = ev[k]; best = i0 + k * blockDim.x; }
+    }
+    sE[tid] = e; sI[tid] = best;
     __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if (tid < s && rec_better(recs, sbest[tid + s], sbest[tid])) sbest[tid] = sbest[tid + s];
+    for (int s2 = blockDim.x / 2; s2 > 0; s2 >>= 1) {
+        if (tid < s2 && better(sE[tid + s2], sI[tid + s2], sE[tid], sI[tid])) { sE[tid] = sE[tid + s2]; sI[tid] = sI[tid + s2]; }
         __syncthreads();
     }
-    if (tid == 0) {
-        if (sbest[0] >= 0) *out = recs[sbest[0]];
-        else { out->valid = 0; out->m = 0; out->E = 0.0; }
-    }
+    return sI[0];
+}
+
+// per-shard reduction: best of the per-warp records + this shard's counters -> one ShardRec
+__global__ void __launch_bounds__(1024) k_reduce_pack(const BestRec *__restrict__ recs, int nrecs, const SparseStats *__restrict__ stats,
+                                                      ShardRec *__restrict__ out)
+{
+    __shared__ double sE[1024];
+    __shared__ int sI[1024];
+    const int w = block_argmin(recs, nrecs, (int)sizeof(BestRec), sE, sI);
+    const int tid = threadIdx.x;
+    if (w >= 0) {
+        const uint32_t *src = (const uint32_t *)(recs + w);
+        uint32_t *dst = (uint32_t *)&out->best;
+        for (int i = tid; i < (int)(sizeof(BestRec) / 4); i += blockDim.x) dst[i] = src[i];
+    } else if (tid == 0) { out->best.valid = 0; out->best.m = 0; out->best.E = 0.0; }
+    const unsigned long long *ss = (const unsigned long long *)stats;
+    for (int i = tid; i < kStatsSummed; i += blockDim.x) out->sums[i] = ss[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1530,9 +1580,11 @@ struct FinalOut {
     int8_t signs[kMaxG];
 };
 
+// Phase 0 combines the shards: argmin over the nshard records (minimum energy, ties by tuple order — the same winner
+// on every rank), counters summed into D.stats; the winner is left in *gbest for the host.
 template <int W>
 __global__ void __launch_bounds__(256)
-k_finalize(SparseDev D, const BestRec *__restrict__ best, const int *__restrict__ order, FinalOut *out,
+k_finalize(SparseDev D, const ShardRec *__restrict__ shards, int nshard, BestRec *gbest, const int *__restrict__ order, FinalOut *out,
            int8_t *__restrict__ term_signs, uint64_t *__restrict__ memX, double *__restrict__ memA,
            int *__restrict__ memT, int *memCount)
 {
@@ -1540,7 +1592,26 @@ k_finalize(SparseDev D, const BestRec *__restrict__ best, const int *__restrict_
     __shared__ int qC[kMaxG], pivC[kMaxG];
     __shared__ double redE[256];
     __shared__ unsigned long long redI[256];
-    const int tid = threadIdx.x, m = best->m, T = D.T;
+    const int tid = threadIdx.x, T = D.T;
+    {
+        __shared__ int sI[256];
+        const int w = block_argmin(&shards[0].best, nshard, (int)sizeof(ShardRec), redE, sI);
+        if (w >= 0) {
+            const uint32_t *src = (const uint32_t *)&shards[w].best;
+            uint32_t *dst = (uint32_t *)gbest;
+            for (int i = tid; i < (int)(sizeof(BestRec) / 4); i += blockDim.x) dst[i] = src[i];
+        } else if (tid == 0) { gbest->valid = 0; gbest->m = 0; gbest->E = 0.0; }
+        unsigned long long *ss = (unsigned long long *)D.stats;
+        for (int i = tid; i < kStatsSummed; i += blockDim.x) {
+            unsigned long long a = 0;
+            for (int r = 0; r < nshard; r++) a += shards[r].sums[i];
+            ss[i] = a;
+        }
+        __syncthreads();
+        if (w < 0) { if (tid == 0) { out->error = 0; out->m = 0; out->energy = 0.0; *memCount = 0; } return; }
+    }
+    const BestRec *best = gbest;
+    const int m = best->m;
 
     if (tid == 0) {
         out->error = 0;

@@ -36,9 +36,9 @@ struct DevCtx {
     uint64_t *rows = nullptr, *adj = nullptr;
     double *wgt = nullptr, *wabs = nullptr;
     int *order = nullptr;
-    BestRec *wbest = nullptr, *gbest = nullptr, *allbest = nullptr;
+    BestRec *wbest = nullptr, *gbest = nullptr;
+    ShardRec *shardrec = nullptr, *allrec = nullptr;   // this shard's contribution; every shard's (after the all-gather)
     SparseStats *stats = nullptr;
-    unsigned long long *hist_sum = nullptr;
     uint16_t *qA = nullptr, *qB = nullptr, *slow = nullptr, *work = nullptr;
     unsigned int *counters = nullptr;   // [0] next-level count, [1] item counter, [2] slow count, [8..15] root class counts, [16..23] cursors
     unsigned int *perm = nullptr;       // [qcap] heavy-first order of the subtree roots
@@ -100,7 +100,7 @@ struct SparsePlan::Impl {
     template <int W_> Status search_local(DevCtx &c);
     template <int W_> Status launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
                                         unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm);
-    template <int W_> Status finalize(DevCtx &c, const BestRec *host_best, sgs_result *out);
+    template <int W_> Status finalize(DevCtx &c, const ShardRec *src, int nrec, sgs_result *out, SparseStats *tot, BestRec *best);
     template <int W_> Status run_replay(sgs_result *out);
     void fill_stats(const SparseStats &tot, sgs_result *out);
     void fill_empty(const SparseStats &tot, sgs_result *out);
@@ -258,8 +258,8 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
     want(&c.wabs, Tn);
     want(&c.order, Tn);
     want(&c.wbest, c.nwbest);
-    want(&c.allbest, std::max(nshards, 1));
-    want(&c.hist_sum, kStatsSummed);
+    want(&c.shardrec, 1);
+    want(&c.allrec, std::max(nshards, 1));
     want(&c.qA, (size_t)qcap * S);
     want(&c.qB, (size_t)qcap * S);
     want(&c.slow, (size_t)slow_cap * S);
@@ -380,7 +380,7 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
                               int shard, int nsh) {
         unsigned grid = std::min<unsigned>((nin + gen_wpb - 1) / gen_wpb, gen_maxgrid);
         if (grid == 0) return;
-        k_general<W_><<<grid, gen_wpb * 32, gen_pw * gen_wpb, st>>>(D, in, nin, out, out_count, out_cap, shard, nsh, (int)gen_pw, 0);
+        k_general<W_><<<grid, gen_wpb * 32, gen_pw * gen_wpb, st>>>(D, in, nin, out, out_count, out_cap, shard, nsh, (int)gen_pw, 0, nullptr);
         c.launches++;
     };
 
@@ -504,11 +504,11 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         SGS_CUDA_TRY(cudaGetLastError());
     }
 
-    k_reduce_best<<<1, 1024, 0, st>>>(c.wbest, c.nwbest, c.gbest);
+    k_reduce_pack<<<1, 1024, 0, st>>>(c.wbest, c.nwbest, c.stats, c.shardrec);
     c.launches++;
     SGS_CUDA_TRY(cudaGetLastError());
     SGS_CUDA_TRY(cudaEventRecord(c.ev1, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(&c.hbest, c.gbest, sizeof(BestRec), cudaMemcpyDeviceToHost, st));
+    SGS_CUDA_TRY(cudaMemcpyAsync(&c.hbest, &c.shardrec->best, sizeof(BestRec), cudaMemcpyDeviceToHost, st));
     SGS_CUDA_TRY(cudaMemcpyAsync(&c.hstats, c.stats, sizeof(SparseStats), cudaMemcpyDeviceToHost, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
     SGS_CUDA_TRY(cudaEventElapsedTime(&c.ms_device, c.ev0, c.ev1));
@@ -516,21 +516,26 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
     return Status();
 }
 
+// combine the shard records (argmin + summed counters) and turn the winner into the printed result: one launch, one
+// copy of the result span (FinalOut, term signs, statistics, best record)
 template <int W_>
-Status SparsePlan::Impl::finalize(DevCtx &c, const BestRec *host_best, sgs_result *out)
+Status SparsePlan::Impl::finalize(DevCtx &c, const ShardRec *src, int nrec, sgs_result *out, SparseStats *tot, BestRec *best)
 {
     SGS_CUDA_TRY(cudaSetDevice(c.device));
     const SparseDev D = dev_view(c);
     cudaStream_t st = c.stream;
-    if (host_best) SGS_CUDA_TRY(cudaMemcpyAsync(c.gbest, host_best, sizeof(BestRec), cudaMemcpyHostToDevice, st));
-    k_finalize<W_><<<1, 256, 0, st>>>(D, c.gbest, c.order, c.fin, c.term_signs, c.memX, c.memA, c.memT, c.memCount);
+    k_finalize<W_><<<1, 256, 0, st>>>(D, src, nrec, c.gbest, c.order, c.fin, c.term_signs, c.memX, c.memA, c.memT, c.memCount);
     c.launches++;
     SGS_CUDA_TRY(cudaGetLastError());
-    FinalOut fo;
-    std::vector<int8_t> ts(std::max(T, 1));
-    SGS_CUDA_TRY(cudaMemcpyAsync(&fo, c.fin, sizeof(FinalOut), cudaMemcpyDeviceToHost, st));
-    SGS_CUDA_TRY(cudaMemcpyAsync(ts.data(), c.term_signs, std::max(T, 1), cudaMemcpyDeviceToHost, st));
+    const size_t span = (size_t)((const char *)(c.counters + 4) - (const char *)c.fin);
+    std::vector<char> hostspan(span);
+    SGS_CUDA_TRY(cudaMemcpyAsync(hostspan.data(), c.fin, span, cudaMemcpyDeviceToHost, st));
     SGS_CUDA_TRY(cudaStreamSynchronize(st));
+    FinalOut fo;
+    memcpy(&fo, hostspan.data(), sizeof(FinalOut));
+    memcpy(tot, hostspan.data() + ((const char *)c.stats - (const char *)c.fin), sizeof(SparseStats));
+    memcpy(best, hostspan.data() + ((const char *)c.gbest - (const char *)c.fin), sizeof(BestRec));
+    if (!best->valid) return Status();                 // no candidate anywhere: the caller decides what that means
     if (fo.error) return Status::fail(SGS_ERR_LIMIT, "ground-state group rank exceeds the sign-table limit and its terms are linearly dependent");
     const int Wout = (2 * n + 63) / 64;
     out->energy = fo.energy;
@@ -542,7 +547,7 @@ Status SparsePlan::Impl::finalize(DevCtx &c, const BestRec *host_best, sgs_resul
         for (int k = 0; k < Wout; k++) out->gens[(size_t)i * Wout + k] = fo.rows[i * W_ + k];
         out->gen_signs[i] = fo.signs[i];
     }
-    memcpy(out->term_signs, ts.data(), T);
+    memcpy(out->term_signs, hostspan.data() + ((const char *)c.term_signs - (const char *)c.fin), T);
     return Status();
 }
 
@@ -594,8 +599,9 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
             // the last level is expanded by the owner of each parent only: its children land in the owner's
             // queue and k_dfs walks all of them (no shard filter), so the expansion work shards too
             const int own_only = (nshards > 1 && d == rp.depth - 1) ? 1 : 0;
+            if (own_only) SGS_CUDA_TRY(cudaMemsetAsync(c.counters + 3, 0, sizeof(unsigned), st));
             k_general<W_><<<grid, rp.gen_wpb * 32, rp.gen_pw * rp.gen_wpb, st>>>(D, cur, nin, nxt, c.counters, qcap, c.shard, nshards,
-                                                                                 (int)rp.gen_pw, own_only);
+                                                                                 (int)rp.gen_pw, own_only, own_only ? c.counters + 3 : nullptr);
             c.launches++;
             std::swap(cur, nxt);
         }
@@ -618,31 +624,26 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
             if (!sd.ok()) return sd;
         }
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
-        k_reduce_best<<<1, 1024, 0, st>>>(c.wbest, c.nwbest, c.gbest);
+        k_reduce_pack<<<1, 1024, 0, st>>>(c.wbest, c.nwbest, c.stats, c.shardrec);
         c.launches += 1;
         SGS_CUDA_TRY(cudaGetLastError());
         SGS_CUDA_TRY(cudaEventRecord(c.evA, st));
     }
     if (nccl) {
-        std::vector<void *> sendb, recvb, sumb;
+        // the one collective: every shard's (best record, counters)
+        std::vector<void *> sendb, recvb;
         std::vector<cudaStream_t> sts;
-        for (auto &c : devs) { sendb.push_back(c.gbest); recvb.push_back(c.allbest); sumb.push_back(c.stats); sts.push_back(c.stream); }
-        Status s = nccl->all_gather_bytes(sendb, recvb, sizeof(BestRec), sts);
+        for (auto &c : devs) { sendb.push_back(c.shardrec); recvb.push_back(c.allrec); sts.push_back(c.stream); }
+        Status s = nccl->all_gather_bytes(sendb, recvb, sizeof(ShardRec), sts);
         if (!s.ok()) return s;
-        s = nccl->all_reduce_sum_u64(sumb, kStatsSummed, sts);          // hist[0..kMaxG], slow_nodes and paths[] are contiguous u64
-        if (!s.ok()) return s;
-        for (auto &c : devs) {
-            SGS_CUDA_TRY(cudaSetDevice(c.device));
-            k_reduce_best<<<1, 1024, 0, c.stream>>>(c.allbest, nshards, c.gbest);
-            c.launches++;
-        }
     }
     DevCtx &c0 = devs[0];
     SGS_CUDA_TRY(cudaSetDevice(c0.device));
     SGS_CUDA_TRY(cudaEventRecord(c0.evB, c0.stream));
     {
         const SparseDev D = dev_view(c0);
-        k_finalize<W_><<<1, 256, 0, c0.stream>>>(D, c0.gbest, c0.order, c0.fin, c0.term_signs, c0.memX, c0.memA, c0.memT, c0.memCount);
+        k_finalize<W_><<<1, 256, 0, c0.stream>>>(D, nccl ? c0.allrec : c0.shardrec, nccl ? nshards : 1, c0.gbest, c0.order, c0.fin, c0.term_signs,
+                                                 c0.memX, c0.memA, c0.memT, c0.memCount);
         c0.launches++;
         SGS_CUDA_TRY(cudaGetLastError());
     }
@@ -735,47 +736,30 @@ Status SparsePlan::Impl::run(sgs_result *out)
     }
     for (auto &c : devs) if (!c.status.ok()) return c.status;
 
-    // ---- combine the shards: one (energy, generating tuple) record per shard + the counters ----
+    // ---- combine the shards: ONE collective, an all-gather of every shard's (best record, counters); then the same
+    // deterministic argmin, the summed counters and the finalisation in one kernel on every rank ----
     // (timed with CUDA events on the launching stream and added to the device time: the reported
     //  seconds_device covers expansion + walk + collective + finalisation)
-    cudaSetDevice(devs[0].device);
-    cudaEventRecord(devs[0].ev0, devs[0].stream);
-    BestRec best = devs[0].hbest;
-    SparseStats tot = devs[0].hstats;
+    DevCtx &c0 = devs[0];
+    cudaSetDevice(c0.device);
+    cudaEventRecord(c0.ev0, c0.stream);
     if (nccl) {
-        // NCCL all-gather of the per-shard minima and all-reduce(sum) of the counters over NVLink,
-        // then the same deterministic argmin on every GPU
-        for (auto &c : devs) {
-            cudaSetDevice(c.device);
-            static_assert(offsetof(SparseStats, hist) == 0 && offsetof(SparseStats, error) == sizeof(unsigned long long) * kStatsSummed,
-                          "the summed counters lead SparseStats");
-            cudaMemcpyAsync(c.hist_sum, &c.hstats, sizeof(unsigned long long) * kStatsSummed, cudaMemcpyHostToDevice, c.stream);
-        }
-        std::vector<void *> sendb, recvb, sumb;
+        std::vector<void *> sendb, recvb;
         std::vector<cudaStream_t> sts;
-        for (auto &c : devs) { sendb.push_back(c.gbest); recvb.push_back(c.allbest); sumb.push_back(c.hist_sum); sts.push_back(c.stream); }
-        Status s = nccl->all_gather_bytes(sendb, recvb, sizeof(BestRec), sts);
-        if (!s.ok()) return s;
-        s = nccl->all_reduce_sum_u64(sumb, kStatsSummed, sts);
-        if (!s.ok()) return s;
-        for (auto &c : devs) {
-            cudaSetDevice(c.device);
-            k_reduce_best<<<1, 1024, 0, c.stream>>>(c.allbest, nshards, c.gbest);
-            c.launches++;
-        }
-        DevCtx &c0 = devs[0];
-        cudaSetDevice(c0.device);
-        unsigned long long hsum[kStatsSummed];
-        SGS_CUDA_TRY(cudaMemcpyAsync(&best, c0.gbest, sizeof(BestRec), cudaMemcpyDeviceToHost, c0.stream));
-        SGS_CUDA_TRY(cudaMemcpyAsync(hsum, c0.hist_sum, sizeof(hsum), cudaMemcpyDeviceToHost, c0.stream));
-        for (auto &c : devs) { cudaSetDevice(c.device); SGS_CUDA_TRY(cudaStreamSynchronize(c.stream)); }
-        memcpy(&tot, hsum, sizeof(hsum));
-    } else {
-        for (size_t i = 1; i < devs.size(); i++) {      // only reachable with world > 1 && nccl_id == NULL per process: no merge
-            const BestRec &b = devs[i].hbest;
-            (void)b;
-        }
+        for (auto &c : devs) { sendb.push_back(c.shardrec); recvb.push_back(c.allrec); sts.push_back(c.stream); }
+        Status sg = nccl->all_gather_bytes(sendb, recvb, sizeof(ShardRec), sts);
+        if (!sg.ok()) return sg;
     }
+    BestRec best{};
+    SparseStats tot{};
+    Status s;
+    const ShardRec *src = nccl ? c0.allrec : c0.shardrec;
+    const int nrec = nccl ? nshards : 1;
+    if (W == 1) s = finalize<1>(c0, src, nrec, out, &tot, &best);
+    else if (W == 2) s = finalize<2>(c0, src, nrec, out, &tot, &best);
+    else s = finalize<4>(c0, src, nrec, out, &tot, &best);
+    if (!s.ok()) return s;
+    for (auto &c : devs) { cudaSetDevice(c.device); SGS_CUDA_TRY(cudaStreamSynchronize(c.stream)); }
     if (!best.valid) {
         if (nshards > 1 && !nccl) {          // a shard without communicator that owns no candidate: empty result
             fill_empty(tot, out);
@@ -784,14 +768,8 @@ Status SparsePlan::Impl::run(sgs_result *out)
         }
         return Status::fail(SGS_ERR_CUDA, "sparse search produced no candidate");
     }
-
-    DevCtx &c0 = devs[0];
-    Status s;
-    if (W == 1) s = finalize<1>(c0, &best, out);
-    else if (W == 2) s = finalize<2>(c0, &best, out);
-    else s = finalize<4>(c0, &best, out);
-    if (!s.ok()) return s;
     float ms_merge = 0.f;
+    cudaSetDevice(c0.device);
     cudaEventRecord(c0.ev1, c0.stream);
     cudaEventSynchronize(c0.ev1);
     cudaEventElapsedTime(&ms_merge, c0.ev0, c0.ev1);
