@@ -7,6 +7,7 @@ for round in 1 2; do
     cp "$lib" stabilizer_gs_b200/libsgs.so
     echo "$lib c4 : $(python scripts/run_sparse_once.py 24 300 0 5 | tail -1 | sed 's/.*cand=/cand=/')"
     echo "$lib w2 : $(python scripts/run_sparse_once.py 40 500 0 3 | tail -1 | sed 's/.*cand=/cand=/')"
+    echo "$lib w2b: $(python scripts/run_sparse_once.py 40 700 0 2 | tail -1 | sed 's/.*cand=/cand=/')"
   done
 done
 cp /tmp/libsgs_saved.so stabilizer_gs_b200/libsgs.so

@@ -69,6 +69,8 @@ def main():
         val = {h: (row[i], units[i]) for i, h in enumerate(hdr)}
 
         def num(name):
+            if name not in val:
+                return float('nan')
             v, u = val[name]
             x = float(v.replace(',', ''))
             mult = {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'byte': 1.0, 'us': 1e-3, 'ms': 1.0, 'ns': 1e-6, 's': 1e3,
@@ -99,6 +101,7 @@ def main():
             issue_active_pct_ncu=num('smsp__issue_active.avg.pct_of_peak_sustained_active'),
             dram_bytes=num('dram__bytes_read.sum') + num('dram__bytes_write.sum'),
             registers=num('launch__registers_per_thread'))
+        counters[label] = {k: (None if isinstance(v, float) and v != v else v) for k, v in counters[label].items()}
         print(label, json.dumps(counters[label]))
     with open(counters_path, 'w') as f:
         json.dump(counters, f, indent=1)
