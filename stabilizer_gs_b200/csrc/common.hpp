@@ -19,6 +19,7 @@ struct Status {
 
 }  // namespace sgs
 
+#define SGS_TRY(expr) do { ::sgs::Status s__ = (expr); if (!s__.ok()) return s__; } while (0)
 #define SGS_CUDA_TRY(expr)                                                                                \
     do {                                                                                                  \
         cudaError_t e__ = (expr);                                                                         \

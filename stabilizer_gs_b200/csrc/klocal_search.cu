@@ -178,7 +178,6 @@ static Status ctl_error(int err, const char *what)
     return Status::fail(err >= 4 ? SGS_ERR_OVERFLOW : SGS_ERR_LIMIT, std::string(what) + ": " + why);
 }
 
-#define SGS_TRY(expr) do { Status s__ = (expr); if (!s__.ok()) return s__; } while (0)
 
 Status KlocalMachine::Impl::init()
 {

@@ -1011,7 +1011,6 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
     //    never become generators below this frame.  Own rows: entries lane and lane + 32; step u broadcasts the
     //    (already reduced) copy of candidate u and clears its lowest set bit from the later candidates and from
     //    the lower rows.
-    const bool two = n > 32;
     uint64_t e0[W], e1[W];
 #pragma unroll
     for (int k = 0; k < W; k++) {
@@ -1171,6 +1170,7 @@ __device__ __noinline__ int level_b_pick(double bw, uint64_t bm, const uint16_t 
 #define SGS_DFS_MINB1 8
 #endif
 constexpr int kDfsWpb = SGS_DFS_WPB;
+enum { kDfsOwnSelf = 1, kDfsExpand = 2 };
 // one-word rows: 64 registers (8 blocks of 4 warps per SM) measured 2 % faster than 80; multi-word rows spill there (-13 %)
 template <int W> constexpr int dfs_min_blocks() { return W == 1 ? SGS_DFS_MINB1 : SGS_DFS_MINB; }
 
@@ -1178,8 +1178,12 @@ template <int W, bool SPLIT, bool PRUNE>
 __global__ void __launch_bounds__(32 * kDfsWpb, dfs_min_blocks<W>())
 k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned int *item_counter,
       int shard, int nshards, int cap, int smem_per_warp, const unsigned int *nitems_dev, const unsigned int *__restrict__ perm,
-      uint16_t *retry_out_, unsigned int *retry_count, unsigned retry_cap, const unsigned int *valid_end)
+      uint16_t *retry_out_, unsigned int *retry_count, unsigned retry_cap, const unsigned int *valid_end, int mode)
 {
+    // mode bit 0 (kDfsOwnSelf): with several shards a root belongs to the shard of its OWN tuple (expansion launch);
+    // mode bit 1 (kDfsExpand): expansion launch — a root is counted and evaluated, its valid children are written to
+    // retry_out as the roots of the walk; nothing is walked here.  This is the last level of the top-of-tree expansion
+    // done incrementally (one alive list, one duplicate check per parent) instead of from scratch per parent by k_general.
     uint16_t *const retry_out = SPLIT ? retry_out_ : nullptr;      // single-shard build: the hand-off code is compiled out
     // retry_out != null: a root whose residues cannot be certified (a commuting dependency: its subtree needs
     // the warp-cooperative level A, hundreds of instructions per candidate) is not walked here; its children
@@ -1293,7 +1297,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         // a subtree root belongs to the shard of its PARENT (hash of the tuple without its last generator): the same
         // partition whether the last expansion level was replicated (first, adaptive run of a plan) or expanded by
         // the parent's owner only (recorded launch sequence)
-        if (nshards > 1 && (int)(tuple_hash(rec + 2, m0 > 0 ? m0 - 1 : 0) % (unsigned)nshards) != shard) continue;
+        if (nshards > 1 && (int)(tuple_hash(rec + 2, (mode & kDfsOwnSelf) ? m0 : (m0 > 0 ? m0 - 1 : 0)) % (unsigned)nshards) != shard) continue;
         __syncwarp();
         for (int i = lane; i < m0; i += 32) path[i] = rec[2 + i];
         __syncwarp();
@@ -1377,14 +1381,14 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         if (q0 >= a) { try_best(E0, m0); continue; }                      // no extension: a leaf
         // (a certified root whose clique walk alone would outlast the rest of a short kernel is split the same way
         //  when a next round exists: level_b answers 2)
-        if (a <= 64 && m0 + (a - q0) < kMaxG && run_level_b(0, a, q0, m0, E0, retry_out ? D.split_cliques : 0.f) == 1) continue;
+        if (!(mode & kDfsExpand) && a <= 64 && m0 + (a - q0) < kMaxG && run_level_b(0, a, q0, m0, E0, retry_out ? D.split_cliques : 0.f) == 1) continue;
         tfail = true;
         if (has_duplicate<W>(R, a, lane)) {
             try_best(E0, m0);
             push_slow(D, path, m0, flags | kFlagExpandOnly, lane);
             continue;
         }
-        if (retry_out && a - q0 >= 4 && m0 + 1 < kMaxG) {
+        if (retry_out && (a - q0 >= 4 || (mode & kDfsExpand)) && m0 + 1 < kMaxG) {
             // every entry from q0 on is a valid child (residues pairwise distinct); each counts itself as a root
             unsigned slot = 0;
             if (lane == 0) slot = atomicAdd(retry_count, (unsigned)(a - q0));

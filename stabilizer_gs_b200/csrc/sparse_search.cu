@@ -80,6 +80,7 @@ struct SparsePlan::Impl {
     unsigned qcap = 0, slow_cap = 0, chunk = 0;
     unsigned retry_cap = 1u << 20;      // roots handed to the next k_dfs round (multi-shard runs); SGS_RETRY_CAP for tests
     int dfs_cap = 0;
+    bool no_dfs_expand = false;         // the expansion-mode launch overflowed its queue once: use k_general for every level
     std::vector<DevCtx> devs;
     std::shared_ptr<NcclWorld> nccl;
     // Replay: the launch sequence of a first (adaptive, host-synchronised) run that needed no work from
@@ -92,6 +93,11 @@ struct SparsePlan::Impl {
         int dfs_cap = 0, dfs_wpb = 8, gen_wpb = 4;
         size_t dfs_pw = 0, gen_pw = 0;
         unsigned dfs_grid = 0, gen_maxgrid = 0;
+        // last expansion level done by the walk kernel in expansion mode (k_dfs, kDfsExpand)
+        bool dfs_expand = false;
+        int exp_cap = 0, exp_wpb = 4;
+        size_t exp_pw = 0;
+        unsigned exp_grid = 0;
     } rp;
 
     ~Impl();
@@ -99,7 +105,9 @@ struct SparsePlan::Impl {
     Status init_device(DevCtx &c);
     template <int W_> Status search_local(DevCtx &c);
     template <int W_> Status launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
-                                        unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm);
+                                        unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm, const unsigned *valid0 = nullptr);
+    template <int W_> Status launch_expand(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
+                                           unsigned count, uint16_t *out);
     template <int W_> Status finalize(DevCtx &c, const ShardRec *src, int nrec, sgs_result *out, SparseStats *tot, BestRec *best);
     template <int W_> Status run_replay(sgs_result *out);
     void fill_stats(const SparseStats &tot, sgs_result *out);
@@ -316,7 +324,7 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
 // children to a second round, and those of the second round to a third (counts stay on the device).
 template <int W_>
 Status SparsePlan::Impl::launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
-                                    unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm)
+                                    unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm, const unsigned *valid0)
 {
     cudaStream_t st = c.stream;
     // (measured on config 4: the hand-off rounds cost 6 % at 2 shards, are neutral at 4 and cut the walk by a quarter at 8)
@@ -331,21 +339,46 @@ Status SparsePlan::Impl::launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid
 #define SGS_DFS(SPL, PRN, ...) k_dfs<W_, SPL, PRN><<<grid, wpb * 32, pw * wpb, st>>>(__VA_ARGS__)
     if (split) {
         if (prune) {
-            SGS_DFS(true, true, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc, retry_cap, nullptr);
-            SGS_DFS(true, true, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap, rc + 1);
-            SGS_DFS(false, true, D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3);
+            SGS_DFS(true, true, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc, retry_cap, valid0, 0);
+            SGS_DFS(true, true, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap, rc + 1, 0);
+            SGS_DFS(false, true, D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3, 0);
         } else {
-            SGS_DFS(true, false, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc, retry_cap, nullptr);
-            SGS_DFS(true, false, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap, rc + 1);
-            SGS_DFS(false, false, D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3);
+            SGS_DFS(true, false, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc, retry_cap, valid0, 0);
+            SGS_DFS(true, false, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap, rc + 1, 0);
+            SGS_DFS(false, false, D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3, 0);
         }
         c.launches += 3;
     } else {
-        if (prune) SGS_DFS(false, true, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, nullptr);
-        else SGS_DFS(false, false, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, nullptr);
+        if (prune) SGS_DFS(false, true, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, valid0, 0);
+        else SGS_DFS(false, false, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, valid0, 0);
         c.launches++;
     }
 #undef SGS_DFS
+    SGS_CUDA_TRY(cudaGetLastError());
+    return Status();
+}
+
+// The last level of the top-of-tree expansion, done by the walk kernel in expansion mode: every parent (a node of the
+// level before the subtree roots) is evaluated and counted, its valid children are written to `out` as the subtree
+// roots.  One alive list and one duplicate check per parent instead of a from-scratch evaluation per parent by
+// k_general (121 -> ~30 us on config 4); with several shards a parent belongs to the shard of its own tuple, so its
+// children land in the owner's queue and the walk needs no filter.  counters[4] = number of roots written,
+// counters[5] = first slot that did not fit (0xffffffff: none), counters[6] = work-item cursor of this launch.
+template <int W_>
+Status SparsePlan::Impl::launch_expand(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
+                                       unsigned count, uint16_t *out)
+{
+    cudaStream_t st = c.stream;
+    SGS_CUDA_TRY(cudaMemsetAsync(c.counters + 4, 0, 3 * sizeof(unsigned), st));
+    SGS_CUDA_TRY(cudaMemsetAsync(c.counters + 5, 0xFF, sizeof(unsigned), st));
+    const int mode = kDfsOwnSelf | kDfsExpand;
+    if (opts.prune)
+        k_dfs<W_, true, true><<<grid, wpb * 32, pw * wpb, st>>>(D, items, count, c.counters + 6, c.shard, nshards, cap, (int)pw, nullptr, nullptr, out,
+                                                                c.counters + 4, qcap, nullptr, mode);
+    else
+        k_dfs<W_, true, false><<<grid, wpb * 32, pw * wpb, st>>>(D, items, count, c.counters + 6, c.shard, nshards, cap, (int)pw, nullptr, nullptr, out,
+                                                                 c.counters + 4, qcap, nullptr, mode);
+    c.launches++;
     SGS_CUDA_TRY(cudaGetLastError());
     return Status();
 }
@@ -395,13 +428,26 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
     double ratio = (double)std::max(T, 1);
     int depth = 0;
     SparseStats hs{};
-    unsigned hcnt[4];
+    unsigned hcnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<unsigned> level_counts{1};
     c.had_slow = false;
+    bool dfs_expand = false;
+    double ratio_pred = 0.0;
     while (count > 0 && depth < dmax) {
         if (opts.expand_depth <= 0) {
             const double est_alive = ratio * std::max(depth, 1) / 2.0;
             if (depth > 0 && count >= min_items && est_alive <= 64.0) break;
+        }
+        // Can the NEXT level be the last one?  Then the walk kernel produces it itself (launch_expand), incrementally.
+        // Clique-like growth: count_{d+1} ~ count_d * ratio_d * d / (2 (d + 1)).
+        // (opt-in, SGS_DFS_EXPAND=1: measured on config 4 it saves 26 us of expansion and costs 50 us of walk — the
+        //  k_general levels stay the default; the mode is kept for instances whose last level is large, and tested)
+        if (!no_dfs_expand && depth >= 1 && getenv("SGS_DFS_EXPAND")) {
+            const double predicted = (double)count * ratio * depth / (2.0 * (depth + 1));
+            const double ratio_next = predicted / (double)count;
+            const bool last = opts.expand_depth > 0 ? depth == dmax - 1
+                                                    : (predicted >= (double)min_items && ratio_next * (depth + 1) / 2.0 <= 64.0);
+            if (last && predicted * 1.5 <= (double)qcap && ratio * depth / 2.0 <= 1500.0) { dfs_expand = true; ratio_pred = std::max(1.0, ratio_next); break; }
         }
         // worst case: the branching cannot grow (ratio is non-increasing for clique-like trees)
         const double bound = (double)count * std::min<double>((double)std::max(T, 1), ratio);
@@ -440,7 +486,10 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         // list arena per warp: a root holds a ~ ratio * depth / 2 alive terms (ratio = measured mean number of
         // children of the last expanded level; binomial spread), the lists of the levels below it halve:
         // 2.2 x (mean + 4 sigma), in steps of 32 entries.  A root that needs more goes to the exact kernel.
-        const double a_est = std::max(8.0, ratio * std::max(depth, 1) / 2.0);
+        // (after an expansion-mode launch the roots sit one level deeper: predicted ratio, depth + 1)
+        const double ratio_w = dfs_expand ? ratio_pred : ratio;
+        const int depth_w = dfs_expand ? depth + 1 : depth;
+        const double a_est = std::max(8.0, ratio_w * std::max(depth_w, 1) / 2.0);
         int cap = (int)(2.2 * (a_est + 4.0 * std::sqrt(a_est)));
         if (const char *v = getenv("SGS_DFS_CAP")) if (atoi(v) > 0) cap = atoi(v);
         cap = std::min(2048, std::max(96, (cap + 31) & ~31));
@@ -448,35 +497,62 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         const size_t dfs_pw = dfs_smem_bytes<W_>(dfs_cap, opts.prune != 0);
         int dfs_wpb = kDfsWpb;
         while (dfs_wpb > 1 && dfs_pw * dfs_wpb > 200 * 1024) dfs_wpb >>= 1;
-        int dfs_occ = 1 << 30;
+        // expansion-mode launch: one list per parent (a ~ ratio * depth / 2 alive terms, 5 sigma of room)
+        int exp_cap = 0, exp_wpb = kDfsWpb;
+        size_t exp_pw = 0;
+        if (dfs_expand) {
+            const double a_par = std::max(8.0, ratio * depth / 2.0);
+            exp_cap = std::min(2048, std::max(96, ((int)(1.25 * (a_par + 5.0 * std::sqrt(a_par))) + 31) & ~31));
+            exp_pw = dfs_smem_bytes<W_>(exp_cap, opts.prune != 0);
+            while (exp_wpb > 1 && exp_pw * exp_wpb > 200 * 1024) exp_wpb >>= 1;
+        }
+        int dfs_occ = 1 << 30, exp_occ = 1 << 30;
         {
             const void *variants[4] = {(const void *)k_dfs<W_, false, false>, (const void *)k_dfs<W_, true, false>,
                                        (const void *)k_dfs<W_, false, true>, (const void *)k_dfs<W_, true, true>};
             for (const void *f : variants) {
                 int o = 1;
-                SGS_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dfs_pw * dfs_wpb)));
+                SGS_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(dfs_pw * dfs_wpb, exp_pw * exp_wpb)));
                 SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, f, dfs_wpb * 32, dfs_pw * dfs_wpb));
                 dfs_occ = std::min(dfs_occ, o);
+                if (dfs_expand) {
+                    SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, f, exp_wpb * 32, exp_pw * exp_wpb));
+                    exp_occ = std::min(exp_occ, o);
+                }
             }
         }
         dfs_occ = std::max(1, dfs_occ);
         const unsigned dfs_maxgrid = (unsigned)std::min<long long>((long long)c.sms * dfs_occ, c.nwbest / dfs_wpb);
-        const unsigned grid = std::min<unsigned>(dfs_maxgrid, (count + dfs_wpb - 1) / dfs_wpb);
+        // (roots of an expansion-mode launch are counted on the device: a full grid)
+        const unsigned grid = dfs_expand ? dfs_maxgrid : std::min<unsigned>(dfs_maxgrid, (count + dfs_wpb - 1) / dfs_wpb);
+        unsigned exp_grid = 0;
+        if (dfs_expand) {
+            const unsigned mg = (unsigned)std::min<long long>((long long)c.sms * std::max(1, exp_occ), c.nwbest / exp_wpb);
+            exp_grid = std::max(1u, std::min<unsigned>(mg, (count + exp_wpb - 1) / exp_wpb));
+        }
         if (&c == &devs[0]) {
             rp.depth = depth; rp.counts = level_counts; rp.dfs_cap = dfs_cap; rp.dfs_wpb = dfs_wpb; rp.dfs_pw = dfs_pw;
             rp.dfs_grid = grid; rp.gen_wpb = gen_wpb; rp.gen_pw = gen_pw; rp.gen_maxgrid = gen_maxgrid;
+            rp.dfs_expand = dfs_expand; rp.exp_cap = exp_cap; rp.exp_wpb = exp_wpb; rp.exp_pw = exp_pw; rp.exp_grid = exp_grid;
+        }
+        if (dfs_expand) {
+            SGS_TRY(launch_expand<W_>(c, D, exp_grid, exp_wpb, exp_pw, exp_cap, cur, count, nxt));
+            std::swap(cur, nxt);
         }
         SGS_CUDA_TRY(cudaEventRecord(c.evh0, st));
         // heavy-first order pays when the walk is short (several shards): the longest subtrees must not start last
         const bool use_perm = nshards > 1 && !getenv("SGS_NOPERM");
+        const unsigned *cnt_dev = dfs_expand ? c.counters + 4 : nullptr;        // roots written by the expansion-mode launch
+        const unsigned cnt_host = dfs_expand ? qcap : count;
         if (use_perm) {
             SGS_CUDA_TRY(cudaMemsetAsync(c.counters + 8, 0, 16 * sizeof(unsigned), st));
-            const unsigned cg = std::min<unsigned>((count + 255) / 256, (unsigned)c.sms * 4);
-            k_class_count<<<cg, 256, 0, st>>>(cur, count, nullptr, S, T, c.counters + 8);
-            k_class_scatter<<<cg, 256, 0, st>>>(cur, count, nullptr, S, T, c.counters + 8, c.counters + 16, c.perm);
+            const unsigned cg = dfs_expand ? (unsigned)c.sms * 4 : std::min<unsigned>((count + 255) / 256, (unsigned)c.sms * 4);
+            k_class_count<<<cg, 256, 0, st>>>(cur, cnt_host, cnt_dev, S, T, c.counters + 8);
+            k_class_scatter<<<cg, 256, 0, st>>>(cur, cnt_host, cnt_dev, S, T, c.counters + 8, c.counters + 16, c.perm);
             c.launches += 2;
         }
-        Status sd = launch_dfs<W_>(c, D, grid, dfs_wpb, dfs_pw, dfs_cap, cur, count, nshards, nullptr, use_perm ? c.perm : nullptr);
+        Status sd = launch_dfs<W_>(c, D, grid, dfs_wpb, dfs_pw, dfs_cap, cur, cnt_host, dfs_expand ? 1 : nshards, cnt_dev,
+                                   use_perm ? c.perm : nullptr, dfs_expand ? c.counters + 5 : nullptr);
         if (!sd.ok()) return sd;
         SGS_CUDA_TRY(cudaGetLastError());
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
@@ -492,8 +568,13 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         SGS_CUDA_TRY(cudaStreamSynchronize(st));
         if (hs.error) return Status::fail(hs.error == kErrOverflow ? SGS_ERR_OVERFLOW : SGS_ERR_LIMIT,
                                           "sparse search: device limit hit (work-stack overflow, or a group whose sign table exceeds the limit)");
+        if (dfs_expand && hcnt[4] > qcap) {
+            // the predicted size of the last level was too low and its queue overflowed: redo the search with k_general levels only
+            no_dfs_expand = true;
+            return search_local<W_>(c);
+        }
         const unsigned sc = hcnt[2];
-        if (D.trace) fprintf(stderr, "sparse shard %d: work stack %u nodes\n", c.shard, sc);
+        if (D.trace) fprintf(stderr, "sparse shard %d: work stack %u nodes%s\n", c.shard, sc, dfs_expand ? " (last level by k_dfs)" : "");
         if (sc == 0) break;
         c.had_slow = true;
         const unsigned take = std::min(sc, chunk);
@@ -598,18 +679,25 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
             SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, sizeof(unsigned), st));
             // the last level is expanded by the owner of each parent only: its children land in the owner's
             // queue and k_dfs walks all of them (no shard filter), so the expansion work shards too
-            const int own_only = (nshards > 1 && d == rp.depth - 1) ? 1 : 0;
+            const int own_only = (nshards > 1 && d == rp.depth - 1 && !rp.dfs_expand) ? 1 : 0;
             if (own_only) SGS_CUDA_TRY(cudaMemsetAsync(c.counters + 3, 0, sizeof(unsigned), st));
             k_general<W_><<<grid, rp.gen_wpb * 32, rp.gen_pw * rp.gen_wpb, st>>>(D, cur, nin, nxt, c.counters, qcap, c.shard, nshards,
                                                                                  (int)rp.gen_pw, own_only, own_only ? c.counters + 3 : nullptr);
             c.launches++;
             std::swap(cur, nxt);
         }
+        // last level by the walk kernel in expansion mode (parents owned by the shard of their own tuple)
+        if (rp.dfs_expand) {
+            SGS_TRY(launch_expand<W_>(c, D, rp.exp_grid, rp.exp_wpb, rp.exp_pw, rp.exp_cap, cur, rp.counts[rp.depth], nxt));
+            std::swap(cur, nxt);
+        }
+        const bool dev_count = rp.dfs_expand || (nshards > 1 && rp.depth > 0);      // queue length only known on the device
+        const unsigned *ndev = rp.dfs_expand ? c.counters + 4 : (dev_count ? c.counters : nullptr);
+        const unsigned nroots = rp.dfs_expand ? qcap : rp.counts[rp.depth];
         const bool use_perm = nshards > 1 && !getenv("SGS_NOPERM");
         if (use_perm) {
-            const unsigned cnt = rp.counts[rp.depth];
-            const unsigned cg = std::max(1u, std::min<unsigned>((cnt + 255) / 256, (unsigned)c.sms * 4));
-            const unsigned *ndev = (nshards > 1 && rp.depth > 0) ? c.counters : nullptr;
+            const unsigned cnt = nroots;
+            const unsigned cg = rp.dfs_expand ? (unsigned)c.sms * 4 : std::max(1u, std::min<unsigned>((cnt + 255) / 256, (unsigned)c.sms * 4));
             SGS_CUDA_TRY(cudaMemsetAsync(c.counters + 8, 0, 16 * sizeof(unsigned), st));
             k_class_count<<<cg, 256, 0, st>>>(cur, cnt, ndev, S, T, c.counters + 8);
             k_class_scatter<<<cg, 256, 0, st>>>(cur, cnt, ndev, S, T, c.counters + 8, c.counters + 16, c.perm);
@@ -618,9 +706,8 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         SGS_CUDA_TRY(cudaEventRecord(c.evh0, st));
         // with a parent-sharded last level the queue length is only known on the device: counters[0]
         {
-            Status sd = launch_dfs<W_>(c, D, rp.dfs_grid, rp.dfs_wpb, rp.dfs_pw, rp.dfs_cap, cur, rp.counts[rp.depth],
-                                       (nshards > 1 && rp.depth > 0) ? 1 : nshards, (nshards > 1 && rp.depth > 0) ? c.counters : nullptr,
-                                       use_perm ? c.perm : nullptr);
+            Status sd = launch_dfs<W_>(c, D, rp.dfs_grid, rp.dfs_wpb, rp.dfs_pw, rp.dfs_cap, cur, nroots, dev_count ? 1 : nshards, ndev,
+                                       use_perm ? c.perm : nullptr, rp.dfs_expand ? c.counters + 5 : nullptr);
             if (!sd.ok()) return sd;
         }
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));

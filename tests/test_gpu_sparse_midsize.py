@@ -83,6 +83,31 @@ def test_midsize_vs_live_oracle(n, T, seed):
         _note(n, r)
 
 
+@pytest.mark.parametrize('path', ORACLE_GOLDEN[:4], ids=_name)
+def test_midsize_expansion_by_the_walk_kernel(monkeypatch, path):
+    """SGS_DFS_EXPAND=1: the last level of the top-of-tree expansion is produced by k_dfs in expansion mode (one alive
+    list per parent) instead of k_general — same counts, same answer, one shard and virtual shards, both launch sequences"""
+    S = sgs()
+    g, text, ref = _load(path)
+    monkeypatch.setenv('SGS_DFS_EXPAND', '1')
+    H = S.HamHandle.from_text(text)
+    for depth in (0, 2, 3):
+        r = S.sparse_search(H, expand_depth=depth)
+        check_same(r, ref)
+    plan = S.SparsePlan(H)
+    a, b = plan.run(), plan.run()
+    plan.close()
+    check_same(a, ref); check_same(b, ref)
+    first, second = [], []
+    for k in range(4):
+        plan = S.SparsePlan(H, rank=k, world=4)
+        first.append(plan.run()); second.append(plan.run())
+        plan.close()
+    for parts in (first, second):
+        cand, hist, best = _merge(parts)
+        assert cand == ref['candidates'] and hist == ref['rank_hist'] and best['generators'] == ref['generators']
+
+
 def _merge(parts):
     hist = {}
     for p in parts:
