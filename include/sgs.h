@@ -132,7 +132,11 @@ int sgs_sparse_plan_run(sgs_sparse_plan *p, sgs_result *out);
 void sgs_sparse_plan_free(sgs_sparse_plan *p);
 
 /* StateMachine(H).evolve() until m == n, generate_gs(), get_stab_gs()
- * (cpp/klocal_sparse.cpp:26-75, cpp/state.cpp:445-550). */
+ * (cpp/klocal_sparse.cpp:26-75, cpp/state.cpp:445-550).
+ * opts.ngpus > 1 (or world > 1 with an nccl_id): the multi-GPU DP — the counterpart of the reference's omp-parallel
+ * state loop (cpp/state.cpp:494-517).  Every GPU holds the site's states; the move phase of a site and the all-pairs
+ * key ranking are shared out, the results exchanged with NCCL (all-gather / all-reduce per site), the merge is
+ * replicated: bit-identical to the one-GPU result.  Pays from ~10^4-10^5 states per site on. */
 int sgs_klocal_search(const sgs_ham *h, const sgs_opts *opts, sgs_result *out);
 
 /* Finer-grained DP handle for the periodic driver (py/klocal_periodic.py):

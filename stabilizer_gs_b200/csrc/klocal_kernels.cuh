@@ -611,11 +611,11 @@ __device__ __noinline__ int dd_rank_ties(const DdView &D, const K *keys, int c, 
     return cnt;
 }
 template <typename K>
-SGS_D void dd_rank_tiles(const DdView &D, const K *keys, int nuniq, int wid, int nw, int lane)
+SGS_D void dd_rank_tiles(const DdView &D, const K *keys, int nuniq, int wid, int nw, int lane, int slice = 0, int nslices = 1)
 {
     const int ntl = (nuniq + 31) >> 5, nqc = (nuniq + kRankChunk - 1) / kRankChunk;
-    for (int task = wid; task < ntl * nqc; task += nw) {
-        const int p = (task % ntl) * 32 + lane, q0 = (task / ntl) * kRankChunk, q1 = min(q0 + kRankChunk, nuniq);
+    for (long long task = (long long)wid * nslices + slice; task < (long long)ntl * nqc; task += (long long)nw * nslices) {
+        const int p = (int)(task % ntl) * 32 + lane, q0 = (int)(task / ntl) * kRankChunk, q1 = min(q0 + kRankChunk, nuniq);
         const bool valid = p < nuniq;
         const uint64_t pc = valid ? D.lpre[p] : 0;                  // an invalid lane counts nothing that is used
         int cnt = 0;
@@ -716,8 +716,16 @@ struct DpBufs {
     int tstride, slab_stride;
 };
 
+// phase_part (multi-GPU DP, grid mode, one site per launch): 0 = a complete site step;
+//   1 = the move phase (P0) of the states [s_lo, s_hi) only — nothing is committed, the outputs (moved states, their
+//       tables and back-pointers, valid-term spans, fan-out counts, history adds) are then all-gathered across the GPUs;
+//   2 = scan, emit, de-duplicate, leaders (P1-P4) on the whole batch, replicated;
+//   3 = the key-order ranking (P5, all-pairs: the dominant phase of a large batch) for the tasks t = s_lo mod s_hi only
+//       (s_lo = this GPU's rank, s_hi = number of GPUs); the partial ranks are then all-reduced (sum);
+//   4 = merge (P6) and commit, replicated.
 template <int MODE>
-__global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms H, DpBufs B, int m0, int nsteps, int resume)
+__global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms H, DpBufs B, int m0, int nsteps, int resume, int phase_part,
+                                                                        int s_lo, int s_hi)
 {
     const StepSync<MODE> grid;
     constexpr bool CL = MODE != kGrid;
@@ -753,14 +761,14 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
         // ---- P0: one warp per state.  Every block first extracts the rows of the window's terms (last site in
         //      [m, m+k+2)) relative to o_m into shared memory: the serial loops below would otherwise wait for a
         //      global load per term.
-        if (tid == 0) ctl->nuniq = 0;
+        if (tid == 0 && phase_part <= 2) ctl->nuniq = 0;      // (parts 3 and 4 of a multi-GPU step read what part 2 counted)
         {
             const int b0 = H.boff[m], nwin = min(H.boff[min(m + k + 2, H.n + 1)] - b0, 64 * kDpVW);
             __syncthreads();
             for (int i = threadIdx.x; i < nwin; i += blockDim.x) relw[i] = term_rel(H, b0 + i, m - k + 1);
             __syncthreads();
         }
-        for (int s = wid; s < nin; s += nw) {
+        for (int s = (phase_part == 1 ? s_lo : 0) + wid; s < (phase_part == 0 ? nin : (phase_part == 1 ? min(s_hi, nin) : 0)); s += nw) {
             // the state, its right environment and (while the tables are small) the sign table with its scratch
             // are staged in shared memory: the serial group algebra below never waits for L2
             MoveStage &ms = stage[threadIdx.x >> 5];
@@ -798,10 +806,11 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
             }
             if (lane == 0) B.nacc[s] = cnt;
         }
+        if (phase_part == 1) break;                            // (uniform) the other GPUs' slices arrive by all-gather
         grid.sync();
         SGS_PROF(ctl, 0);
         // ---- P1
-        if (blockIdx.x == 0) {
+        if (blockIdx.x == 0 && phase_part <= 2) {
             const int tot = block_scan(B.nacc, B.off, nin, part);
             if (threadIdx.x == 0) {
                 if (tot > capc) atomicMax(&ctl->err, 6);
@@ -818,7 +827,7 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
         DdView D = B.D;
         if (MODE == kBlock && 2 * total <= kSmemSlots) { D.tab = stab; D.mask = kSmemSlots - 1; }
         // ---- P2: key = valid bits for last site in [m1+1, min(m1+k-1, n)), positions relative to boff[m1]
-        {
+        if (phase_part <= 2) {
             const int lo = H.boff[min(m1 + 1, H.n + 1)] - H.boff[m1];
             const int hi = H.boff[min(max(m1 + k - 1, m1 + 1), H.n)] - H.boff[m1];
             for (int s = wid; s < nin; s += nw) {
@@ -854,7 +863,7 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
         grid.sync();
         SGS_PROF(ctl, 2);
         // ---- P3
-        {
+        if (phase_part <= 2) {
             const int lo = H.boff[min(m1 + 1, H.n + 1)] - H.boff[m1];
             const int hi = H.boff[min(max(m1 + k - 1, m1 + 1), H.n)] - H.boff[m1];
             const int vlo = min(lo, 63);
@@ -864,16 +873,19 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
         grid.sync();
         SGS_PROF(ctl, 3);
         // ---- P4
-        for (int c = tid; c < total; c += nth) dd_lead(D, c, &ctl->nuniq);
+        if (phase_part <= 2) for (int c = tid; c < total; c += nth) dd_lead(D, c, &ctl->nuniq);
         grid.sync();
         SGS_PROF(ctl, 4);
+        if (phase_part == 2) break;                            // (uniform) the ranking is shared out next
         const int nuniq = ctl->nuniq;
         if (nuniq > caps) { err = 5; break; }
         if ((long long)hb_off + (long long)nuniq * tstride > hb_cap) { err = 7; break; }
         // ---- P5
-        dd_rank_tiles(D, B.keys, nuniq, wid, nw, lane);
+        if (phase_part == 0) dd_rank_tiles(D, B.keys, nuniq, wid, nw, lane);
+        else if (phase_part == 3) dd_rank_tiles(D, B.keys, nuniq, wid, nw, lane, s_lo, s_hi);
         grid.sync();
         SGS_PROF(ctl, 5);
+        if (phase_part == 3) break;                            // (uniform) partial ranks: summed over the GPUs next
         // ---- P6: exact ties are won by the later child (merge_gs keeps the newcomer unless the incumbent is
         //      strictly lower, cpp/stab.cpp:832); valid bits outside the key come from the first child
         //      (State::merge_gs copies state1, cpp/state.cpp:415-419)
@@ -913,6 +925,10 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_dp_run(DpTerms 
         hm_off += nin; hb_off += nuniq * tstride; step++; nin = nuniq; cur ^= 1; gen++;
     }
     grid.sync();                                             // every exit above is uniform; nobody reads ctl any more
+    if (phase_part >= 1 && phase_part <= 3) {                 // a partial step: nothing is committed; errors stay in ctl->err for the next part
+        if (tid == 0 && err) atomicMax(&ctl->err, err);
+        return;
+    }
     if (tid == 0) {
         if (err) { atomicMax(&ctl->err, err); nin = 0; }
         ctl->nin = nin; ctl->cur = cur; ctl->hm_off = hm_off; ctl->hb_off = hb_off; ctl->step = step;
@@ -988,6 +1004,24 @@ SGS_D void *sr_take(SrCtl *ctl, char *pool, size_t bytes)       // one thread
     return pool + at;
 }
 
+// The link lists of a level are filled through atomic cursors: sorting every list makes the level table (and with it
+// the child order and the accept masks of the DP) the same on every run and on every GPU of a multi-GPU DP.  One thread
+// per group; the lists are short.  Runs for level `lv` while the next level's first phase is under way (nothing there
+// touches level lv's links), so it costs no barrier.
+SGS_D void sr_sort_links(const DpLevelDev &Lv, int tid, int nth)
+{
+    int *idx = const_cast<int *>(Lv.map_idx);
+    for (int g = tid; g < Lv.count; g += nth) {
+        const int a = Lv.map_off[g], z = Lv.map_off[g + 1];
+        for (int i = a + 1; i < z; i++) {
+            const int v = idx[i];
+            int j = i - 1;
+            while (j >= a && idx[j] > v) { idx[j + 1] = idx[j]; j--; }
+            idx[j + 1] = v;
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_sr_run(DpTerms H, SrBufs B, int m_hi, int m_lo, int resume)
 {
@@ -1012,8 +1046,10 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_sr_run(DpTerms 
     if (tid == 0) { ctl->nbr[0] = 0; ctl->nbr[1] = 0; ctl->nbr[2] = 0; ctl->nuniq = 0; }
     grid.sync();
     unsigned long long tprof = gtime();
+    int unsorted = -1;                                        // level whose link lists are filled but not yet sorted
     for (; m >= m_lo && !err; m--) {
         const DpLevelDev Ln = B.levels[m + 1];
+        if (unsorted >= 0) { sr_sort_links(Ln, tid, nth); unsorted = -1; }      // (unsorted == m + 1)
         const int o = m - k + 1, b0 = H.boff[m], b1 = H.boff[m + 1];
         if (b1 - b0 > 30) { err = 3; break; }
         if (Ln.count > B.cap) { err = 4; break; }
@@ -1152,7 +1188,9 @@ __global__ void __launch_bounds__(StepSync<MODE>::kThreads, 1) k_sr_run(DpTerms 
         grid.sync();
         SGS_PROF(ctl, 7);
         gen += 2;
+        unsorted = m;
     }
+    if (unsorted >= 0) sr_sort_links(B.levels[unsorted], tid, nth);            // the last level this kernel filled
     grid.sync();
     if (tid == 0) {
         if (err) atomicMax(&ctl->err, err);

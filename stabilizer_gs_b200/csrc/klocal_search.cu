@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <thread>
 #include <vector>
 
 #include "arena.hpp"
@@ -18,6 +19,7 @@
 #include "group_ops.hpp"
 #include "klocal_kernels.cuh"
 #include "klocal_search.hpp"
+#include "nccl_glue.hpp"
 
 namespace sgs {
 
@@ -446,6 +448,7 @@ Status KlocalMachine::Impl::write_ctl(int nin, bool reset_history)
 // the one host synchronisation point of the DP: closes the timed segment and refreshes the control block
 Status KlocalMachine::Impl::sync_ctl()
 {
+    SGS_CUDA_TRY(cudaSetDevice(device));
     if (hctl_valid && !seg_open) return Status();
     if (seg_open) SGS_CUDA_TRY(cudaEventRecord(e1, st));
     SGS_CUDA_TRY(cudaMemcpyAsync(&hctl, dp.ctl, sizeof(DpCtl), cudaMemcpyDeviceToHost, st));
@@ -524,8 +527,8 @@ Status KlocalMachine::Impl::advance(int nsteps)
     if (!seg_open) { SGS_CUDA_TRY(cudaEventRecord(e0, st)); seg_open = true; }
     hctl_valid = false;
     epoch++;
-    int m0 = m_, resume = 0;
-    void *args[] = {&terms, &dp, &m0, &nsteps, &resume};
+    int m0 = m_, resume = 0, part = 0, s_lo = 0, s_hi = 0;
+    void *args[] = {&terms, &dp, &m0, &nsteps, &resume, &part, &s_lo, &s_hi};
     const void *const fns[3] = {(const void *)k_dp_run<kGrid>, (const void *)k_dp_run<kCluster>, (const void *)k_dp_run<kBlock>};
     SGS_TRY(launch_persistent(fns, small_dp, args, &resume));
     m_ += nsteps;
@@ -563,6 +566,7 @@ Status KlocalMachine::Impl::traceback(int state, int entry, std::vector<std::pai
 // StateMachine::generate_gs + State::get_stab_gs (cpp/state.cpp:421-442,535-550)
 Status KlocalMachine::Impl::ground_state(sgs_result *out)
 {
+    SGS_CUDA_TRY(cudaSetDevice(device));        // (a multi-GPU driver may have left another device current)
     std::vector<HostState> hs;
     Status s = get_states(hs);
     if (!s.ok()) return s;
@@ -968,6 +972,133 @@ int klocal_sright_log(const KlocalMachine &M, int *pairs, int cap)
     return np;
 }
 
+// ------------------------------------------------------------------------------------------------ multi-GPU DP
+// StateMachine::evolve (cpp/state.cpp:483-533) on several GPUs.  The reference parallelises the loop over the states
+// of a site (omp parallel for, :494) and merges under a lock (:501); here the states of a site are REPLICATED on
+// every GPU and the expensive half of a site step — State::move_to_next + project_to + check_Sright_validity of every
+// state, the move phase of k_dp_run — is sharded: GPU g moves the states [g * per, (g + 1) * per), the results
+// (moved states, their 2^rank tables with back-pointers, valid-term spans, fan-out counts, history adds) are
+// exchanged by one NCCL group of in-place all-gathers over NVLink, and every GPU then runs the same deterministic
+// emit / de-duplicate / order / merge on the whole batch, ending with identical state lists and histories (so the
+// traceback needs no communication).  One host round trip per site: worth it from ~10^4 states per site on; below
+// that one GPU's persistent kernel wins.  Errors met by one GPU in its slice travel with an
+// all-reduce(max) of the control block's error word in the same group.
+struct KlocalMulti {
+    std::vector<std::unique_ptr<KlocalMachine>> M;      // one replica per local device
+    std::shared_ptr<NcclWorld> nccl;
+
+    Status create(const Hamiltonian &H, const sgs_opts &opts, int scale)
+    {
+        const int ng = std::max(1, opts.ngpus), world = std::max(1, opts.world);
+        std::vector<int> ids;
+        // the replicas (right environments included: "replicas only") are built concurrently, one host thread per device
+        M.resize(ng);
+        std::vector<Status> st(ng);
+        std::vector<std::thread> th;
+        for (int i = 0; i < ng; i++) {
+            ids.push_back(opts.device + i);
+            th.emplace_back([&, i]() {
+                sgs_opts o = opts;
+                o.device = opts.device + i; o.ngpus = 1;
+                st[i] = KlocalMachine::create(H, o, -1, M[i], scale);
+            });
+        }
+        for (auto &t : th) t.join();
+        for (auto &x : st) if (!x.ok()) return x;
+        return NcclWorld::get(ids, std::max(0, opts.rank), world, opts.nccl_id, nccl);
+    }
+
+    Status advance(int nsteps)
+    {
+        const int N = nccl->size();
+        for (int it = 0; it < nsteps; it++) {
+            for (auto &m : M) SGS_TRY(m->impl()->sync_ctl());
+            KlocalMachine::Impl &K0 = *M[0]->impl();
+            if (K0.hctl.err) return ctl_error(K0.hctl.err, "k-local DP");
+            const int nin = K0.hctl.nin, hm_off = K0.hctl.hm_off;
+            const int per = (nin + N - 1) / N;
+            if ((long long)per * N > K0.caps || (long long)hm_off + (long long)per * N > K0.hm_cap)
+                return Status::fail(SGS_ERR_OVERFLOW, "k-local DP: batch buffers too small for the per-site exchange");
+            // move phase of this GPU's slice
+            for (size_t i = 0; i < M.size(); i++) {
+                KlocalMachine::Impl &K = *M[i]->impl();
+                SGS_CUDA_TRY(cudaSetDevice(K.device));
+                const int g = nccl->global_rank((int)i);
+                int m0 = K.m_, one = 1, resume = 0, part = 1, s_lo = std::min(nin, g * per), s_hi = std::min(nin, (g + 1) * per);
+                void *args[] = {&K.terms, &K.dp, &m0, &one, &resume, &part, &s_lo, &s_hi};
+                if (!K.seg_open) { SGS_CUDA_TRY(cudaEventRecord(K.e0, K.st)); K.seg_open = true; }
+                SGS_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_dp_run<kGrid>, dim3(K.nsm), dim3(256), args, 0, K.st));
+                K.launches++;
+            }
+            // the per-site exchange
+            if (per > 0) {
+                std::vector<std::vector<void *>> base;
+                std::vector<void *> errw;
+                std::vector<cudaStream_t> sts;
+                const size_t slab = (size_t)2 * K0.slab_stride;
+                const std::vector<size_t> bytes = {(size_t)per * sizeof(DpMoved), (size_t)per * sizeof(Ech), (size_t)per * sizeof(int),
+                                                   (size_t)per * slab * sizeof(double), (size_t)per * slab * sizeof(DpBack),
+                                                   (size_t)per * sizeof(DpHistAdd)};
+                for (auto &m : M) {
+                    KlocalMachine::Impl &K = *m->impl();
+                    base.push_back({K.dp.moved, K.dp.span, K.dp.nacc, K.dp.slabE, K.dp.slabB, K.dp.hm + hm_off});
+                    errw.push_back(&K.dp.ctl->err);
+                    sts.push_back(K.st);
+                }
+                SGS_TRY(nccl->gather_arrays_and_max(base, bytes, errw, sts));
+            }
+            auto launch_part = [&](int part, bool slice) -> Status {
+                for (size_t i = 0; i < M.size(); i++) {
+                    KlocalMachine::Impl &K = *M[i]->impl();
+                    SGS_CUDA_TRY(cudaSetDevice(K.device));
+                    int m0 = K.m_, one = 1, resume = 0, s_lo = slice ? nccl->global_rank((int)i) : 0, s_hi = slice ? N : 0;
+                    void *args[] = {&K.terms, &K.dp, &m0, &one, &resume, &part, &s_lo, &s_hi};
+                    SGS_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_dp_run<kGrid>, dim3(K.nsm), dim3(256), args, 0, K.st));
+                    K.launches++;
+                }
+                return Status();
+            };
+            // scan, emit, de-duplicate, leaders: replicated on the whole batch
+            SGS_TRY(launch_part(2, false));
+            // the key-order ranking (all-pairs, the dominant phase of a large batch) is shared out by task;
+            // the partial ranks are summed over the GPUs
+            int total = 0, nuniq = 0;
+            for (auto &m : M) {
+                KlocalMachine::Impl &K = *m->impl();
+                K.hctl_valid = false;
+                SGS_TRY(K.sync_ctl());
+                if (K.hctl.err) return ctl_error(K.hctl.err, "k-local DP");
+                total = K.hctl.total; nuniq = K.hctl.nuniq;
+            }
+            // the compacted leader list is built with an atomic cursor: every GPU takes rank 0's order, so that task t
+            // means the same (32 leaders) x (64 prefixes) everywhere
+            if (nuniq > 0) {
+                std::vector<std::vector<void *>> bufs;
+                std::vector<cudaStream_t> sts;
+                for (auto &m : M) { bufs.push_back({m->impl()->dp.D.lidx, m->impl()->dp.D.lpre}); sts.push_back(m->impl()->st); }
+                SGS_TRY(nccl->broadcast_arrays(bufs, {(size_t)nuniq * sizeof(int), (size_t)nuniq * sizeof(uint64_t)}, sts));
+            }
+            SGS_TRY(launch_part(3, true));
+            if (total > 0) {
+                std::vector<void *> rk;
+                std::vector<cudaStream_t> sts;
+                for (auto &m : M) { rk.push_back(m->impl()->dp.D.rank); sts.push_back(m->impl()->st); }
+                SGS_TRY(nccl->all_reduce_sum_i32(rk, (size_t)total, sts));
+            }
+            // merge and commit: replicated
+            SGS_TRY(launch_part(4, false));
+            for (auto &m : M) {
+                KlocalMachine::Impl &K = *m->impl();
+                K.m_++;
+                K.hctl_valid = false;
+                K.epoch++;
+            }
+        }
+        for (auto &m : M) SGS_TRY(m->impl()->sync_ctl());
+        return Status();
+    }
+};
+
 Status klocal_search(const Hamiltonian &H, const sgs_opts &opts, sgs_result *out)
 {
     const auto t0 = std::chrono::steady_clock::now();
@@ -975,20 +1106,31 @@ Status klocal_search(const Hamiltonian &H, const sgs_opts &opts, sgs_result *out
     std::vector<int> sr(H.n + 1), sp(H.n + 1, 0);
     std::vector<DpStepLog> dlog;
     double ms_create = 0, ms_dp = 0;
+    const bool multi = opts.ngpus > 1 || (opts.world > 1 && opts.nccl_id != nullptr);
+    KlocalMulti MM;
     for (int scale = 1;; scale *= 4) {
         const auto ta = std::chrono::steady_clock::now();
         M.reset();                         // hand the arena back before asking for a bigger one
-        Status s = KlocalMachine::create(H, opts, -1, M, scale);
+        MM = KlocalMulti();
+        Status s = multi ? MM.create(H, opts, scale) : KlocalMachine::create(H, opts, -1, M, scale);
         if (s.ok()) {
+            if (multi) M = std::move(MM.M[0]);          // (results are read from the first local replica; it stays a member of MM below)
             const auto tb = std::chrono::steady_clock::now();
             ms_create = std::chrono::duration<double>(tb - ta).count() * 1e3;
             sp[0] = M->nstates();
-            s = M->impl()->advance(H.n);   // all n sites in one persistent launch
+            if (multi) {
+                MM.M[0] = std::move(M);
+                s = MM.advance(H.n);       // one exchange per site
+                M = std::move(MM.M[0]);
+            } else {
+                s = M->impl()->advance(H.n);   // all n sites in one persistent launch
+            }
             if (s.ok()) s = M->impl()->fetch_log(dlog);
             ms_dp = std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count() * 1e3;
         }
         if (s.ok()) break;
         if (s.code != SGS_ERR_OVERFLOW || scale >= 1024) return s;     // a batch outgrew its buffers: redo with 4x the capacity
+        if (multi) MM.M.clear();
     }
     for (int m = 0; m <= H.n; m++) sr[m] = M->sright_count(m);
     for (const DpStepLog &e : dlog) if (e.m + 1 <= H.n) sp[e.m + 1] = e.nuniq;

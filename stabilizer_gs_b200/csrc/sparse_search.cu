@@ -224,21 +224,8 @@ Status SparsePlan::Impl::init()
         // repeated one-shot searches with the same id reuse the communicator (an id can bootstrap only one)
         std::vector<int> ids;
         for (auto &d : devs) ids.push_back(d.device);
-        std::string key(opts.nccl_id ? (const char *)opts.nccl_id : "", opts.nccl_id ? SGS_NCCL_ID_BYTES : 0);
-        key += "|" + std::to_string(std::max(0, opts.rank)) + "|" + std::to_string(world);
-        for (int d : ids) key += "," + std::to_string(d);
-        static std::mutex mu;
-        static std::map<std::string, std::shared_ptr<NcclWorld>> cache;
-        std::lock_guard<std::mutex> lk(mu);
-        auto it = cache.find(key);
-        if (it != cache.end()) nccl = it->second;
-        else {
-            std::shared_ptr<NcclWorld> w(new NcclWorld());
-            Status s = w->init(ids, std::max(0, opts.rank), world, opts.nccl_id);
-            if (!s.ok()) return s;
-            cache[key] = w;
-            nccl = w;
-        }
+        Status s = NcclWorld::get(ids, std::max(0, opts.rank), world, opts.nccl_id, nccl);
+        if (!s.ok()) return s;
     }
     return Status();
 }
