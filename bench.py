@@ -296,6 +296,11 @@ def main():
     dev_s, hot_s, wall0, launches, res = 0.0, 0.0, time.perf_counter(), 0, None
     for _ in range(args.steps):
         C.flush_l2(device)            # untimed: term tables start each step cold in L2, resident in HBM
+        if dist is not None:
+            # untimed: the ranks enter the step together.  A step ends with a collective, so without this a rank's
+            # CUDA-event time would also count how much later than itself the slowest rank's HOST issued the step
+            # (the steps are host-paced by the flush above); the whole-loop wall time is reported beside it.
+            dist.barrier()
         res = plan.run()
         dev_s += res['seconds_device']
         hot_s += res['seconds_hot_kernel']

@@ -1660,38 +1660,58 @@ k_finalize(SparseDev D, const ShardRec *__restrict__ shards, int nshard, BestRec
     const BestRec *best = gbest;
     const int m = best->m;
 
-    if (tid == 0) {
-        out->error = 0;
-        // K1: reduced row echelon form, pivot = lowest set bit, with phase tracking
+    if (tid < 32) {
+        // K1: reduced row echelon form, pivot = lowest set bit, with phase tracking.  One warp: the earlier rows are
+        // spread over the lanes.  The group is abelian, so a product of its elements (phase included) does not depend
+        // on the order of the factors, and because every earlier pivot column is set in its own row only, WHICH earlier
+        // rows reduce the new one can be read off the new row before any of them is applied.
+        const int lane = tid;
+        if (lane == 0) out->error = 0;
         for (int i = 0; i < m; i++) {
-            uint64_t v[W];
+            uint64_t v[W], acc[W];
             const int t = best->g[i];
-            for (int k = 0; k < W; k++) v[k] = D.rows[(size_t)t * W + k];
-            int q = row_plus_phase<W>(v);
-            for (int b = 0; b < i; b++)
-                if (row_bit<W>(v, pivC[b])) row_mul<W>(v, q, C + b * W, qC[b]);
-            const int pv = row_lowbit<W>(v);
-            for (int b = 0; b < i; b++)                       // clear the new pivot from earlier rows
-                if (row_bit<W>(C + b * W, pv)) row_mul<W>(C + b * W, qC[b], v, q);
-            for (int k = 0; k < W; k++) C[i * W + k] = v[k];
-            qC[i] = q; pivC[i] = pv;
-        }
-        for (int i = 1; i < m; i++) {                         // sort rows by pivot (insertion sort)
-            uint64_t v[W];
-            for (int k = 0; k < W; k++) v[k] = C[i * W + k];
-            const int q = qC[i], pv = pivC[i];
-            int j = i - 1;
-            while (j >= 0 && pivC[j] > pv) {
-                for (int k = 0; k < W; k++) C[(j + 1) * W + k] = C[j * W + k];
-                qC[j + 1] = qC[j]; pivC[j + 1] = pivC[j];
-                j--;
+            for (int k = 0; k < W; k++) { v[k] = D.rows[(size_t)t * W + k]; acc[k] = 0; }
+            int q = row_plus_phase<W>(v), qa = 0;
+            for (int b = lane; b < i; b += 32)
+                if (row_bit<W>(v, pivC[b])) row_mul<W>(acc, qa, C + b * W, qC[b]);
+            for (int off = 16; off > 0; off >>= 1) {
+                uint64_t o[W];
+                for (int k = 0; k < W; k++) o[k] = __shfl_xor_sync(0xffffffffu, acc[k], off);
+                const int oq = __shfl_xor_sync(0xffffffffu, qa, off);
+                row_mul<W>(acc, qa, o, oq);
             }
-            for (int k = 0; k < W; k++) C[(j + 1) * W + k] = v[k];
-            qC[j + 1] = q; pivC[j + 1] = pv;
+            row_mul<W>(v, q, acc, qa);
+            const int pv = row_lowbit<W>(v);
+            for (int b = lane; b < i; b += 32)                // clear the new pivot from earlier rows
+                if (row_bit<W>(C + b * W, pv)) row_mul<W>(C + b * W, qC[b], v, q);
+            if (lane == 0) {
+                for (int k = 0; k < W; k++) C[i * W + k] = v[k];
+                qC[i] = q; pivC[i] = pv;
+            }
+            __syncwarp();
         }
-        // canonicalize_signs (cpp/stab.cpp:685-691): tables are indexed against '+' generators
-        for (int i = 0; i < m; i++) qC[i] = row_plus_phase<W>(C + i * W);
-        *memCount = 0;
+        {                                                     // sort rows by pivot: every row counts the smaller pivots
+            uint64_t v[2][W];
+            int pos[2], pvs[2];
+            for (int h = 0; h < 2; h++) {
+                const int b = lane + 32 * h;
+                pos[h] = 0; pvs[h] = 0;
+                if (b < m) {
+                    pvs[h] = pivC[b];
+                    for (int k = 0; k < W; k++) v[h][k] = C[b * W + k];
+                    for (int j = 0; j < m; j++) pos[h] += pivC[j] < pvs[h];
+                }
+            }
+            __syncwarp();
+            // canonicalize_signs (cpp/stab.cpp:685-691): tables are indexed against '+' generators
+            for (int h = 0; h < 2; h++)
+                if (lane + 32 * h < m) {
+                    for (int k = 0; k < W; k++) C[pos[h] * W + k] = v[h][k];
+                    pivC[pos[h]] = pvs[h];
+                    qC[pos[h]] = row_plus_phase<W>(v[h]);
+                }
+        }
+        if (lane == 0) *memCount = 0;
     }
     __syncthreads();
 
