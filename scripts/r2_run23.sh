@@ -1,0 +1,11 @@
+# split rule = 24 roots per resident warp; k_finalize generator preload; one-shot trace
+(time timeout 900 python -m pytest tests/test_gpu_sparse.py tests/test_gpu_sparse_midsize.py tests/test_gpu_limits.py tests/test_gpu_python_api.py -m gpu -x -q) > gpurun_out/r2r_tests.log 2>&1; echo "sparse gpu tests rc=$?"; tail -4 gpurun_out/r2r_tests.log
+run() { echo "== $*"; env "${@:5}" timeout 300 python scripts/shard_sweep.py $1 $2 0 $3 $4 2>&1 | tail -1 | sed 's/.*| //'; }
+run 24 300 8 6 A=1
+run 24 300 4 6 A=1
+run 30 400 8 3 A=1
+run 40 500 8 3 A=1
+timeout 120 python scripts/e2e_trace.py 2>&1 | tail -40
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 16 --csv --log-file gpurun_out/r2r_launches.csv python scripts/run_sparse_once.py 24 300 0 2 > gpurun_out/r2r_ncu1.log 2>&1; echo "launch list rc=$?"; grep finalize gpurun_out/r2r_launches.csv | cut -d, -f5,15-
+timeout 600 python bench.py --no-config5 > gpurun_out/r2r_bench.json 2> gpurun_out/r2r_bench.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/r2r_bench.json')); print(d['ms_per_step'], d['roofline']['hot_kernel_ms'], d['e2e']['ms_per_step'])"

@@ -1635,7 +1635,7 @@ k_finalize(SparseDev D, const ShardRec *__restrict__ shards, int nshard, BestRec
            int8_t *__restrict__ term_signs, uint64_t *__restrict__ memX, double *__restrict__ memA,
            int *__restrict__ memT, int *memCount)
 {
-    __shared__ uint64_t C[kMaxG * W];
+    __shared__ uint64_t C[kMaxG * W], G[kMaxG * W];
     __shared__ int qC[kMaxG], pivC[kMaxG];
     __shared__ double redE[256];
     __shared__ unsigned long long redI[256];
@@ -1667,10 +1667,14 @@ k_finalize(SparseDev D, const ShardRec *__restrict__ shards, int nshard, BestRec
         // rows reduce the new one can be read off the new row before any of them is applied.
         const int lane = tid;
         if (lane == 0) out->error = 0;
+        for (int b = lane; b < m; b += 32) {                  // all generator rows at once: one round trip, not m
+            const int t = best->g[b];
+            for (int k = 0; k < W; k++) G[b * W + k] = D.rows[(size_t)t * W + k];
+        }
+        __syncwarp();
         for (int i = 0; i < m; i++) {
             uint64_t v[W], acc[W];
-            const int t = best->g[i];
-            for (int k = 0; k < W; k++) { v[k] = D.rows[(size_t)t * W + k]; acc[k] = 0; }
+            for (int k = 0; k < W; k++) { v[k] = G[i * W + k]; acc[k] = 0; }
             int q = row_plus_phase<W>(v), qa = 0;
             for (int b = lane; b < i; b += 32)
                 if (row_bit<W>(v, pivC[b])) row_mul<W>(acc, qa, C + b * W, qC[b]);
@@ -1711,11 +1715,13 @@ k_finalize(SparseDev D, const ShardRec *__restrict__ shards, int nshard, BestRec
                     qC[pos[h]] = row_plus_phase<W>(v[h]);
                 }
         }
-        if (lane == 0) *memCount = 0;
     }
     __syncthreads();
 
-    // K2: decompose every term over the '+' canonical generators
+    // K2: decompose every term over the '+' canonical generators.  The members are written in ascending term order
+    // (ballot + per-warp counts: no atomics, no sort), which is the summation order of the energies below.
+    __shared__ int wcnt[8];
+    int nm = 0;
     for (int t0 = 0; t0 < T; t0 += blockDim.x) {
         const int t = t0 + tid;
         bool member = false;
@@ -1733,22 +1739,20 @@ k_finalize(SparseDev D, const ShardRec *__restrict__ shards, int nshard, BestRec
                 member = row_is_zero<W>(v);
             }
         }
+        const unsigned bal = __ballot_sync(0xffffffffu, member);
+        if ((tid & 31) == 0) wcnt[tid >> 5] = __popc(bal);
+        __syncthreads();
+        int before = 0, all = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { before += w < (tid >> 5) ? wcnt[w] : 0; all += wcnt[w]; }
         if (member) {   // P_t = tau * prod_{i in x} C_i^+, tau = (-1)^{q/2}; bit 30 of memT carries tau < 0
-            const int slot = atomicAdd(memCount, 1);
+            const int slot = nm + before + __popc(bal & ((1u << (tid & 31)) - 1u));
             memT[slot] = t | ((q & 2) ? (1 << 30) : 0); memX[slot] = x; memA[slot] = (q & 2) ? -D.wgt[t] : D.wgt[t];
         }
         if (t < T) term_signs[order[t]] = 0;
+        nm += all;
+        __syncthreads();
     }
-    __syncthreads();
-    const int nm = *memCount;
-    if (tid == 0) {   // deterministic summation order: ascending term index
-        for (int i = 1; i < nm; i++) {
-            const int t = memT[i]; const uint64_t x = memX[i]; const double a = memA[i];
-            int j = i - 1;
-            while (j >= 0 && (memT[j] & 0xffff) > (t & 0xffff)) { memT[j + 1] = memT[j]; memX[j + 1] = memX[j]; memA[j + 1] = memA[j]; j--; }
-            memT[j + 1] = t; memX[j + 1] = x; memA[j + 1] = a;
-        }
-    }
+    if (tid == 0) *memCount = nm;
     __syncthreads();
 
     // K5: first minimum over the 2^m sign patterns

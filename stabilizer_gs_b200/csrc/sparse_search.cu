@@ -105,7 +105,8 @@ struct SparsePlan::Impl {
     Status init_device(DevCtx &c);
     template <int W_> Status search_local(DevCtx &c);
     template <int W_> Status launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
-                                        unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm, const unsigned *valid0 = nullptr);
+                                        unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm, const unsigned *valid0,
+                                        unsigned long long roots_per_shard);
     template <int W_> Status launch_expand(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
                                            unsigned count, uint16_t *out);
     template <int W_> Status finalize(DevCtx &c, const ShardRec *src, int nrec, sgs_result *out, SparseStats *tot, BestRec *best);
@@ -311,11 +312,17 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
 // children to a second round, and those of the second round to a third (counts stay on the device).
 template <int W_>
 Status SparsePlan::Impl::launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
-                                    unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm, const unsigned *valid0)
+                                    unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm, const unsigned *valid0,
+                                    unsigned long long roots_per_shard)
 {
     cudaStream_t st = c.stream;
-    // (measured on config 4: the hand-off rounds cost 6 % at 2 shards, are neutral at 4 and cut the walk by a quarter at 8)
-    const bool split = (nshards >= 5 || getenv("SGS_SPLIT")) && !getenv("SGS_NOSPLIT");
+    // The hand-off rounds pay only when the whole walk of a shard is about as short as its longest subtree (a few
+    // 100 us on one warp), which then alone decides how long the launch lasts: config 4 at 8 shards, 70k roots per shard,
+    // walk 0.55 -> 0.39 ms.  A longer walk hides that tail behind the dynamic fetch (roots come heaviest first) and
+    // re-rooting the children is pure cost: n=30/T=400 at 8 shards (170k roots per shard) 1.46 ms without the rounds,
+    // 1.57 with them; n=40/T=500 at 8 shards 6.6 vs 9.4 ms; config 4 at 2 shards 0.85 vs 1.05 ms.  The root count per
+    // resident warp is the proxy for the length of the walk.
+    const bool split = ((nshards > 1 && roots_per_shard < 24ull * grid * (unsigned)wpb) || getenv("SGS_SPLIT")) && !getenv("SGS_NOSPLIT");
     unsigned *rc = c.counters + 24;      // [0] round-2 count, [1] its valid end, [2] round-3 count, [3] its valid end, [4], [5] item counters
     if (split) {
         SGS_CUDA_TRY(cudaMemsetAsync(rc, 0, 6 * sizeof(unsigned), st));
@@ -539,7 +546,8 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
             c.launches += 2;
         }
         Status sd = launch_dfs<W_>(c, D, grid, dfs_wpb, dfs_pw, dfs_cap, cur, cnt_host, dfs_expand ? 1 : nshards, cnt_dev,
-                                   use_perm ? c.perm : nullptr, dfs_expand ? c.counters + 5 : nullptr);
+                                   use_perm ? c.perm : nullptr, dfs_expand ? c.counters + 5 : nullptr,
+                                   (unsigned long long)count * (dfs_expand ? 8u : 1u) / (unsigned)nshards);
         if (!sd.ok()) return sd;
         SGS_CUDA_TRY(cudaGetLastError());
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
@@ -694,7 +702,8 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         // with a parent-sharded last level the queue length is only known on the device: counters[0]
         {
             Status sd = launch_dfs<W_>(c, D, rp.dfs_grid, rp.dfs_wpb, rp.dfs_pw, rp.dfs_cap, cur, nroots, dev_count ? 1 : nshards, ndev,
-                                       use_perm ? c.perm : nullptr, rp.dfs_expand ? c.counters + 5 : nullptr);
+                                       use_perm ? c.perm : nullptr, rp.dfs_expand ? c.counters + 5 : nullptr,
+                                       (unsigned long long)rp.counts[rp.depth] * (rp.dfs_expand ? 8u : 1u) / (unsigned)nshards);
             if (!sd.ok()) return sd;
         }
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
