@@ -76,6 +76,7 @@ struct SparseDev {
     unsigned int slow_cap;
     int trace;                   // SGS_TRACE: per-root timing diagnostics into stats->dbg
     unsigned long long *inc;     // branch-and-bound mode: best energy found so far on this device (order-encoded double)
+    unsigned long long *wtime;   // SGS_WALK_TRACE builds: [2 * warps] start / end time of every walk warp (globaltimer)
     float split_cliques;         // multi-shard runs: expected cliques from which a root hands its children to the next k_dfs round
 };
 
@@ -661,7 +662,8 @@ SGS_D bool has_duplicate(const uint64_t *R, int n, int lane)
 // (2) builds the list's commutation bit-matrix with POPC + __ballot_sync, then (3) every lane walks the
 // cliques that start at "its" vertices privately with 64-bit masks.
 // Returns false (nothing counted) if the residues are dependent.
-constexpr int kMaxLB = 64;
+constexpr int kMaxLB = 96;          // entries of a level-B frame (three rows per lane); its candidates: <= 64 (the walk's mask width)
+constexpr int kFoldCand = 52;       // multi-word rows: the 64-bit image is tried up to this many candidates (it fails with probability ~ entries * 2^(candidates - 64))
 constexpr int kMaxDep = 6;
 constexpr float kSplitCliques = 2500.f;   // expected cliques from which a root's children go to the next k_dfs round (multi-shard runs)
 
@@ -815,15 +817,15 @@ SGS_D void lb_walk_frame(const M *ADm, const double *WAc, uint16_t *EL, int ncan
 // Forward elimination across the lanes with the candidates as the only pivots — the lower rows are reduced along
 // and must stay non-zero — two pivots per step so that the shuffle -> lowest bit -> test -> XOR chains of
 // consecutive pivots overlap (the loop is latency-bound).  Half the pivots of an elimination of all n rows.
-SGS_D bool rows_dependent_1w(uint64_t p0, uint64_t p1, int n, int nlow, int lane)
+SGS_D bool rows_dependent_1w(uint64_t p0, uint64_t p1, uint64_t p2, int n, int nlow, int lane)
 {
-    const bool two = n > 32;
-    const bool low0 = lane < nlow, low1 = lane + 32 < nlow;
+    const bool two = n > 32, three = n > 64;
+    const bool low0 = lane < nlow, low1 = lane + 32 < nlow, low2 = lane + 64 < nlow;
     int u = nlow;
 #pragma unroll 1
     for (; u + 1 < n; u += 2) {
-        const uint64_t c0 = __shfl_sync(0xffffffffu, u < 32 ? p0 : p1, u & 31);
-        uint64_t c1 = __shfl_sync(0xffffffffu, u + 1 < 32 ? p0 : p1, (u + 1) & 31);
+        const uint64_t c0 = __shfl_sync(0xffffffffu, u < 32 ? p0 : (u < 64 ? p1 : p2), u & 31);
+        uint64_t c1 = __shfl_sync(0xffffffffu, u + 1 < 32 ? p0 : (u + 1 < 64 ? p1 : p2), (u + 1) & 31);
         if (c0 == 0) return true;
         const uint64_t l0 = c0 & (0 - c0);
         if (c1 & l0) c1 ^= c0;
@@ -837,15 +839,20 @@ SGS_D bool rows_dependent_1w(uint64_t p0, uint64_t p1, int n, int nlow, int lane
             if (p1 & l0) p1 ^= c0;
             if (p1 & l1) p1 ^= c1;
         }
+        if (three && (lane + 64 > u + 1 || low2)) {
+            if (p2 & l0) p2 ^= c0;
+            if (p2 & l1) p2 ^= c1;
+        }
     }
     if (u < n) {
-        const uint64_t c0 = __shfl_sync(0xffffffffu, u < 32 ? p0 : p1, u & 31);
+        const uint64_t c0 = __shfl_sync(0xffffffffu, u < 32 ? p0 : (u < 64 ? p1 : p2), u & 31);
         if (c0 == 0) return true;
         const uint64_t l0 = c0 & (0 - c0);
         if (low0 && (p0 & l0)) p0 ^= c0;
         if (low1 && (p1 & l0)) p1 ^= c0;
+        if (low2 && (p2 & l0)) p2 ^= c0;
     }
-    return __any_sync(0xffffffffu, (low0 && p0 == 0) || (low1 && p1 == 0));
+    return __any_sync(0xffffffffu, (low0 && p0 == 0) || (low1 && p1 == 0) || (low2 && p2 == 0));
 }
 
 // expected number of cliques of a graph with n vertices and e edges (edge density p): sum_k C(n,k) p^(k(k-1)/2)
@@ -867,12 +874,13 @@ SGS_D float expected_cliques(int n, int e)
 template <int W>
 __device__ __noinline__ bool rows_dependent_full(const uint64_t *R, int n, int nlow, int lane)
 {
-    const bool two = n > 32;
-    uint64_t e0[W], e1[W];
+    const bool two = n > 32, three = n > 64;
+    uint64_t e0[W], e1[W], e2[W];
 #pragma unroll
     for (int k = 0; k < W; k++) {
         e0[k] = lane < n ? R[lane * W + k] : 0;
         e1[k] = lane + 32 < n ? R[(lane + 32) * W + k] : 0;
+        e2[k] = lane + 64 < n ? R[(lane + 64) * W + k] : 0;
     }
 #pragma unroll 1
     for (int u = nlow; u < n; u++) {
@@ -880,14 +888,14 @@ __device__ __noinline__ bool rows_dependent_full(const uint64_t *R, int n, int n
         bool nz = false;
 #pragma unroll
         for (int k = 0; k < W; k++) {
-            cu[k] = __shfl_sync(0xffffffffu, u < 32 ? e0[k] : e1[k], u & 31);
+            cu[k] = __shfl_sync(0xffffffffu, u < 32 ? e0[k] : (u < 64 ? e1[k] : e2[k]), u & 31);
             lm[k] = nz ? 0 : (cu[k] & (0 - cu[k]));
             nz |= cu[k] != 0;
         }
         if (!nz) return true;
-        uint64_t h0 = 0, h1 = 0;
+        uint64_t h0 = 0, h1 = 0, h2 = 0;
 #pragma unroll
-        for (int k = 0; k < W; k++) { h0 |= e0[k] & lm[k]; h1 |= e1[k] & lm[k]; }
+        for (int k = 0; k < W; k++) { h0 |= e0[k] & lm[k]; h1 |= e1[k] & lm[k]; h2 |= e2[k] & lm[k]; }
         if ((lane > u || lane < nlow) && h0) {
 #pragma unroll
             for (int k = 0; k < W; k++) e0[k] ^= cu[k];
@@ -896,11 +904,15 @@ __device__ __noinline__ bool rows_dependent_full(const uint64_t *R, int n, int n
 #pragma unroll
             for (int k = 0; k < W; k++) e1[k] ^= cu[k];
         }
-    }
-    uint64_t z0 = 0, z1 = 0;
+        if (three && (lane + 64 > u || lane + 64 < nlow) && h2) {
 #pragma unroll
-    for (int k = 0; k < W; k++) { z0 |= e0[k]; z1 |= e1[k]; }
-    return __any_sync(0xffffffffu, (lane < nlow && z0 == 0) || (lane + 32 < nlow && z1 == 0));
+            for (int k = 0; k < W; k++) e2[k] ^= cu[k];
+        }
+    }
+    uint64_t z0 = 0, z1 = 0, z2 = 0;
+#pragma unroll
+    for (int k = 0; k < W; k++) { z0 |= e0[k]; z1 |= e1[k]; z2 |= e2[k]; }
+    return __any_sync(0xffffffffu, (lane < nlow && z0 == 0) || (lane + 32 < nlow && z1 == 0) || (lane + 64 < nlow && z2 == 0));
 }
 
 // ... and the analysis of a frame whose certificate failed: an elimination of ALL n residues that tracks which
@@ -1011,37 +1023,40 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
     //    never become generators below this frame.  Own rows: entries lane and lane + 32; step u broadcasts the
     //    (already reduced) copy of candidate u and clears its lowest set bit from the later candidates and from
     //    the lower rows.
-    uint64_t e0[W], e1[W];
+    uint64_t e0[W], e1[W], e2[W];
 #pragma unroll
     for (int k = 0; k < W; k++) {
         e0[k] = lane < n ? R[lane * W + k] : 0;
         e1[k] = lane + 32 < n ? R[(lane + 32) * W + k] : 0;
+        e2[k] = lane + 64 < n ? R[(lane + 64) * W + k] : 0;
     }
     bool dependent = false;
     // Multi-word rows: if the images under a linear map onto 64 bits (the words folded together by rotations)
     // are independent, so are the rows — one-word elimination at half the cost or less; with <= 62 entries it
     // rarely fails, and when it does the full-width elimination below decides.
     bool proven = false;
-    if (W > 1 && n <= 62) {
-        uint64_t p0 = e0[0], p1 = e1[0];
+    if (W > 1 && n - nlow <= kFoldCand) {
+        uint64_t p0 = e0[0], p1 = e1[0], p2 = e2[0];
 #pragma unroll
         for (int k = 1; k < W; k++) {
             const int rot = (23 * k) & 63;
             p0 ^= (e0[k] << rot) | (e0[k] >> (64 - rot));
             p1 ^= (e1[k] << rot) | (e1[k] >> (64 - rot));
+            p2 ^= (e2[k] << rot) | (e2[k] >> (64 - rot));
         }
-        const bool dep = rows_dependent_1w(p0, p1, n, nlow, lane);
+        const bool dep = rows_dependent_1w(p0, p1, p2, n, nlow, lane);
         proven = !dep;
         if (lane == 0) pc[dep ? kPathFoldFull : kPathFoldOk]++;
     }
     if (W == 1) {
-        dependent = rows_dependent_1w(e0[0], e1[0], n, nlow, lane);
+        dependent = rows_dependent_1w(e0[0], e1[0], e2[0], n, nlow, lane);
         proven = true;
     }
     if (!proven) dependent = rows_dependent_full<W>(R, n, nlow, lane);      // (multi-word rows whose folded image was inconclusive)
     if (dependent) {
         // rare (a handful per thousand frames on random instances): out of line, the hot code must stay inside the instruction caches
-        if (!level_b_dependent<W>(R, n, lane)) { if (lane == 0) pc[kPathNoCert]++; return 0; }
+        // (the dependency analysis works on 64-bit entry masks: a longer list goes back to the caller uncertified)
+        if (n > 64 || !level_b_dependent<W>(R, n, lane)) { if (lane == 0) pc[kPathNoCert]++; return 0; }
         if (lane == 0) pc[kPathDepCert]++;
     }
     // 2. commutation graph of the candidates only (list positions nlow..n-1; vertex = position - nlow): lane
@@ -1088,7 +1103,7 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         __syncwarp();
         uint32_t bm32 = 0;
         lb_walk_frame<uint32_t, PRUNE>(AD32, WA + nlow, EL, ncand, lane < ncand ? (a32 & ((1u << lane) - 1u)) : 0u, 0u, depth, hc, bw, bm32, lane, SW, need);
-        bm = (uint64_t)bm32 << nlow;
+        bm = (uint64_t)bm32;
     } else {
         uint64_t sc0[W], sc1[W];
 #pragma unroll
@@ -1120,7 +1135,7 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         uint64_t bmr = 0;
         lb_walk_frame<uint64_t, PRUNE>(AD, WA + nlow, EL, ncand, a0 & ((1ULL << lane) - 1ULL), lane + 32 < ncand ? (a1 & ((1ULL << (lane + 32)) - 1ULL)) : 0ULL,
                                        depth, hc, bw, bmr, lane, SW, need);
-        bm = bmr << nlow;
+        bm = bmr;
     }
     __syncwarp();
     return 1;
@@ -1254,7 +1269,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         const bool cand = bm != 0 && (Ef - bw) <= bestE;
         if (__any_sync(0xffffffffu, cand)) {
             double w;
-            const int sz = level_b_pick(bw, bm, TT + lb, path, depth, lane, &w);
+            const int sz = level_b_pick(bw, bm, TT + lb + nlow, path, depth, lane, &w);      // (bm: mask over the candidates)
             try_best(Ef - w, depth + sz);
         }
         return 1;
@@ -1268,6 +1283,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     bool tfail = false;
     unsigned tinfo = 0;
     const unsigned tround = valid_end ? (retry_out ? 2u : 3u) : 1u;
+    const unsigned long long twarp0 = trace ? gtimer() : 0ull;
 #pragma unroll 1
     for (;;) {
         // ---- fetch the next subtree root owned by this shard ----
@@ -1381,7 +1397,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         if (q0 >= a) { try_best(E0, m0); continue; }                      // no extension: a leaf
         // (a certified root whose clique walk alone would outlast the rest of a short kernel is split the same way
         //  when a next round exists: level_b answers 2)
-        if (!(mode & kDfsExpand) && a <= 64 && m0 + (a - q0) < kMaxG && run_level_b(0, a, q0, m0, E0, retry_out ? D.split_cliques : 0.f) == 1) continue;
+        if (!(mode & kDfsExpand) && a <= kMaxLB && a - q0 <= 64 && m0 + (a - q0) < kMaxG && run_level_b(0, a, q0, m0, E0, retry_out ? D.split_cliques : 0.f) == 1) continue;
         tfail = true;
         if (has_duplicate<W>(R, a, lane)) {
             try_best(E0, m0);
@@ -1503,7 +1519,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                 for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, d);
                 if (Ec - csum > thr) { try_best(Ec, depth + 1); continue; }     // (the child itself is still a candidate)
             }
-            if (nal <= 64 && depth + 1 + (nal - nlow) < kMaxG && run_level_b(cb, nal, nlow, depth + 1, Ec, 0.f) == 1) continue;
+            if (nal <= kMaxLB && nal - nlow <= 64 && depth + 1 + (nal - nlow) < kMaxG && run_level_b(cb, nal, nlow, depth + 1, Ec, 0.f) == 1) continue;
             // residues pairwise distinct ⇒ every child of this child is a new group whose only members
             // are its generators.  Otherwise the exact kernel expands it.
             if (has_duplicate<W>(R + cb * W, nal, lane)) {
@@ -1523,6 +1539,11 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     }
 
     __syncwarp();
+    if (trace && lane == 0) {                              // warp lifetimes: idle share = 1 - sum / (warps x kernel time)
+        const unsigned long long te = gtimer();
+        atomicAdd(&D.stats->dbg[4], te - twarp0);
+        if (tround == 1u) { D.wtime[2 * gw] = twarp0; D.wtime[2 * gw + 1] = te; }
+    }
     if (bestE < 1e300) {
         if (lane == 0) { myrec->E = bestE; myrec->m = bestM; myrec->valid = 1; }
         for (int i = lane; i < bestM; i += 32) myrec->g[i] = bestG[i];

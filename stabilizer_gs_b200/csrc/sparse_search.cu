@@ -50,6 +50,7 @@ struct DevCtx {
     double *memA = nullptr;
     int *memT = nullptr, *memCount = nullptr;
     int nwbest = 0;
+    unsigned long long *wtime = nullptr;
     void *arena = nullptr;
     // results of the local search
     SparseStats hstats{};
@@ -137,6 +138,7 @@ SparseDev SparsePlan::Impl::dev_view(const DevCtx &c) const
 {
     SparseDev D{};
     D.n = n; D.T = T; D.TW = TW; D.S = S;
+    D.wtime = c.wtime;
     D.rows = c.rows; D.wgt = c.wgt; D.wabs = c.wabs; D.adj = c.adj;
     D.wbest = c.wbest; D.stats = c.stats;
     D.slow = c.slow; D.slow_count = c.counters + 2; D.slow_cap = slow_cap;
@@ -254,6 +256,7 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
     want(&c.wabs, Tn);
     want(&c.order, Tn);
     want(&c.wbest, c.nwbest);
+    want(&c.wtime, (size_t)c.nwbest * 2);
     want(&c.shardrec, 1);
     want(&c.allrec, std::max(nshards, 1));
     want(&c.qA, (size_t)qcap * S);
@@ -535,7 +538,7 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         }
         SGS_CUDA_TRY(cudaEventRecord(c.evh0, st));
         // heavy-first order pays when the walk is short (several shards): the longest subtrees must not start last
-        const bool use_perm = nshards > 1 && !getenv("SGS_NOPERM");
+        const bool use_perm = !getenv("SGS_NOPERM");
         const unsigned *cnt_dev = dfs_expand ? c.counters + 4 : nullptr;        // roots written by the expansion-mode launch
         const unsigned cnt_host = dfs_expand ? qcap : count;
         if (use_perm) {
@@ -689,7 +692,7 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         const bool dev_count = rp.dfs_expand || (nshards > 1 && rp.depth > 0);      // queue length only known on the device
         const unsigned *ndev = rp.dfs_expand ? c.counters + 4 : (dev_count ? c.counters : nullptr);
         const unsigned nroots = rp.dfs_expand ? qcap : rp.counts[rp.depth];
-        const bool use_perm = nshards > 1 && !getenv("SGS_NOPERM");
+        const bool use_perm = !getenv("SGS_NOPERM");
         if (use_perm) {
             const unsigned cnt = nroots;
             const unsigned cg = rp.dfs_expand ? (unsigned)c.sms * 4 : std::max(1u, std::min<unsigned>((cnt + 255) / 256, (unsigned)c.sms * 4));
@@ -762,6 +765,19 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         const unsigned long long *g = c0.hstats.dbg;
         fprintf(stderr, "  walk: longest root %.1f us; roots not certified at the root %llu (%.3f warp-ms of %.3f); roots > 50 us: %llu (%.3f warp-ms)\n",
                 g[0] * 1e-3, g[1], g[2] * 1e-6, g[3] * 1e-6, g[5], g[6] * 1e-6);
+        fprintf(stderr, "  warp lifetimes %.3f warp-ms in total (%u warps x walk time = %.3f)\n", g[4] * 1e-6, rp.dfs_grid * rp.dfs_wpb, rp.dfs_grid * rp.dfs_wpb * e2);
+        if (g[4]) {
+            const unsigned nw = rp.dfs_grid * rp.dfs_wpb;
+            std::vector<unsigned long long> wt(2 * (size_t)nw);
+            cudaMemcpy(wt.data(), c0.wtime, wt.size() * 8, cudaMemcpyDeviceToHost);
+            unsigned long long t0w = ~0ull, t1w = 0;
+            for (unsigned i = 0; i < nw; i++) { t0w = std::min(t0w, wt[2 * i]); t1w = std::max(t1w, wt[2 * i + 1]); }
+            std::vector<double> ends(nw);
+            for (unsigned i = 0; i < nw; i++) ends[i] = (double)(wt[2 * i + 1] - t0w) * 1e-3;
+            std::sort(ends.begin(), ends.end());
+            fprintf(stderr, "  warp end times (us after the first start): 1%% %.0f, 10%% %.0f, 25%% %.0f, 50%% %.0f, 75%% %.0f, 90%% %.0f, 99%% %.0f, last %.0f\n",
+                    ends[nw / 100], ends[nw / 10], ends[nw / 4], ends[nw / 2], ends[3 * (size_t)nw / 4], ends[9 * (size_t)nw / 10], ends[99 * (size_t)nw / 100], ends[nw - 1]);
+        }
         fprintf(stderr, "  longest root: round %llu, rank %llu, alive %llu, candidates %llu, certified %d\n", (g[7] >> 21) & 7, (g[7] >> 15) & 63,
                 (g[7] >> 8) & 127, (g[7] >> 1) & 127, (int)!(g[7] & 1));
     }
