@@ -110,9 +110,10 @@ typedef struct {
     /* sparse search diagnostics (the parity tests assert that every path of the walk was exercised):
      * [0] certified frames walked with 32-bit clique masks, [1] with 64-bit masks, [2] multi-word independence
      * proven on the folded 64-bit image, [3] decided by the full-width elimination, [4] dependent residues
-     * certified by the clique test, [5] frames not certified, [6] warp-cooperative child frames (level A);
+     * certified by the clique test, [5] frames not certified, [6] warp-cooperative child frames (level A),
+     * [7] certified frames of more than 64 entries;
      * saturating; summed over shards when a communicator combines them */
-    uint32_t walk_paths[7];
+    uint32_t walk_paths[8];
 } sgs_result;
 void sgs_result_free(sgs_result *r);     /* frees the buffers inside *r (not r itself)        */
 

@@ -40,7 +40,7 @@ class Result(C.Structure):
                 ('states_per_site', C.POINTER(C.c_int)), ('transitions', C.c_uint64),
                 ('seconds_total', C.c_double), ('seconds_device', C.c_double),
                 ('seconds_hot_kernel', C.c_double), ('kernel_launches', C.c_uint32),
-                ('walk_paths', C.c_uint32 * 7)]
+                ('walk_paths', C.c_uint32 * 8)]
 
 
 class Orbit(C.Structure):
@@ -167,7 +167,7 @@ def result_to_dict(r, n):
              rank_hist={i: int(r.rank_hist[i]) for i in range(SGS_MAX_RANK + 1) if r.rank_hist[i]},
              seconds_total=r.seconds_total, seconds_device=r.seconds_device,
              seconds_hot_kernel=r.seconds_hot_kernel, kernel_launches=int(r.kernel_launches),
-             transitions=int(r.transitions), walk_paths=[int(r.walk_paths[i]) for i in range(7)])
+             transitions=int(r.transitions), walk_paths=[int(r.walk_paths[i]) for i in range(8)])
     if r.nsites:
         d['sright_counts'] = [int(r.sright_counts[i]) for i in range(r.nsites + 1)]
         d['states_per_site'] = [int(r.states_per_site[i]) for i in range(r.nsites + 1)]

@@ -57,7 +57,7 @@ struct BestRec {
 struct SparseStats {
     unsigned long long hist[kMaxG + 1];   // candidates per rank
     unsigned long long slow_nodes;        // candidates evaluated by k_general
-    unsigned long long paths[8];          // which code paths of the walk ran (kPath*; summed over shards like hist)
+    unsigned long long paths[9];          // which code paths of the walk ran (kPath*; summed over shards like hist)
     unsigned int error;                   // SGS_ERR_* (positive) set by a kernel
     unsigned int pad;
     unsigned long long dbg[8];            // SGS_TRACE diagnostics of the walk (see k_dfs)
@@ -81,7 +81,7 @@ struct SparseDev {
 };
 
 enum { kErrOverflow = 8, kErrLimit = 6 };
-constexpr int kStatsSummed = kMaxG + 2 + 8;   // leading u64 words of SparseStats that add up over shards (hist, slow_nodes, paths)
+constexpr int kStatsSummed = kMaxG + 2 + 9;   // leading u64 words of SparseStats that add up over shards (hist, slow_nodes, paths)
 // SparseStats::paths — diagnostics the parity tests assert on (sgs_result.walk_paths)
 enum {
     kPathWalk32 = 0,     // certified frames walked with 32-bit clique masks (<= 32 candidates)
@@ -91,8 +91,10 @@ enum {
     kPathDepCert = 4,    // dependent residues, certified because no dependency is a clique
     kPathNoCert = 5,     // frames level B could not certify (commuting dependency / > kMaxDep dependencies)
     kPathLevelA = 6,     // warp-cooperative child frames pushed below a root
-    kPathSplit = 7       // roots whose children were handed to a next k_dfs round
+    kPathWide = 7,       // certified frames of more than 64 entries (three rows per lane in the certificate)
+    kPathSplit = 8       // roots whose children were handed to a next k_dfs round
 };
+constexpr int kNumPaths = 9;
 
 SGS_D unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // order-preserving encoding of a double into an unsigned key (atomicMin on the key = min on the double)
@@ -599,7 +601,7 @@ __host__ __device__ inline size_t dfs_smem_bytes(int cap, bool prune)
 {
     size_t b = 0;
     b += (size_t)cap * W * 8;          // residues
-    b += (size_t)cap * 8;              // |w| of each list entry
+    b += 64 * 8;                       // |w| of the candidates of the level-B frame being walked
     b += dfs_scratch_bytes<W>();       // root basis, later the level-B commutation bit-matrix (64-bit or 32-bit form)
     b += (size_t)kMaxEdgesSmem * 2;    // edge list of the level-B walk (one chunk)
     b += (size_t)kMaxFramesA * 8;      // frame E
@@ -610,7 +612,7 @@ __host__ __device__ inline size_t dfs_smem_bytes(int cap, bool prune)
     b += 64;                           // basis pivots
     b += 8;                            // alignment slack
     if (prune) b += 64 * 8;            // suffix sums of the candidate weights (branch-and-bound mode)
-    b += 8 * 4;                        // code-path counters
+    b += (kNumPaths + 1) * 4;          // code-path counters
     return (b + 15) & ~(size_t)15;
 }
 
@@ -1012,7 +1014,7 @@ SGS_D bool level_b_dependent(const uint64_t *R, int n, int lane)
 // (not inlined: it is called from two places of k_dfs and a single copy keeps the hot loops inside the
 //  instruction cache)
 template <int W, bool PRUNE>
-__device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_t *AD, uint32_t *AD32, uint16_t *EL, int n, int nlow, int depth,
+__device__ __noinline__ int level_b(const uint64_t *R, const uint16_t *TTc, const double *__restrict__ wabs, double *WC, uint64_t *AD, uint32_t *AD32, uint16_t *EL, int n, int nlow, int depth,
                   uint32_t *hc, double &bw, uint64_t &bm, int lane, float split_cliques, double *SW, double need, uint32_t *pc)
 {
     // 1. the certificate: the residues of the CANDIDATES (positions nlow..n-1) are linearly independent and no
@@ -1023,6 +1025,10 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
     //    never become generators below this frame.  Own rows: entries lane and lane + 32; step u broadcasts the
     //    (already reduced) copy of candidate u and clears its lowest set bit from the later candidates and from
     //    the lower rows.
+    // (the candidates' weights |w| for the walk: gathered from the term table into the warp's scratch while the
+    //  certificate runs — the lists carry no weights)
+    if (lane < n - nlow) WC[lane] = wabs[TTc[lane]];
+    if (lane + 32 < n - nlow) WC[lane + 32] = wabs[TTc[lane + 32]];
     uint64_t e0[W], e1[W], e2[W];
 #pragma unroll
     for (int k = 0; k < W; k++) {
@@ -1066,7 +1072,8 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
     if (PRUNE) {
         // certified: below this frame members = generators, so no group can weigh more than all candidates
         // together.  Suffix sums of the candidate weights (warp scan), then the frame-level bound.
-        double x1 = lane + 32 < ncand ? WA[nlow + lane + 32] : 0.0, x0 = lane < ncand ? WA[nlow + lane] : 0.0;
+        __syncwarp();
+        double x1 = lane + 32 < ncand ? WC[lane + 32] : 0.0, x0 = lane < ncand ? WC[lane] : 0.0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const double y1 = __shfl_down_sync(0xffffffffu, x1, o), y0 = __shfl_down_sync(0xffffffffu, x0, o);
@@ -1099,11 +1106,14 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
             if (expected_cliques(ncand, e) > split_cliques) return 2;
         }
         if (lane < ncand) AD32[lane] = up32;
-        if (lane == 0) pc[kPathWalk32]++;
+        if (lane == 0) { pc[kPathWalk32]++; if (n > 64) pc[kPathWide]++; }
         __syncwarp();
+        // (bw / bm are references into the caller's frame, i.e. local memory: the walk works on register copies)
         uint32_t bm32 = 0;
-        lb_walk_frame<uint32_t, PRUNE>(AD32, WA + nlow, EL, ncand, lane < ncand ? (a32 & ((1u << lane) - 1u)) : 0u, 0u, depth, hc, bw, bm32, lane, SW, need);
+        double bwl = -1.0;
+        lb_walk_frame<uint32_t, PRUNE>(AD32, WC, EL, ncand, lane < ncand ? (a32 & ((1u << lane) - 1u)) : 0u, 0u, depth, hc, bwl, bm32, lane, SW, need);
         bm = (uint64_t)bm32;
+        bw = bwl;
     } else {
         uint64_t sc0[W], sc1[W];
 #pragma unroll
@@ -1130,12 +1140,14 @@ __device__ __noinline__ int level_b(const uint64_t *R, const double *WA, uint64_
         }
         AD[lane] = up0;
         if (lane + 32 < ncand) AD[lane + 32] = up1;
-        if (lane == 0) pc[kPathWalk64]++;
+        if (lane == 0) { pc[kPathWalk64]++; if (n > 64) pc[kPathWide]++; }
         __syncwarp();
         uint64_t bmr = 0;
-        lb_walk_frame<uint64_t, PRUNE>(AD, WA + nlow, EL, ncand, a0 & ((1ULL << lane) - 1ULL), lane + 32 < ncand ? (a1 & ((1ULL << (lane + 32)) - 1ULL)) : 0ULL,
-                                       depth, hc, bw, bmr, lane, SW, need);
+        double bwl = -1.0;
+        lb_walk_frame<uint64_t, PRUNE>(AD, WC, EL, ncand, a0 & ((1ULL << lane) - 1ULL), lane + 32 < ncand ? (a1 & ((1ULL << (lane + 32)) - 1ULL)) : 0ULL,
+                                       depth, hc, bwl, bmr, lane, SW, need);
         bm = bmr;
+        bw = bwl;
     }
     __syncwarp();
     return 1;
@@ -1211,7 +1223,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     if (valid_end) nitems = min(nitems, *valid_end);
     unsigned char *p = smem_raw + (size_t)warp * smem_per_warp;
     uint64_t *R = (uint64_t *)p;        p += (size_t)cap * W * 8;
-    double *WA = (double *)p;           p += (size_t)cap * 8;
+    double *WC = (double *)p;           p += 64 * 8;      // |w| of the candidates of the level-B frame being walked
     uint64_t *B = (uint64_t *)p;        // root basis; dead once the root's residues are written, then:
     uint64_t *AD = (uint64_t *)p;       // level-B commutation bit-matrix, 64-bit form
     uint32_t *AD32 = (uint32_t *)(p + 64 * 8);   // ... and 32-bit form
@@ -1229,8 +1241,8 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     p = smem_raw + (((size_t)(p - smem_raw) + 7) & ~(size_t)7);
     double *SW = (double *)p;           // [64] suffix sums of the candidate weights (branch-and-bound build only)
     if (PRUNE) p += 64 * 8;
-    uint32_t *pc = (uint32_t *)p;       // [8] code-path counters (kPath*)
-    if (lane < 8) pc[lane] = 0;
+    uint32_t *pc = (uint32_t *)p;       // [kNumPaths] code-path counters (kPath*)
+    if (lane < kNumPaths) pc[lane] = 0;
 
     const unsigned gw = blockIdx.x * wpb + warp;
     BestRec *myrec = D.wbest + gw;
@@ -1263,7 +1275,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         double bw = -1.0;
         uint64_t bm = 0;
         // a clique of weight w gives the energy Ef - w: it reaches the incumbent iff w >= Ef - thr
-        const int rc = level_b<W, PRUNE>(R + lb * W, WA + lb, AD, AD32, EL, n, nlow, depth, hc, bw, bm, lane, split, SW, Ef - thr, pc);
+        const int rc = level_b<W, PRUNE>(R + lb * W, TT + lb + nlow, D.wabs, WC, AD, AD32, EL, n, nlow, depth, hc, bw, bm, lane, split, SW, Ef - thr, pc);
         if (rc != 1) return rc;
         // does any lane's best clique reach the incumbent?
         const bool cand = bm != 0 && (Ef - bw) <= bestE;
@@ -1377,7 +1389,6 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             q0 += (t <= core0);
 #pragma unroll
             for (int k = 0; k < W; k++) R[i * W + k] = v[k];
-            WA[i] = D.wabs[t];
             if (PRUNE) wall += D.wabs[t];
         }
         __syncwarp();
@@ -1441,7 +1452,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             uint64_t rj[W], sw[W];
 #pragma unroll
             for (int k = 0; k < W; k++) { rj[k] = R[(base + jq) * W + k]; sw[k] = swapzx(rj[k]); }
-            const double Ec = E - WA[base + jq];
+            const double Ec = E - D.wabs[TT[base + jq]];
 
             // pass 1: which list entries commute with the new generator (POPC), and is any above it?
             int nal = 0, nlow = 0;
@@ -1508,8 +1519,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
 #pragma unroll
                     for (int k = 0; k < W; k++) R[pos * W + k] = v[k];
                     TT[pos] = TT[base + i];
-                    WA[pos] = WA[base + i];
-                    if (PRUNE) csum += WA[base + i];
+                    if (PRUNE) csum += D.wabs[TT[base + i]];
                 }
                 off += __popc(bal);
             }
@@ -1558,7 +1568,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
     __syncwarp();
     for (int i = lane; i <= kMaxG; i += 32)
         if (hist[i]) atomicAdd(&D.stats->hist[i], (unsigned long long)hist[i]);
-    if (lane < 8 && pc[lane]) atomicAdd(&D.stats->paths[lane], (unsigned long long)pc[lane]);
+    if (lane < kNumPaths && pc[lane]) atomicAdd(&D.stats->paths[lane], (unsigned long long)pc[lane]);
 }
 
 // ------------------------------------------------------------------------------------------------

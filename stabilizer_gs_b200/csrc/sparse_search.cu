@@ -488,12 +488,27 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
         const int depth_w = dfs_expand ? depth + 1 : depth;
         const double a_est = std::max(8.0, ratio_w * std::max(depth_w, 1) / 2.0);
         int cap = (int)(2.2 * (a_est + 4.0 * std::sqrt(a_est)));
-        if (const char *v = getenv("SGS_DFS_CAP")) if (atoi(v) > 0) cap = atoi(v);
+        bool cap_forced = false;
+        if (const char *v = getenv("SGS_DFS_CAP")) if (atoi(v) > 0) { cap = atoi(v); cap_forced = true; }
         cap = std::min(2048, std::max(96, (cap + 31) & ~31));
+        int dfs_wpb = kDfsWpb;
+        while (dfs_wpb > 1 && dfs_smem_bytes<W_>(cap, opts.prune != 0) * dfs_wpb > 200 * 1024) dfs_wpb >>= 1;
+        if (!cap_forced) {
+            // the arena bounds the resident warps of a large instance (n = 40, T = 1000: 384 entries = 16 warps per SM):
+            // give up to a fifth of the spread allowance (down to 1.9 x (mean + 3 sigma)) when that buys another block per SM
+            const int cap_min = std::min(cap, std::max(96, ((int)(1.9 * (a_est + 3.0 * std::sqrt(a_est))) + 31) & ~31));
+            const void *f = (const void *)k_dfs<W_, false, false>;
+            SGS_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dfs_smem_bytes<W_>(cap, opts.prune != 0) * dfs_wpb)));
+            int best_occ = 0, best_cap = cap;
+            for (int cx = cap; cx >= cap_min; cx -= 32) {
+                int o = 0;
+                SGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, f, dfs_wpb * 32, dfs_smem_bytes<W_>(cx, opts.prune != 0) * dfs_wpb));
+                if (o > best_occ) { best_occ = o; best_cap = cx; }
+            }
+            cap = best_cap;
+        }
         dfs_cap = cap;
         const size_t dfs_pw = dfs_smem_bytes<W_>(dfs_cap, opts.prune != 0);
-        int dfs_wpb = kDfsWpb;
-        while (dfs_wpb > 1 && dfs_pw * dfs_wpb > 200 * 1024) dfs_wpb >>= 1;
         // expansion-mode launch: one list per parent (a ~ ratio * depth / 2 alive terms, 5 sigma of room)
         int exp_cap = 0, exp_wpb = kDfsWpb;
         size_t exp_pw = 0;
@@ -640,7 +655,7 @@ void SparsePlan::Impl::fill_stats(const SparseStats &tot, sgs_result *out)
         out->sum_2m += (double)tot.hist[i] * std::ldexp(1.0, i);
     }
     out->slow_nodes = tot.slow_nodes;
-    for (int i = 0; i < 7; i++) out->walk_paths[i] = (uint32_t)std::min<unsigned long long>(tot.paths[i], 0xffffffffull);
+    for (int i = 0; i < 8; i++) out->walk_paths[i] = (uint32_t)std::min<unsigned long long>(tot.paths[i], 0xffffffffull);
 }
 
 // result of a shard (rank of a world without communicator) that owns no candidate: energy +inf, no generator

@@ -32,6 +32,8 @@ INSTANCES = {
     'oracle_sparse_36_140_4': (36, 140, 4),
     'oracle_sparse_40_110_5': (40, 110, 5),
     'oracle_sparse_40_200_6': (40, 200, 6),
+    'oracle_sparse_40_170_7': (40, 170, 7),     # roots of 65-96 alive terms: the three-row certificate of level B
+    'oracle_sparse_30_150_8': (30, 150, 8),
     'oracle_sparse_24_300_0': (24, 300, 0),
 }
 

@@ -25,8 +25,8 @@ ORACLE_GOLDEN = sorted(f for f in glob.glob(os.path.join(GOLDEN, 'oracle_sparse_
 CONFIG4 = os.path.join(GOLDEN, 'oracle_sparse_24_300_0.json')
 
 # accumulated over the tests of this module; asserted at the end (test_every_walk_path_was_exercised)
-PATHS = {'w1': [0] * 7, 'w2': [0] * 7}
-NAMES = ['walk32', 'walk64', 'fold_ok', 'fold_full', 'dep_certified', 'not_certified', 'level_a']
+PATHS = {'w1': [0] * 8, 'w2': [0] * 8}
+NAMES = ['walk32', 'walk64', 'fold_ok', 'fold_full', 'dep_certified', 'not_certified', 'level_a', 'wide']
 
 
 def sgs():
@@ -48,7 +48,7 @@ def _load(path):
 
 def _note(g_n, r):
     acc = PATHS['w1' if g_n <= 32 else 'w2']
-    for i in range(7):
+    for i in range(8):
         acc[i] += r['walk_paths'][i]
 
 
@@ -308,3 +308,4 @@ def test_every_walk_path_was_exercised():
     assert w2[0] > 0 and w2[1] > 0, 'W=2: both mask widths of lb_walk'
     assert w2[2] > 0, 'W=2: folded-image certificate'
     assert w1[6] > 0 and w2[6] > 0, 'level-A descent below a root'
+    assert w1[7] > 0 and w2[7] > 0, 'certified frames of 65-96 entries (three rows per lane)'
