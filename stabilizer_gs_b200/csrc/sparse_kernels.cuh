@@ -647,9 +647,54 @@ __device__ __forceinline__ bool has_duplicate_body(const uint64_t *R, int n, int
 }
 template <int W>
 __device__ __noinline__ bool has_duplicate_cold(const uint64_t *R, int n, int lane) { return has_duplicate_body<W>(R, n, lane); }
+// The same question for a list of 33..128 entries in O(n): the entries are inserted row by row (32 lanes at a time)
+// into an open-addressing table of 256 16-bit slots (tab: the edge list's shared memory, unused between walks).  No
+// atomics: the lanes that found their slot empty all write, one store lands, everyone reads back; a lane that meets
+// another entry — an earlier row's or the winner of this round — compares residues with it and probes on.  (The
+// all-pairs scheme above costs ~n^2/32 broadcast compares: 1 800 instructions at n = 125 against ~300 here.)
 template <int W>
-SGS_D bool has_duplicate(const uint64_t *R, int n, int lane)
+__device__ __noinline__ bool has_duplicate_hash(const uint64_t *R, int n, uint16_t *tab, int lane)
 {
+    for (int i = lane; i < 128; i += 32) ((uint32_t *)tab)[i] = 0;
+    __syncwarp();
+    bool dup = false;
+#pragma unroll 1
+    for (int r0 = 0; r0 < n; r0 += 32) {
+        const int i = r0 + lane;
+        bool pending = i < n;
+        uint64_t v[W];
+        uint64_t hh = 0x9E3779B97F4A7C15ULL;
+#pragma unroll
+        for (int k = 0; k < W; k++) { v[k] = pending ? R[i * W + k] : 0; hh = (hh ^ v[k]) * 0xBF58476D1CE4E5B9ULL; hh ^= hh >> 31; }
+        unsigned h = (unsigned)(hh >> 40) & 255u;
+#pragma unroll 1
+        while (__any_sync(0xffffffffu, pending)) {
+            const unsigned occ = pending ? tab[h] : 0u;
+            const bool tryw = pending && occ == 0u;
+            if (pending && occ != 0u) {                       // an entry of an earlier row (or round) sits here
+                dup |= row_equal<W>(R + (occ - 1u) * W, v);
+                h = (h + 1u) & 255u;
+            }
+            if (tryw) tab[h] = (uint16_t)(i + 1);
+            __syncwarp();
+            if (tryw) {
+                const unsigned got = tab[h];
+                if (got == (unsigned)(i + 1)) pending = false;
+                else { dup |= row_equal<W>(R + (got - 1u) * W, v); h = (h + 1u) & 255u; }
+            }
+            if (dup) pending = false;
+            __syncwarp();
+        }
+    }
+    return __any_sync(0xffffffffu, dup);
+}
+template <int W>
+SGS_D bool has_duplicate(const uint64_t *R, int n, uint16_t *tab, int lane)
+{
+#ifndef SGS_HASH_W1
+#define SGS_HASH_W1 0      // (one-word rows: the extra out-of-line call costs 3 % of config 4 through register allocation; their big lists are rare)
+#endif
+    if ((W > 1 || SGS_HASH_W1) && n > 32 && n <= 128) return has_duplicate_hash<W>(R, n, tab, lane);
     if (W == 1) return has_duplicate_body<W>(R, n, lane);
     return has_duplicate_cold<W>(R, n, lane);
 }
@@ -1410,7 +1455,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
         //  when a next round exists: level_b answers 2)
         if (!(mode & kDfsExpand) && a <= kMaxLB && a - q0 <= 64 && m0 + (a - q0) < kMaxG && run_level_b(0, a, q0, m0, E0, retry_out ? D.split_cliques : 0.f) == 1) continue;
         tfail = true;
-        if (has_duplicate<W>(R, a, lane)) {
+        if (has_duplicate<W>(R, a, EL, lane)) {
             try_best(E0, m0);
             push_slow(D, path, m0, flags | kFlagExpandOnly, lane);
             continue;
@@ -1455,9 +1500,18 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             const double Ec = E - D.wabs[TT[base + jq]];
 
             // pass 1: which list entries commute with the new generator (POPC), and is any above it?
+            // (roomy: the child list fits behind its parent whatever its length — pass 2 counts as it writes and
+            //  pass 1 is skipped; a child without extension then wrote a list for nothing, which is rare this high up)
+            const int depth = m0 + fd;                      // rank of the frame's group
+            const int cb = base + a;
+#ifndef SGS_ROOMY_W1
+#define SGS_ROOMY_W1 1
+#endif
+            const bool roomy = (W > 1 || SGS_ROOMY_W1) && a > 32 && cb + a <= cap && depth + 1 < kMaxG && fd + 1 < kMaxFramesA;
             int nal = 0, nlow = 0;
-            unsigned hiAny;
-            if (a <= 32) {
+            unsigned hiAny = 0;
+            if (roomy) {
+            } else if (a <= 32) {
                 bool com = false;
                 if (lane < a && lane != jq) com = !row_anticommute_sw<W>(R + (base + lane) * W, sw);
                 const unsigned bal = __ballot_sync(0xffffffffu, com);
@@ -1465,7 +1519,6 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                 nal = __popc(bal);
                 nlow = nal - __popc(hiAny);
             } else {
-                hiAny = 0;
 #pragma unroll 1
                 for (int r0 = 0; r0 < a; r0 += 32) {
                     const int i = r0 + lane;
@@ -1479,8 +1532,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                     nal += __popc(bal);
                 }
             }
-            const int depth = m0 + fd;                      // rank of the frame's group
-            if (hiAny == 0) {                               // the child has no extension: a leaf of the tree
+            if (!roomy && hiAny == 0) {                     // the child has no extension: a leaf of the tree
                 if (Ec <= bestE) {
                     if (lane == 0) path[depth] = TT[base + jq];
                     try_best(Ec, depth + 1);
@@ -1488,8 +1540,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                 continue;
             }
             if (lane == 0) path[depth] = TT[base + jq];
-            const int cb = base + a;
-            if (cb + nal > cap || depth + 1 >= kMaxG || fd + 1 >= kMaxFramesA) {     // out of list / frame space: the exact kernel takes over
+            if (!roomy && (cb + nal > cap || depth + 1 >= kMaxG || fd + 1 >= kMaxFramesA)) {     // out of list / frame space: the exact kernel takes over
                 __syncwarp();
                 try_best(Ec, depth + 1);
                 push_slow(D, path, depth + 1, kFlagExpandOnly, lane);
@@ -1510,6 +1561,12 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                     com = !row_anticommute_sw<W>(v, sw);
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, com);
+                if (roomy) {
+                    const int rel = jq - r0;
+                    if (rel >= 32) nlow += __popc(bal);
+                    else if (rel >= 0) { nlow += __popc(bal & ((1u << rel) - 1u)); hiAny |= (bal >> rel) >> 1; }
+                    else hiAny |= bal;
+                }
                 if (com) {
                     if (row_bit<W>(v, pv)) {
 #pragma unroll
@@ -1524,6 +1581,13 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
                 off += __popc(bal);
             }
             __syncwarp();
+            if (roomy) {
+                nal = off - cb;
+                if (hiAny == 0) {                           // (a leaf after all)
+                    try_best(Ec, depth + 1);
+                    continue;
+                }
+            }
             if (PRUNE) {
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, d);
@@ -1532,7 +1596,7 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             if (nal <= kMaxLB && nal - nlow <= 64 && depth + 1 + (nal - nlow) < kMaxG && run_level_b(cb, nal, nlow, depth + 1, Ec, 0.f) == 1) continue;
             // residues pairwise distinct ⇒ every child of this child is a new group whose only members
             // are its generators.  Otherwise the exact kernel expands it.
-            if (has_duplicate<W>(R + cb * W, nal, lane)) {
+            if (has_duplicate<W>(R + cb * W, nal, EL, lane)) {
                 try_best(Ec, depth + 1);
                 push_slow(D, path, depth + 1, kFlagExpandOnly, lane);
                 continue;
