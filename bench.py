@@ -212,12 +212,15 @@ def roofline_block(workload, hot_s_per_step, world, peaks, rank_hist, T, n):
                                 'the kernel evaluates candidates incrementally, so this exceeds 1 and is not a utilisation')
     if ctr:
         # all shards together execute the same instructions as one (the tree is partitioned, the top is KBs)
-        alu_lane_ops = ctr['inst_executed_pipe_alu'] * 32.0
+        # (a capture of one virtual shard of the workload — instance_scale = its share of the candidates — stands
+        #  for the whole launch: counts divided by the share)
+        share = float(ctr['instance_scale']) if ctr.get('instance_scale') else 1.0
+        alu_lane_ops = ctr['inst_executed_pipe_alu'] * 32.0 / share
         achieved = alu_lane_ops / hot_s_per_step
         blk.update(achieved=achieved / 1e12, frac=achieved / peak,
                    frac_lane_weighted=achieved / peak * ctr['thread_inst_executed'] / (32.0 * ctr['inst_executed']),
-                   issue_slot_frac=ctr['inst_executed'] / hot_s_per_step / (peak / 32.0 * 2.0),
-                   traffic=ctr.get('dram_bytes'), source=src, counters=ctr,
+                   issue_slot_frac=ctr['inst_executed'] / share / hot_s_per_step / (peak / 32.0 * 2.0),
+                   traffic=(ctr['dram_bytes'] / share if ctr.get('dram_bytes') is not None else None), source=src, counters=ctr,
                    note='achieved = executed ALU-pipe warp instructions of one k_dfs launch (ncu, this build and workload) x 32 '
                         'lanes / live CUDA-event time of the kernel; frac = achieved / peak = the ALU-pipe utilisation; '
                         'traffic = dram read+write bytes of the same launch (the tables are KBs and L2-resident: the bound is '
