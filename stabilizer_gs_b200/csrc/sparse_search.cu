@@ -99,6 +99,7 @@ struct SparsePlan::Impl {
         int exp_cap = 0, exp_wpb = 4;
         size_t exp_pw = 0;
         unsigned exp_grid = 0;
+        unsigned long long roots_per_shard = 0;      // the walk's proxy for its own length (hand-off rounds or not): same in both launch sequences
     } rp;
 
     ~Impl();
@@ -407,10 +408,11 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
     gen_occ = std::max(1, gen_occ);
     const unsigned gen_maxgrid = (unsigned)std::min<long long>((long long)c.sms * gen_occ, c.nwbest / gen_wpb);
     auto launch_general = [&](const uint16_t *in, unsigned nin, uint16_t *out, unsigned *out_count, unsigned out_cap,
-                              int shard, int nsh) {
+                              int shard, int nsh, int own_only = 0) {
         unsigned grid = std::min<unsigned>((nin + gen_wpb - 1) / gen_wpb, gen_maxgrid);
         if (grid == 0) return;
-        k_general<W_><<<grid, gen_wpb * 32, gen_pw * gen_wpb, st>>>(D, in, nin, out, out_count, out_cap, shard, nsh, (int)gen_pw, 0, nullptr);
+        k_general<W_><<<grid, gen_wpb * 32, gen_pw * gen_wpb, st>>>(D, in, nin, out, out_count, out_cap, shard, nsh, (int)gen_pw, own_only,
+                                                                    own_only ? c.counters + 3 : nullptr);
         c.launches++;
     };
 
@@ -430,7 +432,12 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
     c.had_slow = false;
     bool dfs_expand = false;
     double ratio_pred = 0.0;
-    while (count > 0 && depth < dmax) {
+    // sharded: the last level was expanded by the owner of each parent only (as the recorded launch sequence does): this
+    // shard's queue then holds its own roots and nothing else, the walk needs no filter.  The level is chosen by
+    // predicting that it will be the last one (clique-like growth); a prediction that turns out wrong in either
+    // direction costs time, never the partition — a root belongs to the shard of its parent's tuple in every case.
+    bool sharded = false;
+    while (count > 0 && depth < dmax && !sharded) {
         if (opts.expand_depth <= 0) {
             const double est_alive = ratio * std::max(depth, 1) / 2.0;
             if (depth > 0 && count >= min_items && est_alive <= 64.0) break;
@@ -460,15 +467,23 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
             SGS_CUDA_TRY(cudaStreamSynchronize(st));
             if (hcnt[0] > qcap) break;
         }
+        bool own = false;
+        if (nshards > 1 && depth >= 1 && !getenv("SGS_NO_OWN_LEVEL")) {
+            const double predicted = (double)count * ratio * depth / (2.0 * (depth + 1));
+            const double ratio_next = predicted / (double)count;
+            own = opts.expand_depth > 0 ? depth == dmax - 1 : (predicted >= (double)min_items && ratio_next * (depth + 1) / 2.0 <= 64.0);
+        }
         SGS_CUDA_TRY(cudaMemsetAsync(c.counters, 0, sizeof(unsigned), st));
-        launch_general(cur, count, nxt, c.counters, qcap, c.shard, nshards);
+        if (own) SGS_CUDA_TRY(cudaMemsetAsync(c.counters + 3, 0, sizeof(unsigned), st));
+        launch_general(cur, count, nxt, c.counters, qcap, c.shard, nshards, own ? 1 : 0);
         SGS_CUDA_TRY(cudaGetLastError());
         SGS_CUDA_TRY(cudaMemcpyAsync(hcnt, c.counters, sizeof(hcnt), cudaMemcpyDeviceToHost, st));
         SGS_CUDA_TRY(cudaMemcpyAsync(&hs, c.stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
         SGS_CUDA_TRY(cudaStreamSynchronize(st));
         if (hs.error) return Status::fail(hs.error == kErrOverflow ? SGS_ERR_OVERFLOW : SGS_ERR_LIMIT,
                                           "sparse search: device limit hit while expanding the tree (queue overflow or rank/table limit)");
-        ratio = std::max(1.0, (double)hcnt[0] / (double)count);
+        sharded = own;
+        ratio = std::max(1.0, (double)hcnt[0] * (own ? nshards : 1) / (double)count);
         if (D.trace) fprintf(stderr, "sparse shard %d: level %d -> %u nodes\n", c.shard, depth + 1, hcnt[0]);
         count = hcnt[0];
         level_counts.push_back(count);
@@ -563,9 +578,10 @@ Status SparsePlan::Impl::search_local(DevCtx &c)
             k_class_scatter<<<cg, 256, 0, st>>>(cur, cnt_host, cnt_dev, S, T, c.counters + 8, c.counters + 16, c.perm);
             c.launches += 2;
         }
-        Status sd = launch_dfs<W_>(c, D, grid, dfs_wpb, dfs_pw, dfs_cap, cur, cnt_host, dfs_expand ? 1 : nshards, cnt_dev,
-                                   use_perm ? c.perm : nullptr, dfs_expand ? c.counters + 5 : nullptr,
-                                   (unsigned long long)count * (dfs_expand ? 8u : 1u) / (unsigned)nshards);
+        const unsigned long long rps = sharded ? (unsigned long long)count : (unsigned long long)count * (dfs_expand ? 8u : 1u) / (unsigned)nshards;
+        if (&c == &devs[0]) rp.roots_per_shard = rps;
+        Status sd = launch_dfs<W_>(c, D, grid, dfs_wpb, dfs_pw, dfs_cap, cur, cnt_host, (dfs_expand || sharded) ? 1 : nshards, cnt_dev,
+                                   use_perm ? c.perm : nullptr, dfs_expand ? c.counters + 5 : nullptr, rps);
         if (!sd.ok()) return sd;
         SGS_CUDA_TRY(cudaGetLastError());
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
@@ -706,7 +722,8 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         }
         const bool dev_count = rp.dfs_expand || (nshards > 1 && rp.depth > 0);      // queue length only known on the device
         const unsigned *ndev = rp.dfs_expand ? c.counters + 4 : (dev_count ? c.counters : nullptr);
-        const unsigned nroots = rp.dfs_expand ? qcap : rp.counts[rp.depth];
+        // (device-side count: the recorded number is only this plan's first shard's — the host bound is the queue capacity)
+        const unsigned nroots = (rp.dfs_expand || dev_count) ? qcap : rp.counts[rp.depth];
         const bool use_perm = !getenv("SGS_NOPERM");
         if (use_perm) {
             const unsigned cnt = nroots;
@@ -720,8 +737,7 @@ Status SparsePlan::Impl::run_replay(sgs_result *out)
         // with a parent-sharded last level the queue length is only known on the device: counters[0]
         {
             Status sd = launch_dfs<W_>(c, D, rp.dfs_grid, rp.dfs_wpb, rp.dfs_pw, rp.dfs_cap, cur, nroots, dev_count ? 1 : nshards, ndev,
-                                       use_perm ? c.perm : nullptr, rp.dfs_expand ? c.counters + 5 : nullptr,
-                                       (unsigned long long)rp.counts[rp.depth] * (rp.dfs_expand ? 8u : 1u) / (unsigned)nshards);
+                                       use_perm ? c.perm : nullptr, rp.dfs_expand ? c.counters + 5 : nullptr, rp.roots_per_shard);
             if (!sd.ok()) return sd;
         }
         SGS_CUDA_TRY(cudaEventRecord(c.evh1, st));
