@@ -34,6 +34,7 @@ INSTANCES = {
     'oracle_sparse_40_200_6': (40, 200, 6),
     'oracle_sparse_40_170_7': (40, 170, 7),     # roots of 65-96 alive terms: the three-row certificate of level B
     'oracle_sparse_30_150_8': (30, 150, 8),
+    'oracle_sparse_40_260_9': (40, 260, 9),     # config 5's shape at expand_depth 1: roots of ~130 alive terms (level A), children of ~65 (three-row level B)
     'oracle_sparse_24_300_0': (24, 300, 0),
 }
 

@@ -71,6 +71,18 @@ def test_midsize_vs_oracle_golden(path, depth):
     _note(g['n'], r)
 
 
+def test_config5_shape_vs_oracle_golden():
+    """n=40, T=260 with the roots at depth 1 has the shape of config 5 below its roots — lists of ~130 alive terms that
+    only the warp-cooperative level A can take, children of ~65 that level B certifies with three rows per lane and walks
+    with 64-bit masks — at a size the CPU oracle enumerates (36 175 733 candidates, 102 s on 8 cores)."""
+    S = sgs()
+    g, text, ref = _load(os.path.join(GOLDEN, 'oracle_sparse_40_260_9.json'))
+    r = S.sparse_search(S.HamHandle.from_text(text), expand_depth=1)
+    check_same(r, ref)
+    wp = r['walk_paths']
+    assert wp[6] > 0 and wp[7] > 0 and wp[1] > 0 and wp[2] > 0, wp      # level A, > 64 entries, 64-bit walk, folded certificate
+
+
 @pytest.mark.parametrize('n,T,seed', [(28, 150, 11), (40, 160, 12)])
 def test_midsize_vs_live_oracle(n, T, seed):
     """the same comparison against the oracle run now (not a stored vector)"""
