@@ -313,7 +313,7 @@ Status SparsePlan::Impl::init_device(DevCtx &c)
 
 // The walk below the subtree roots.  With several shards the walk is short, so a root that cannot be certified
 // at once (a commuting dependency below it) would pin one warp for most of the kernel: such roots hand their
-// children to a second round, and those of the second round to a third (counts stay on the device).
+// children to a second launch (counts stay on the device).
 template <int W_>
 Status SparsePlan::Impl::launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid, int wpb, size_t pw, int cap, const uint16_t *items,
                                     unsigned count, int nsh, const unsigned *count_dev, const unsigned *perm, const unsigned *valid0,
@@ -336,16 +336,26 @@ Status SparsePlan::Impl::launch_dfs(DevCtx &c, const SparseDev &D, unsigned grid
     const bool prune = opts.prune != 0;
 #define SGS_DFS(SPL, PRN, ...) k_dfs<W_, SPL, PRN><<<grid, wpb * 32, pw * wpb, st>>>(__VA_ARGS__)
     if (split) {
+        // one hand-off round: the second launch walks whatever it meets itself (a child of an uncertifiable root that
+        // is uncertifiable again has ~25 alive terms: a third, nearly empty launch cost more than it saved — config 4 at 8
+        // shards 0.395 -> 0.364 ms; SGS_ROUNDS=3 brings the third launch back for A/B runs)
+        const bool two = !(getenv("SGS_ROUNDS") && atoi(getenv("SGS_ROUNDS")) == 3);
         if (prune) {
             SGS_DFS(true, true, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc, retry_cap, valid0, 0);
-            SGS_DFS(true, true, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap, rc + 1, 0);
-            SGS_DFS(false, true, D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3, 0);
+            if (two) SGS_DFS(false, true, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, nullptr, nullptr, 0, rc + 1, 0);
+            else {
+                SGS_DFS(true, true, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap, rc + 1, 0);
+                SGS_DFS(false, true, D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3, 0);
+            }
         } else {
             SGS_DFS(true, false, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, c.retry[0], rc, retry_cap, valid0, 0);
-            SGS_DFS(true, false, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap, rc + 1, 0);
-            SGS_DFS(false, false, D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3, 0);
+            if (two) SGS_DFS(false, false, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, nullptr, nullptr, 0, rc + 1, 0);
+            else {
+                SGS_DFS(true, false, D, c.retry[0], retry_cap, rc + 4, 0, 1, cap, (int)pw, rc, nullptr, c.retry[1], rc + 2, retry_cap, rc + 1, 0);
+                SGS_DFS(false, false, D, c.retry[1], retry_cap, rc + 5, 0, 1, cap, (int)pw, rc + 2, nullptr, nullptr, nullptr, 0, rc + 3, 0);
+            }
         }
-        c.launches += 3;
+        c.launches += two ? 2 : 3;
     } else {
         if (prune) SGS_DFS(false, true, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, valid0, 0);
         else SGS_DFS(false, false, D, items, count, c.counters + 1, c.shard, nsh, cap, (int)pw, count_dev, perm, nullptr, rc, 0, valid0, 0);
