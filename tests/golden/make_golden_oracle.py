@@ -34,6 +34,8 @@ INSTANCES = {
     'oracle_sparse_40_200_6': (40, 200, 6),
     'oracle_sparse_40_170_7': (40, 170, 7),     # roots of 65-96 alive terms: the three-row certificate of level B
     'oracle_sparse_30_150_8': (30, 150, 8),
+    'oracle_sparse_70_150_10': (70, 150, 10),   # four-word rows (n > 64) at a size where level A / the wide level B / the hashed duplicate check run
+    'oracle_sparse_100_200_11': (100, 200, 11),
     'oracle_sparse_40_260_9': (40, 260, 9),     # config 5's shape at expand_depth 1: roots of ~130 alive terms (level A), children of ~65 (three-row level B)
     'oracle_sparse_24_300_0': (24, 300, 0),
 }
