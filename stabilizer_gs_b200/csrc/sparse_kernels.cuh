@@ -24,10 +24,10 @@
 //                 generator's residue at its pivot bit, __ballot_sync compaction, __match_any_sync
 //                 duplicate-residue detection.  While residues stay pairwise distinct no term outside
 //                 the generating set can enter the group, so E_min = -sum |w_g| exactly; the first
-//                 duplicate hands that node to k_general.  Once a list has <= 64 entries the warp proves by
-//                 Gaussian elimination that no dependent term can appear anywhere below it (level_b); the
-//                 subtree is then the set of cliques of the candidates' commutation graph, walked by the
-//                 lanes independently with bit masks (lb_walk).  Template flags: SPLIT (multi-shard runs:
+//                 duplicate hands that node to k_general.  Once a list has <= 96 entries, <= 64 of them
+//                 candidates, the warp proves by Gaussian elimination that no dependent term can appear anywhere
+//                 below it (level_b); the subtree is then the set of cliques of the candidates' commutation
+//                 graph, walked by the lanes independently with bit masks (lb_walk_edges).  Template flags: SPLIT (multi-shard runs:
 //                 heavy or uncertifiable roots hand their children to a next round), PRUNE (optional
 //                 branch and bound against a device-wide incumbent).
 //   k_class_count / k_class_scatter : heavy-first order of the subtree roots (multi-shard runs).
@@ -700,15 +700,15 @@ SGS_D bool has_duplicate(const uint64_t *R, int n, uint16_t *tab, int lane)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Level B of the walk: a frame (compacted list of the n <= 64 terms still commuting with the group, their
+// Level B of the walk: a frame (compacted list of the n <= kMaxLB terms still commuting with the group, their
 // residues mod the group) whose residues are LINEARLY INDEPENDENT over GF(2) cannot produce a dependent
 // term anywhere below it: no alive term can fall into a descendant group and no two can merge into one
 // coset.  Every descendant is then "group + a clique of the commutation graph of the list", its members are
 // exactly its generators and E_min = E_frame - sum |w|.  The warp (1) certifies independence by Gaussian
 // elimination across lanes (pivot row broadcast with shuffles, lowest-set-bit pivot, XOR elimination),
-// (2) builds the list's commutation bit-matrix with POPC + __ballot_sync, then (3) every lane walks the
-// cliques that start at "its" vertices privately with 64-bit masks.
-// Returns false (nothing counted) if the residues are dependent.
+// (2) builds the candidates' commutation bit-matrix with POPC, then (3) the lanes walk the cliques privately with
+// 32- or 64-bit masks, work items dealt from a shared list.  (In its final form the certificate is taken over
+// the candidates only, see level_b.)  Returns 0 (nothing counted) if the frame cannot be certified.
 constexpr int kMaxLB = 96;          // entries of a level-B frame (three rows per lane); its candidates: <= 64 (the walk's mask width)
 constexpr int kFoldCand = 52;       // multi-word rows: the 64-bit image is tried up to this many candidates (it fails with probability ~ entries * 2^(candidates - 64))
 constexpr int kMaxDep = 6;
