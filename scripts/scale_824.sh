@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
-for n in 8 2 4; do
+for n in ${SCALE_NS:-8 2 4}; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 3 2> gpurun_out/r2w_n$n.err | tail -1 > gpurun_out/r2w_n$n.json; echo "n$n rc=$?"
   python - <<PY
 import json
