@@ -1362,7 +1362,9 @@ k_dfs(SparseDev D, const uint16_t *__restrict__ items, unsigned nitems, unsigned
             troot = tn; tfail = false; tinfo = 0;
         }
         if (it >= nitems) break;
-        if (*(volatile unsigned int *)&D.stats->error) break;      // a limit was hit somewhere: the search is void, stop early
+        // (a limit was hit somewhere: the search is void, stop early — polled every 16th root: the flag is an L2 round trip
+        //  in front of every root's dependent loads)
+        if ((it & 15u) == 0 && *(volatile unsigned int *)&D.stats->error) break;
         if (PRUNE) thr = fmin(prune_threshold(bestE), prune_threshold(dec_double(*(volatile unsigned long long *)D.inc)));
         const uint16_t *rec = items + (size_t)(perm ? perm[it] : it) * D.S;
         const int m0 = rec[0];
